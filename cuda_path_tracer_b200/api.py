@@ -1,0 +1,249 @@
+"""Python mirror of the reference's integrator interface — class PathTracer
+(src/lib/path_tracer.hpp:60-99) — over the C ABI in include/b200pt.h.
+
+Names, argument meaning and defaults follow the reference so the parity tests read
+like tests of the reference: create_buffers / resize_image / path_trace / denoise /
+send_to_preview / restart / iteration(), fields max_iterations, current_gpu_method,
+atrous_denoiser.{filter_size,color_weight,normal_weight,position_weight}.
+Everything that touches rays or pixels runs in libb200pt.so on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _abi
+from ._abi import check, load_library
+from .scene_description import Camera, SceneDescription
+
+
+class GPUMethod:
+    """GPUMethod (path_tracer.hpp:58).  Both run on the same wavefront kernels; the
+    value selects which of the reference's two RNG disciplines is reproduced."""
+    megakernel = _abi.RNG_PIXEL_STREAM
+    streaming = _abi.RNG_SLOT_RESEED
+
+
+class DisplayBufferType:
+    final, color, normal, depth, denoised = 0, 1, 2, 3, 4
+
+
+@dataclass
+class EdgeAvoidingATrousDenoiser:
+    """denoising/edge_avoiding_a_trous_denoiser.hpp:7-22"""
+    filter_size: int = 10
+    color_weight: float = 0.45
+    normal_weight: float = 0.30
+    position_weight: float = 0.25
+    clamp_fix: bool = False
+
+
+class Scene:
+    """Device-resident scene == Scene/Aggregate (scene.hpp:23-67) after build_scene()."""
+
+    def __init__(self, handle, file_info=None):
+        self._h = handle
+        self.file_info = file_info
+
+    @staticmethod
+    def from_description(desc: SceneDescription, device: int = 0) -> "Scene":
+        lib = load_library()
+        d, keep = desc.to_desc()
+        h = C.c_void_p()
+        check(lib.pt_scene_create(C.byref(d), device, C.byref(h)))
+        del keep
+        return Scene(h)
+
+    @staticmethod
+    def from_file(json_path: str, device: int = 0) -> "Scene":
+        """read_scene (assets/scene_parser.cpp:6-22)."""
+        lib = load_library()
+        h = C.c_void_p()
+        info = _abi.pt_scene_file_info()
+        check(lib.pt_scene_load_file(json_path.encode(), device, C.byref(h), C.byref(info)))
+        return Scene(h, info)
+
+    @property
+    def info(self) -> _abi.pt_scene_info:
+        i = _abi.pt_scene_info()
+        check(load_library().pt_scene_get_info(self._h, C.byref(i)))
+        return i
+
+    def trace_batch(self, rays8: np.ndarray) -> np.ndarray:
+        """Closest hits of n rays {o, t_min, d, t_max} -> structured array of pt_hit."""
+        rays = np.ascontiguousarray(rays8, dtype=np.float32).reshape(-1, 8)
+        out = np.zeros(rays.shape[0], dtype=HIT_DTYPE)
+        check(load_library().pt_trace_batch(self._h, rays.ctypes.data, rays.shape[0], out.ctypes.data))
+        return out
+
+    def close(self):
+        if self._h:
+            load_library().pt_scene_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+HIT_DTYPE = np.dtype([("t", "<f4"), ("point", "<f4", 3), ("normal", "<f4", 3), ("material", "<u4"),
+                      ("side", "<u4"), ("object", "<i4"), ("prim", "<i4"), ("pad", "<u4")])
+assert HIT_DTYPE.itemsize == C.sizeof(_abi.pt_hit)
+
+
+class PathTracer:
+    def __init__(self, max_depth: int = 50, samples_per_pass: int = 0, profile: bool = False,
+                 stream: int | None = None):
+        self.max_iterations = 1
+        self.current_gpu_method = GPUMethod.megakernel
+        self.atrous_denoiser = EdgeAvoidingATrousDenoiser()
+        self.max_depth = max_depth
+        self.samples_per_pass = samples_per_pass
+        self.profile = profile
+        self._stream = stream
+        self._ctx = None
+        self._scene = None
+        self._res = (0, 0)
+
+    # -- PathTracer::create_buffers (path_tracer.cu:559-564)
+    def create_buffers(self, resolution, scene):
+        lib = load_library()
+        if isinstance(scene, SceneDescription):
+            scene = Scene.from_description(scene)
+        self._destroy_ctx()
+        self._scene = scene
+        p = _abi.pt_params()
+        lib.pt_params_default(C.byref(p))
+        p.max_depth = self.max_depth
+        p.rng_mode = self.current_gpu_method
+        p.samples_per_pass = self.samples_per_pass
+        p.profile = 1 if self.profile else 0
+        h = C.c_void_p()
+        w, hh = int(resolution[0]), int(resolution[1])
+        check(lib.pt_ctx_create(scene._h, w, hh, C.byref(p), C.c_void_p(self._stream or 0), C.byref(h)))
+        self._ctx = h
+        self._res = (w, hh)
+
+    # -- PathTracer::resize_image (path_tracer.cu:527-545)
+    def resize_image(self, resolution):
+        check(load_library().pt_ctx_resize(self._ctx, int(resolution[0]), int(resolution[1])))
+        self._res = (int(resolution[0]), int(resolution[1]))
+
+    # -- PathTracer::restart / iteration
+    def restart(self):
+        check(load_library().pt_ctx_restart(self._ctx))
+
+    def iteration(self) -> int:
+        return load_library().pt_ctx_iteration(self._ctx)
+
+    # -- PathTracer::path_trace (path_tracer.cu:389-477): one spp per call, no-op at max_iterations
+    def path_trace(self, camera: Camera, resolution=None):
+        lib = load_library()
+        check(lib.pt_ctx_set_max_iterations(self._ctx, int(self.max_iterations)))
+        cam = camera.to_c()
+        check(lib.pt_path_trace(self._ctx, C.byref(cam)))
+
+    def render(self, camera: Camera, n_iterations: int):
+        """The CLI loop `for i < spp: path_trace` (cli.cpp:96-99) as one batched call."""
+        lib = load_library()
+        check(lib.pt_ctx_set_max_iterations(self._ctx, int(self.max_iterations)))
+        cam = camera.to_c()
+        check(lib.pt_render(self._ctx, C.byref(cam), int(n_iterations)))
+
+    def render_range(self, camera: Camera, first_iteration: int, n_iterations: int):
+        cam = camera.to_c()
+        check(load_library().pt_render_range(self._ctx, C.byref(cam), int(first_iteration), int(n_iterations)))
+
+    def synchronize(self):
+        check(load_library().pt_sync(self._ctx))
+
+    # -- PathTracer::denoise (path_tracer.cu:479-485)
+    def denoise(self, resolution=None):
+        d = self.atrous_denoiser
+        p = _abi.pt_denoise_params()
+        load_library().pt_denoise_params_default(C.byref(p))
+        p.filter_size = int(d.filter_size)
+        p.color_weight = float(d.color_weight)
+        p.normal_weight = float(d.normal_weight)
+        p.position_weight = float(d.position_weight)
+        p.clamp_fix = 1 if d.clamp_fix else 0
+        check(load_library().pt_denoise(self._ctx, C.byref(p)))
+
+    # -- PathTracer::send_to_preview (path_tracer.cu:487-520)
+    def send_to_preview(self, dev_pbo=None, resolution=None, type: int = DisplayBufferType.final):
+        """Tonemap into an RGBA8 image.  dev_pbo: device pointer (int) or None -> numpy [H,W,4]."""
+        lib = load_library()
+        w, h = self._res
+        if dev_pbo is not None:
+            check(lib.pt_resolve_rgba8(self._ctx, int(type), C.c_void_p(int(dev_pbo)), 1))
+            return None
+        out = np.empty((h, w, 4), dtype=np.uint8)
+        check(lib.pt_resolve_rgba8(self._ctx, int(type), out.ctypes.data, 0))
+        return out
+
+    def download(self, type: int) -> np.ndarray:
+        """Raw float means of a frame buffer: [H,W,3], or [H,W] for depth."""
+        w, h = self._res
+        out = np.empty((h, w) if type == DisplayBufferType.depth else (h, w, 3), dtype=np.float32)
+        check(load_library().pt_download_f32(self._ctx, int(type), out.ctypes.data))
+        return out
+
+    def upload_frame(self, color, normal, depth, camera: Camera):
+        c = np.ascontiguousarray(color, dtype=np.float32)
+        n = np.ascontiguousarray(normal, dtype=np.float32)
+        d = np.ascontiguousarray(depth, dtype=np.float32)
+        cam = camera.to_c()
+        check(load_library().pt_ctx_upload_frame(self._ctx, c.ctypes.data, n.ctypes.data, d.ctypes.data,
+                                                 C.byref(cam)))
+
+    def sums_ptr(self):
+        p = C.c_void_p()
+        n = C.c_uint64()
+        check(load_library().pt_ctx_sums(self._ctx, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def set_sample_count(self, n: int):
+        check(load_library().pt_ctx_set_sample_count(self._ctx, int(n)))
+
+    def set_stream(self, stream: int | None):
+        check(load_library().pt_ctx_set_stream(self._ctx, C.c_void_p(stream or 0)))
+
+    def stats(self) -> _abi.pt_stats:
+        s = _abi.pt_stats()
+        check(load_library().pt_get_stats(self._ctx, C.byref(s)))
+        return s
+
+    def reset_stats(self):
+        check(load_library().pt_reset_stats(self._ctx))
+
+    def _destroy_ctx(self):
+        if self._ctx:
+            load_library().pt_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def close(self):
+        self._destroy_ctx()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def write_image_file(filename: str, rgba: np.ndarray):
+    """write_image_file (src/lib/image.cpp:9-22)."""
+    img = np.ascontiguousarray(rgba, dtype=np.uint8)
+    h, w = img.shape[:2]
+    check(load_library().pt_write_png_rgba8(filename.encode(), img.ctypes.data, w, h))
+
+
+def cli_main(argv: list[str]) -> int:
+    """`cuda_pt [options] <filename>` (src/main.cpp, src/cli/cli.cpp)."""
+    args = [b"cuda_pt"] + [a.encode() for a in argv]
+    arr = (C.c_char_p * len(args))(*args)
+    return int(load_library().pt_cli_main(len(args), arr))

@@ -1,0 +1,32 @@
+// bvh_build.h — host BVH builder + flattener (replaces the reference's
+// bvh_from_mesh, src/lib/accelerators/bvh.cpp:211-253).
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace pt {
+
+// One world-space triangle (instance already applied).
+struct BuildTri {
+  float v0[3], v1[3], v2[3];
+  uint32_t prim;     // triangle index in the input index buffer / 3
+  uint32_t object;   // scene object index
+  uint32_t material; // material-table index of that object
+};
+
+struct FlatBVH {
+  std::vector<float> nodes; // 16 floats per node  (layout: common.cuh)
+  std::vector<float> tris;  // 12 floats per triangle, leaf order
+  uint32_t n_nodes = 0;
+  uint32_t n_tris = 0; // including the trailing null triangle, if any
+  uint32_t depth = 0;
+  double sah_cost = 0.0;
+};
+
+// Binned-SAH (16 bins x 3 axes) top-down build, <= 4 triangles per leaf,
+// OpenMP task-parallel; depth is bounded so the 64-entry traversal stack of
+// the extend kernel can never overflow (the reference's 24-entry stack is
+// unchecked, src/lib/static_stack.hpp:21-25).
+void build_bvh(const std::vector<BuildTri>& tris, FlatBVH& out);
+
+} // namespace pt

@@ -1,0 +1,186 @@
+// common.cuh — device-side data model of the B200 wavefront path tracer.
+//
+// Behavioural spec followed here (reference = LesleyLai/cuda-path-tracer):
+//   RNG         src/lib/hash.cuh:4-14 + thrust minstd_rand / uniform_real_distribution
+//   camera      src/lib/ray_gen.cu:34-61, src/lib/camera.cpp:5-13
+//   Ray         src/lib/ray.hpp:8-20  (origin, t_min, direction, t_max == two float4)
+// Nothing in this file is shared with the reference's sources; the layouts are
+// float4-packed SoA so that every path-state access is one 16-byte load/store.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#define PT_HD __host__ __device__ __forceinline__
+#define PT_D __device__ __forceinline__
+
+namespace pt {
+
+// ---------------------------------------------------------------- float3 math
+struct f3 {
+  float x, y, z;
+};
+PT_HD f3 mk3(float x, float y, float z) { return f3{x, y, z}; }
+PT_HD f3 operator+(f3 a, f3 b) { return f3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+PT_HD f3 operator-(f3 a, f3 b) { return f3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+PT_HD f3 operator-(f3 a) { return f3{-a.x, -a.y, -a.z}; }
+PT_HD f3 operator*(f3 a, f3 b) { return f3{a.x * b.x, a.y * b.y, a.z * b.z}; }
+PT_HD f3 operator*(f3 a, float s) { return f3{a.x * s, a.y * s, a.z * s}; }
+PT_HD f3 operator*(float s, f3 a) { return f3{a.x * s, a.y * s, a.z * s}; }
+PT_HD f3 operator/(f3 a, float s) { return f3{a.x / s, a.y / s, a.z / s}; }
+// glm::dot(vec3): (x*x' + y*y') + z*z'
+PT_HD float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+PT_HD f3 cross3(f3 a, f3 b)
+{
+  return f3{a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y};
+}
+// glm::normalize(v) = v * inversesqrt(dot(v,v)), inversesqrt(x) = 1/sqrt(x)
+PT_HD f3 normalize3(f3 v) { return v * (1.0f / sqrtf(dot3(v, v))); }
+PT_HD float length3(f3 v) { return sqrtf(dot3(v, v)); }
+
+// ---------------------------------------------------------------------- RNG
+// Wang-style integer hash, the seed function of the reference (hash.cuh:4-14).
+PT_HD uint32_t wang_hash(uint32_t a)
+{
+  a = (a + 0x7ed55d16u) + (a << 12);
+  a = (a ^ 0xc761c23cu) ^ (a >> 19);
+  a = (a + 0x165667b1u) + (a << 5);
+  a = (a + 0xd3a2646cu) ^ (a << 9);
+  a = (a + 0xfd7046c5u) + (a << 3);
+  a = (a ^ 0xb55a4f09u) ^ (a >> 16);
+  return a;
+}
+
+// thrust::default_random_engine == minstd_rand: x <- 48271 x mod (2^31 - 1).
+// seed(s): x = s mod m, 0 -> 1 (linear_congruential_engine.inl:45-55).
+PT_HD uint32_t minstd_seed(uint32_t s)
+{
+  uint32_t x = s % 2147483647u;
+  return x == 0u ? 1u : x;
+}
+PT_HD uint32_t minstd_next(uint32_t x)
+{
+  return (uint32_t)(((uint64_t)x * 48271ull) % 2147483647ull);
+}
+// thrust::uniform_real_distribution<float>(0,1): float(x - min) / (1 + float(max - min))
+// with min = 1, max = 2^31 - 2  ->  float(x - 1) / 2147483648.f
+PT_HD float minstd_uniform(uint32_t& x)
+{
+  x = minstd_next(x);
+  return (float)(x - 1u) / 2147483648.0f;
+}
+// x * a^n mod m by squaring == engine.discard(n)
+PT_HD uint32_t minstd_discard(uint32_t x, uint32_t n)
+{
+  uint64_t a = 48271ull, r = x;
+  while (n) {
+    if (n & 1u) r = (r * a) % 2147483647ull;
+    a = (a * a) % 2147483647ull;
+    n >>= 1;
+  }
+  return (uint32_t)r;
+}
+
+// ------------------------------------------------------------------- camera
+// Precomputed form of GPUCamera (camera.hpp:10-15) as a kernel parameter; one
+// per launch, no __constant__ state shared between contexts.
+struct DevCamera {
+  float m[12];      // camera_matrix columns 0..2 (xyz each), then column 3 xyz = origin
+  float vp_w, vp_h; // viewport_width, viewport_height (focal length 1)
+  float fw_m1;      // float(W-1)
+  float fh_m1;      // float(H-1)
+  float fh;         // float(H)
+  uint32_t width, height;
+};
+
+// generate_ray (ray_gen.cu:34-61). x,y are continuous pixel coordinates.
+PT_HD void camera_ray(const DevCamera& c, float x, float y, f3& o, f3& d)
+{
+  const float u = x / c.fw_m1;
+  const float v = (c.fh - y) / c.fh_m1;
+  // lower_left_corner + u*horizontal + v*vertical - origin (zero terms are exact)
+  const float lx = -(c.vp_w / 2.0f) + u * c.vp_w;
+  const float ly = -(c.vp_h / 2.0f) + v * c.vp_h;
+  const float lz = -1.0f;
+  o = mk3(c.m[9], c.m[10], c.m[11]);
+  // glm mat4*vec4 association: (m0*v0 + m1*v1) + (m2*v2 + m3*v3), v3 = 0
+  f3 w;
+  w.x = (c.m[0] * lx + c.m[3] * ly) + (c.m[6] * lz);
+  w.y = (c.m[1] * lx + c.m[4] * ly) + (c.m[7] * lz);
+  w.z = (c.m[2] * lx + c.m[5] * ly) + (c.m[8] * lz);
+  d = normalize3(w);
+}
+
+// ------------------------------------------------------------ device scene
+// World-space, instance-baked triangle: 48 B = three float4; leaves are
+// contiguous runs of up to PT_LEAF_MAX triangles.
+//   t0 = (v0.xyz, bits(triangle index in the input index buffer / 3))
+//   t1 = (e1.xyz, bits(object index))       e1 = v1 - v0
+//   t2 = (e2.xyz, bits(material index))     e2 = v2 - v0
+//
+// BVH2 node, 64 B (half a 128-B line), children's boxes stored in the parent:
+//   n0 = (c0.min.x, c0.max.x, c0.min.y, c0.max.y)
+//   n1 = (c1.min.x, c1.max.x, c1.min.y, c1.max.y)
+//   n2 = (c0.min.z, c0.max.z, c1.min.z, c1.max.z)
+//   n3 = bits(child0, child1, -, -);  child >= 0: inner node index
+//        child < 0: leaf, ~child = (first_triangle << 3) | (count - 1)
+#define PT_LEAF_MAX 4
+#define PT_STACK 64
+#define PT_SENTINEL 0x7fffffff
+
+// Sphere object, replicating ray_object_intersection_test's sphere branch
+// (path_tracer.cu:87-98): world->object rows, object->world rows (affine).
+struct DevSphere {
+  float inv[12]; // row-major 3x4 of world->object
+  float m[12];   // row-major 3x4 of object->world
+  float cx, cy, cz, radius;
+  uint32_t material;
+  int32_t object;
+  uint32_t pad[2];
+};
+
+struct DevMaterial {
+  float r, g, b; // albedo
+  float param;   // fuzz or refraction index
+  int32_t type;
+  int32_t pad[3];
+};
+
+struct DevScene {
+  const float4* nodes; // 4 float4 per node
+  const float4* tris;  // 3 float4 per triangle
+  const DevSphere* spheres;
+  const DevMaterial* materials;
+  uint32_t n_spheres;
+  uint32_t n_spheres_before; // spheres[0..n_before) precede the first mesh object
+  uint32_t n_nodes;
+  uint32_t n_tris;
+};
+
+// Hit record written by extend and consumed by shade: 32 B.
+//   hit_a = (t | <0 miss, point.xyz)   hit_b = (normal.xyz, bits(material | side<<31))
+// Path state, all indexed by path id = sample_in_pass * pixels + pixel:
+//   ray_o = (origin.xyz, t_min)   ray_d = (direction.xyz, t_max)
+//   thr   = (throughput.rgb, bits(rng state))
+//   gbuf  = (first-hit normal.xyz, first-hit t)
+struct PathState {
+  float4* ray_o;
+  float4* ray_d;
+  float4* thr;
+  float4* hit_a;
+  float4* hit_b;
+  float4* gbuf;
+};
+
+// One wavefront pass = `samples` consecutive iterations of every pixel.
+struct PassParams {
+  DevCamera cam;
+  uint32_t pixels;
+  uint32_t tiles_x, tiles_y; // 8x4-pixel warp tiles
+  uint32_t samples;
+  uint32_t first_iteration;
+  uint32_t rng_mode;
+};
+
+} // namespace pt

@@ -1,0 +1,779 @@
+// context.cpp — C-ABI entry points: scene upload and the PathTracer-shaped
+// integrator context (include/b200pt.h).  Host orchestration only; every
+// computation on rays/pixels happens in kernels.cu.
+#include "bvh_build.h"
+#include "internal.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+namespace pt {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const std::string& msg)
+{
+  g_last_error = msg;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what)
+{
+  g_last_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+  return PT_ERR_CUDA;
+}
+
+static double now_ms()
+{
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+// transform_point (transform.hpp:37-42): (m0*x + m1*y) + (m2*z + m3*1), then / w
+static void xform_point(const float* m, const float* p, float* out)
+{
+  float v[4];
+  for (int r = 0; r < 4; ++r)
+    v[r] = (m[0 * 4 + r] * p[0] + m[1 * 4 + r] * p[1]) + (m[2 * 4 + r] * p[2] + m[3 * 4 + r] * 1.0f);
+  out[0] = v[0] / v[3];
+  out[1] = v[1] / v[3];
+  out[2] = v[2] / v[3];
+}
+
+static bool is_affine(const float* m)
+{
+  return m[3] == 0.f && m[7] == 0.f && m[11] == 0.f && m[15] == 1.f;
+}
+
+static void rows3x4(const float* colmajor, float* out12)
+{
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 4; ++c) out12[r * 4 + c] = colmajor[c * 4 + r];
+}
+
+} // namespace pt
+
+using namespace pt;
+
+extern "C" {
+
+const char* pt_last_error(void) { return g_last_error.c_str(); }
+int pt_version(void) { return 100; }
+
+void pt_params_default(pt_params* p)
+{
+  if (!p) return;
+  std::memset(p, 0, sizeof(*p));
+  p->max_depth = 50; // reference: max_bounces (path_tracer.cu:27)
+  p->rng_mode = PT_RNG_PIXEL_STREAM;
+  p->max_iterations = 0;
+  p->samples_per_pass = 0;
+}
+
+void pt_denoise_params_default(pt_denoise_params* p)
+{
+  if (!p) return;
+  std::memset(p, 0, sizeof(*p));
+  p->filter_size = 10;
+  p->color_weight = 0.45f;
+  p->normal_weight = 0.30f;
+  p->position_weight = 0.25f;
+  p->clamp_fix = 0;
+}
+
+// ------------------------------------------------------------------- scene
+int pt_scene_create(const pt_scene_desc* desc, int device, pt_scene** out)
+{
+  if (!desc || !out) return fail(PT_ERR_INVALID, "pt_scene_create: null argument");
+  *out = nullptr;
+  if (desc->n_indices % 3 != 0) return fail(PT_ERR_INVALID, "index count is not a multiple of 3");
+  if (desc->n_objects && !desc->objects) return fail(PT_ERR_INVALID, "objects is null");
+  if (desc->n_materials == 0 || !desc->materials)
+    return fail(PT_ERR_INVALID, "scene needs at least one material");
+  for (uint64_t i = 0; i < desc->n_indices; ++i)
+    if (desc->indices[i] >= desc->n_vertices)
+      return fail(PT_ERR_INVALID, "vertex index out of range");
+
+  int dev_count = 0;
+  PT_CUDA(cudaGetDeviceCount(&dev_count));
+  if (device < 0 || device >= dev_count) return fail(PT_ERR_INVALID, "no such CUDA device");
+  PT_CUDA(cudaSetDevice(device));
+
+  const double t0 = now_ms();
+  const uint64_t n_tri = desc->n_indices / 3;
+
+  // ---- objects -> spheres (reference order quirks kept) + baked mesh instances
+  std::vector<DevSphere> sph_before, sph_after;
+  std::vector<uint32_t> mesh_objects;
+  bool seen_mesh = false;
+  for (uint32_t i = 0; i < desc->n_objects; ++i) {
+    const pt_object& ob = desc->objects[i];
+    if (ob.material >= desc->n_materials)
+      return fail(PT_ERR_INVALID, "object material index out of range");
+    if (!is_affine(ob.m) || !is_affine(ob.inv))
+      return fail(PT_ERR_INVALID, "projective object transforms are not supported");
+    if (ob.type == PT_OBJ_SPHERE) {
+      if (ob.prim_index >= desc->n_spheres)
+        return fail(PT_ERR_INVALID, "sphere index out of range");
+      const pt_sphere& s = desc->spheres[ob.prim_index];
+      DevSphere d{};
+      rows3x4(ob.inv, d.inv);
+      rows3x4(ob.m, d.m);
+      d.cx = s.center[0], d.cy = s.center[1], d.cz = s.center[2];
+      d.radius = s.radius;
+      d.material = ob.material;
+      d.object = (int32_t)i;
+      (seen_mesh ? sph_after : sph_before).push_back(d);
+    } else if (ob.type == PT_OBJ_MESH) {
+      seen_mesh = true;
+      mesh_objects.push_back(i);
+    } else {
+      return fail(PT_ERR_INVALID, "unknown object type");
+    }
+  }
+
+  std::vector<BuildTri> tris;
+  const uint64_t n_world = n_tri * mesh_objects.size();
+  if (n_world >= (1ull << 28)) return fail(PT_ERR_INVALID, "too many world-space triangles");
+  try {
+    tris.resize(n_world);
+  } catch (...) {
+    return fail(PT_ERR_NOMEM, "out of host memory baking mesh instances");
+  }
+  for (size_t k = 0; k < mesh_objects.size(); ++k) {
+    const uint32_t oi = mesh_objects[k];
+    const pt_object& ob = desc->objects[oi];
+    BuildTri* dst = tris.data() + k * n_tri;
+#pragma omp parallel for schedule(static)
+    for (long long t = 0; t < (long long)n_tri; ++t) {
+      BuildTri& bt = dst[t];
+      xform_point(ob.m, desc->positions + 3 * (size_t)desc->indices[3 * t + 0], bt.v0);
+      xform_point(ob.m, desc->positions + 3 * (size_t)desc->indices[3 * t + 1], bt.v1);
+      xform_point(ob.m, desc->positions + 3 * (size_t)desc->indices[3 * t + 2], bt.v2);
+      bt.prim = (uint32_t)t;
+      bt.object = oi;
+      bt.material = ob.material;
+    }
+  }
+
+  FlatBVH bvh;
+  build_bvh(tris, bvh);
+  const double t1 = now_ms();
+
+  std::vector<DevMaterial> mats(desc->n_materials);
+  for (uint32_t i = 0; i < desc->n_materials; ++i) {
+    const pt_material& m = desc->materials[i];
+    DevMaterial d{};
+    d.type = m.type;
+    d.r = m.albedo[0], d.g = m.albedo[1], d.b = m.albedo[2];
+    d.param = m.type == PT_MAT_METAL ? m.fuzz : (m.type == PT_MAT_DIELECTRIC ? m.refraction_index : 0.f);
+    if (m.type < 0 || m.type > 2) return fail(PT_ERR_INVALID, "unknown material type");
+    mats[i] = d;
+  }
+
+  pt_scene* sc = new pt_scene();
+  sc->device = device;
+  std::vector<DevSphere> spheres = sph_before;
+  spheres.insert(spheres.end(), sph_after.begin(), sph_after.end());
+
+  auto upload = [&](const void* src, size_t bytes, void** dst) -> cudaError_t {
+    *dst = nullptr;
+    if (bytes == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc(dst, bytes);
+    if (e != cudaSuccess) return e;
+    sc->info.device_bytes += bytes;
+    return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+  };
+  cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess) e = upload(bvh.nodes.data(), bvh.nodes.size() * 4, &sc->d_nodes);
+  if (e == cudaSuccess) e = upload(bvh.tris.data(), bvh.tris.size() * 4, &sc->d_tris);
+  if (e == cudaSuccess) e = upload(spheres.data(), spheres.size() * sizeof(DevSphere), &sc->d_spheres);
+  if (e == cudaSuccess) e = upload(mats.data(), mats.size() * sizeof(DevMaterial), &sc->d_materials);
+  if (e != cudaSuccess) {
+    pt_scene_destroy(sc);
+    return cuda_fail(e, "scene upload");
+  }
+  const double t2 = now_ms();
+
+  sc->dev.nodes = (const float4*)sc->d_nodes;
+  sc->dev.tris = (const float4*)sc->d_tris;
+  sc->dev.spheres = (const DevSphere*)sc->d_spheres;
+  sc->dev.materials = (const DevMaterial*)sc->d_materials;
+  sc->dev.n_spheres = (uint32_t)spheres.size();
+  sc->dev.n_spheres_before = (uint32_t)sph_before.size();
+  sc->dev.n_nodes = bvh.n_nodes;
+  sc->dev.n_tris = bvh.n_tris;
+  sc->info.n_triangles = n_tri;
+  sc->info.n_world_triangles = n_world;
+  sc->info.n_bvh_nodes = bvh.n_nodes;
+  sc->info.bvh_depth = bvh.depth;
+  sc->info.n_objects = desc->n_objects;
+  sc->info.n_spheres = (uint32_t)spheres.size();
+  sc->info.n_materials = desc->n_materials;
+  sc->info.build_ms = t1 - t0;
+  sc->info.upload_ms = t2 - t1;
+  *out = sc;
+  return PT_OK;
+}
+
+int pt_scene_destroy(pt_scene* sc)
+{
+  if (!sc) return PT_OK;
+  cudaSetDevice(sc->device);
+  cudaFree(sc->d_nodes);
+  cudaFree(sc->d_tris);
+  cudaFree(sc->d_spheres);
+  cudaFree(sc->d_materials);
+  delete sc;
+  return PT_OK;
+}
+
+int pt_scene_get_info(const pt_scene* sc, pt_scene_info* info)
+{
+  if (!sc || !info) return fail(PT_ERR_INVALID, "pt_scene_get_info: null argument");
+  *info = sc->info;
+  return PT_OK;
+}
+
+int pt_scene_load_file(const char* json_path, int device, pt_scene** out, pt_scene_file_info* info)
+{
+  if (!json_path || !out) return fail(PT_ERR_INVALID, "pt_scene_load_file: null argument");
+  const double t0 = now_ms();
+  SceneFile sf;
+  int rc = load_scene_file(json_path, sf);
+  if (rc != PT_OK) return rc;
+  const double t1 = now_ms();
+  pt_scene_desc d{};
+  d.positions = sf.positions.data();
+  d.n_vertices = sf.positions.size() / 3;
+  d.indices = sf.indices.data();
+  d.n_indices = sf.indices.size();
+  d.objects = sf.objects.data();
+  d.n_objects = (uint32_t)sf.objects.size();
+  d.spheres = sf.spheres.data();
+  d.n_spheres = (uint32_t)sf.spheres.size();
+  d.materials = sf.materials.data();
+  d.n_materials = (uint32_t)sf.materials.size();
+  rc = pt_scene_create(&d, device, out);
+  if (rc != PT_OK) return rc;
+  if (info) {
+    info->camera = sf.camera;
+    info->width = sf.width;
+    info->height = sf.height;
+    info->spp = sf.spp;
+    info->load_ms = t1 - t0;
+  }
+  return PT_OK;
+}
+
+// ----------------------------------------------------------------- context
+static void free_image_buffers(pt_ctx* c)
+{
+  cudaFree(c->d_state);
+  cudaFree(c->pb.queue[0]);
+  cudaFree(c->pb.queue[1]);
+  cudaFree(c->pb.flags);
+  cudaFree(c->pb.block_sums);
+  cudaFree(c->d_sums);
+  for (auto& p : c->d_dn) {
+    cudaFree(p);
+    p = nullptr;
+  }
+  cudaFree(c->d_rgba);
+  cudaFree(c->d_export);
+  c->d_state = nullptr;
+  c->pb.queue[0] = c->pb.queue[1] = nullptr;
+  c->pb.flags = nullptr;
+  c->pb.block_sums = nullptr;
+  c->d_sums = nullptr;
+  c->d_rgba = nullptr;
+  c->d_export = nullptr;
+  c->final_rgb = nullptr;
+}
+
+static int alloc_image_buffers(pt_ctx* c, uint32_t width, uint32_t height)
+{
+  if (width == 0 || height == 0 || (uint64_t)width * height > (1ull << 27))
+    return fail(PT_ERR_INVALID, "unsupported resolution");
+  c->width = width;
+  c->height = height;
+  c->pixels = width * height;
+  uint32_t spp_pass = 1;
+  if (c->params.rng_mode == PT_RNG_SLOT_RESEED) {
+    spp_pass = 1; // slot indices are per iteration
+  } else if (c->params.samples_per_pass > 0) {
+    spp_pass = (uint32_t)c->params.samples_per_pass;
+  } else {
+    const uint64_t target = 1ull << 23; // ~8M paths in flight
+    spp_pass = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(64, target / c->pixels));
+  }
+  c->samples_per_pass = spp_pass;
+  const size_t cap = (size_t)c->pixels * spp_pass;
+  if (cap > (1ull << 30)) return fail(PT_ERR_INVALID, "wavefront too large");
+  c->pb.capacity = (uint32_t)cap;
+  PT_CUDA(cudaMalloc(&c->d_state, cap * sizeof(float4) * 6));
+  float4* base = (float4*)c->d_state;
+  c->pb.ps.ray_o = base + 0 * cap;
+  c->pb.ps.ray_d = base + 1 * cap;
+  c->pb.ps.thr = base + 2 * cap;
+  c->pb.ps.hit_a = base + 3 * cap;
+  c->pb.ps.hit_b = base + 4 * cap;
+  c->pb.ps.gbuf = base + 5 * cap;
+  PT_CUDA(cudaMalloc((void**)&c->pb.queue[0], cap * 4));
+  PT_CUDA(cudaMalloc((void**)&c->pb.queue[1], cap * 4));
+  if (c->params.rng_mode == PT_RNG_SLOT_RESEED) {
+    PT_CUDA(cudaMalloc((void**)&c->pb.flags, cap));
+    PT_CUDA(cudaMalloc((void**)&c->pb.block_sums, ((cap + 2047) / 2048 + 1) * 4));
+  }
+  PT_CUDA(cudaMalloc((void**)&c->d_sums, (size_t)c->pixels * sizeof(float4) * 2));
+  PT_CUDA(cudaMemsetAsync(c->d_sums, 0, (size_t)c->pixels * sizeof(float4) * 2, c->stream));
+  PT_CUDA(cudaMalloc((void**)&c->d_rgba, (size_t)c->pixels * 4));
+  PT_CUDA(cudaMalloc((void**)&c->d_export, (size_t)c->pixels * 3 * 4));
+  c->iteration = 0;
+  c->final_rgb = nullptr;
+  return PT_OK;
+}
+
+int pt_ctx_create(const pt_scene* scene, uint32_t width, uint32_t height, const pt_params* params,
+                  void* stream, pt_ctx** out)
+{
+  if (!scene || !out) return fail(PT_ERR_INVALID, "pt_ctx_create: null argument");
+  *out = nullptr;
+  pt_params p;
+  if (params)
+    p = *params;
+  else
+    pt_params_default(&p);
+  if (p.max_depth <= 0 || p.max_depth > 4096) return fail(PT_ERR_INVALID, "max_depth out of range");
+  if (p.rng_mode != PT_RNG_PIXEL_STREAM && p.rng_mode != PT_RNG_SLOT_RESEED)
+    return fail(PT_ERR_INVALID, "unknown rng_mode");
+  PT_CUDA(cudaSetDevice(scene->device));
+  pt_ctx* c = new pt_ctx();
+  c->scene = scene;
+  c->params = p;
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, scene->device);
+  if (e != cudaSuccess) {
+    delete c;
+    return cuda_fail(e, "cudaGetDeviceProperties");
+  }
+  c->sms = prop.multiProcessorCount;
+  if (stream) {
+    c->stream = (cudaStream_t)stream;
+    c->own_stream = false;
+  } else {
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+      delete c;
+      return cuda_fail(e, "cudaStreamCreate");
+    }
+    c->own_stream = true;
+  }
+  const size_t n_ctr = (size_t)p.max_depth + 2;
+  c->counters_bytes = n_ctr * 2 * sizeof(uint32_t);
+  int rc = PT_OK;
+  do {
+    if ((e = cudaMalloc(&c->d_counters, c->counters_bytes + 16)) != cudaSuccess) break;
+    c->pb.counters = (uint32_t*)c->d_counters;
+    c->pb.work = c->pb.counters + n_ctr;
+    c->pb.total_rays = (unsigned long long*)((char*)c->d_counters + ((c->counters_bytes + 7) & ~7ull));
+    if ((e = cudaMemset(c->d_counters, 0, c->counters_bytes + 16)) != cudaSuccess) break;
+    if ((e = cudaHostAlloc((void**)&c->h_counts, n_ctr * sizeof(uint32_t), cudaHostAllocDefault)) !=
+        cudaSuccess)
+      break;
+    c->bounce_events.resize(n_ctr);
+    for (auto& ev : c->bounce_events)
+      if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) break;
+  } while (0);
+  if (e != cudaSuccess) {
+    rc = cuda_fail(e, "context allocation");
+  } else {
+    rc = alloc_image_buffers(c, width, height);
+  }
+  if (rc != PT_OK) {
+    pt_ctx_destroy(c);
+    return rc;
+  }
+  *out = c;
+  return PT_OK;
+}
+
+int pt_ctx_destroy(pt_ctx* c)
+{
+  if (!c) return PT_OK;
+  cudaSetDevice(c->scene->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  free_image_buffers(c);
+  cudaFree(c->d_counters);
+  cudaFreeHost(c->h_counts);
+  for (auto ev : c->bounce_events)
+    if (ev) cudaEventDestroy(ev);
+  for (auto ev : c->prof_events) cudaEventDestroy(ev);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return PT_OK;
+}
+
+int pt_ctx_resize(pt_ctx* c, uint32_t width, uint32_t height)
+{
+  if (!c) return fail(PT_ERR_INVALID, "pt_ctx_resize: null context");
+  PT_CUDA(cudaSetDevice(c->scene->device));
+  PT_CUDA(cudaStreamSynchronize(c->stream));
+  free_image_buffers(c);
+  return alloc_image_buffers(c, width, height);
+}
+
+int pt_ctx_restart(pt_ctx* c)
+{
+  if (!c) return fail(PT_ERR_INVALID, "pt_ctx_restart: null context");
+  // PathTracer::restart only zeroes the counter (final_gather overwrites at
+  // iteration 0); with running sums the buffers are cleared instead.
+  PT_CUDA(cudaMemsetAsync(c->d_sums, 0, (size_t)c->pixels * sizeof(float4) * 2, c->stream));
+  c->iteration = 0;
+  c->final_rgb = nullptr;
+  return PT_OK;
+}
+
+int pt_ctx_iteration(const pt_ctx* c) { return c ? c->iteration : -1; }
+
+int pt_ctx_set_max_iterations(pt_ctx* c, int n)
+{
+  if (!c) return fail(PT_ERR_INVALID, "null context");
+  c->params.max_iterations = n;
+  return PT_OK;
+}
+
+int pt_ctx_set_stream(pt_ctx* c, void* stream)
+{
+  if (!c) return fail(PT_ERR_INVALID, "null context");
+  PT_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  if (stream) {
+    c->stream = (cudaStream_t)stream;
+    c->own_stream = false;
+  } else {
+    PT_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+  }
+  return PT_OK;
+}
+
+// profile=1 helpers: event pairs per launch, folded into stats at pass end
+enum { TAG_EXT0 = 0, TAG_EXT, TAG_SHADE, TAG_COMPACT, TAG_ACC, TAG_DENOISE, TAG_RESOLVE };
+
+static void prof_begin(pt_ctx* c, int tag)
+{
+  if (!c->params.profile) return;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  cudaEventRecord(a, c->stream);
+  c->prof_events.push_back(a);
+  c->prof_events.push_back(b);
+  c->prof_tags.push_back(tag);
+}
+static void prof_end(pt_ctx* c)
+{
+  if (!c->params.profile) return;
+  cudaEventRecord(c->prof_events.back(), c->stream);
+}
+static void prof_collect(pt_ctx* c)
+{
+  if (!c->params.profile || c->prof_tags.empty()) return;
+  cudaStreamSynchronize(c->stream);
+  for (size_t i = 0; i < c->prof_tags.size(); ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->prof_events[2 * i], c->prof_events[2 * i + 1]);
+    switch (c->prof_tags[i]) {
+    case TAG_EXT0: c->stats.ms_raygen_extend0 += ms; c->stats.n_extend_launches++; break;
+    case TAG_EXT: c->stats.ms_extend += ms; c->stats.n_extend_launches++; break;
+    case TAG_SHADE: c->stats.ms_shade += ms; c->stats.n_shade_launches++; break;
+    case TAG_COMPACT: c->stats.ms_compact += ms; break;
+    case TAG_ACC: c->stats.ms_accumulate += ms; break;
+    case TAG_DENOISE: c->stats.ms_denoise += ms; break;
+    case TAG_RESOLVE: c->stats.ms_resolve += ms; break;
+    }
+    cudaEventDestroy(c->prof_events[2 * i]);
+    cudaEventDestroy(c->prof_events[2 * i + 1]);
+  }
+  c->prof_events.clear();
+  c->prof_tags.clear();
+}
+
+// One wavefront pass over `samples` consecutive iterations of every pixel.
+static int render_pass(pt_ctx* c, const pt_camera& cam, uint32_t first_iteration, uint32_t samples)
+{
+  const LaunchEnv env{c->stream, c->sms};
+  PassParams pp{};
+  pp.cam = make_dev_camera(cam, c->width, c->height);
+  pp.pixels = c->pixels;
+  pp.tiles_x = (c->width + 7) / 8;
+  pp.tiles_y = (c->height + 3) / 4;
+  pp.samples = samples;
+  pp.first_iteration = first_iteration;
+  pp.rng_mode = (uint32_t)c->params.rng_mode;
+  const uint32_t n0 = samples * pp.tiles_x * pp.tiles_y * 32u;
+  const uint32_t max_depth = (uint32_t)c->params.max_depth;
+  const bool stable = c->params.rng_mode == PT_RNG_SLOT_RESEED;
+  const uint32_t kLookBehind = 2;
+
+  PT_CUDA(cudaMemsetAsync(c->d_counters, 0, c->counters_bytes, c->stream));
+  int q = 0;
+  uint32_t launched = 0;
+  for (uint32_t b = 0; b < max_depth; ++b) {
+    if (b >= kLookBehind + 1) {
+      // look-behind early exit: stop enqueueing bounces once an older bounce is
+      // known to have produced no survivors; never blocks the host.
+      const uint32_t probe = b - kLookBehind; // counters[probe] was copied after shade(probe-1)
+      if (cudaEventQuery(c->bounce_events[probe]) == cudaSuccess && c->h_counts[probe] == 0) break;
+    }
+    const bool last = b + 1 == max_depth;
+    if (b == 0) {
+      prof_begin(c, TAG_EXT0);
+      launch_extend_first(env, c->scene->dev, c->pb, pp, n0);
+      prof_end(c);
+    } else {
+      prof_begin(c, TAG_EXT);
+      launch_extend(env, c->scene->dev, c->pb, pp, q, b);
+      prof_end(c);
+    }
+    prof_begin(c, TAG_SHADE);
+    launch_shade(env, c->scene->dev, c->pb, pp, q, b, n0, last);
+    prof_end(c);
+    launched += 2;
+    if (stable && !last) {
+      prof_begin(c, TAG_COMPACT);
+      launch_stable_compact(env, c->pb, pp, q, b);
+      prof_end(c);
+      launched += 3;
+    }
+    if (!last) {
+      PT_CUDA(cudaMemcpyAsync(&c->h_counts[b + 1], c->pb.counters + b + 1, sizeof(uint32_t),
+                              cudaMemcpyDeviceToHost, c->stream));
+      PT_CUDA(cudaEventRecord(c->bounce_events[b + 1], c->stream));
+    }
+    q ^= 1;
+    c->stats.max_bounce_reached = std::max(c->stats.max_bounce_reached, b + 1);
+  }
+  prof_begin(c, TAG_ACC);
+  launch_accumulate(env, c->pb, pp, c->d_sums, c->d_sums + c->pixels, max_depth);
+  prof_end(c);
+  launched += 1;
+  PT_CUDA(cudaGetLastError());
+  c->stats.kernel_launches += launched;
+  c->stats.passes += 1;
+  c->stats.samples += (uint64_t)samples * c->pixels;
+  prof_collect(c);
+  return PT_OK;
+}
+
+int pt_render_range(pt_ctx* c, const pt_camera* cam, int first_iteration, int n_iterations)
+{
+  if (!c || !cam) return fail(PT_ERR_INVALID, "pt_render_range: null argument");
+  if (first_iteration < 0 || n_iterations < 0) return fail(PT_ERR_INVALID, "negative iteration range");
+  PT_CUDA(cudaSetDevice(c->scene->device));
+  c->last_camera = *cam;
+  c->have_camera = true;
+  int done = 0;
+  while (done < n_iterations) {
+    const uint32_t s = (uint32_t)std::min<int>(n_iterations - done, (int)c->samples_per_pass);
+    int rc = render_pass(c, *cam, (uint32_t)(first_iteration + done), s);
+    if (rc != PT_OK) return rc;
+    done += (int)s;
+  }
+  c->iteration += n_iterations;
+  c->final_rgb = nullptr; // path_trace_result_buffer_ = dev_color_buffer_
+  return PT_OK;
+}
+
+int pt_render(pt_ctx* c, const pt_camera* cam, int n_iterations)
+{
+  if (!c) return fail(PT_ERR_INVALID, "pt_render: null context");
+  int n = n_iterations;
+  if (c->params.max_iterations > 0) n = std::min(n, std::max(0, c->params.max_iterations - c->iteration));
+  return pt_render_range(c, cam, c->iteration, n);
+}
+
+int pt_path_trace(pt_ctx* c, const pt_camera* cam) { return pt_render(c, cam, 1); }
+
+int pt_sync(pt_ctx* c)
+{
+  if (!c) return fail(PT_ERR_INVALID, "pt_sync: null context");
+  PT_CUDA(cudaStreamSynchronize(c->stream));
+  return PT_OK;
+}
+
+int pt_denoise(pt_ctx* c, const pt_denoise_params* dp_in)
+{
+  if (!c) return fail(PT_ERR_INVALID, "pt_denoise: null context");
+  pt_denoise_params dp;
+  if (dp_in)
+    dp = *dp_in;
+  else
+    pt_denoise_params_default(&dp);
+  if (dp.filter_size < 1) return fail(PT_ERR_INVALID, "filter_size must be >= 1");
+  if (!c->have_camera) return fail(PT_ERR_INVALID, "pt_denoise before any path_trace / upload_frame");
+  PT_CUDA(cudaSetDevice(c->scene->device));
+  for (auto& p : c->d_dn)
+    if (!p) PT_CUDA(cudaMalloc((void**)&p, (size_t)c->pixels * sizeof(float4)));
+  const LaunchEnv env{c->stream, c->sms};
+  const DevCamera cam = make_dev_camera(c->last_camera, c->width, c->height);
+  prof_begin(c, TAG_DENOISE);
+  launch_denoise_prepare(env, cam, c->d_sums, c->d_sums + c->pixels, c->d_dn[0], c->d_dn[1], c->d_dn[2]);
+  DenoiseParams kp{dp.color_weight, dp.normal_weight, dp.position_weight, dp.clamp_fix};
+  const float4* in = c->d_dn[0];
+  float4* bufs[2] = {c->d_dn[3], c->d_dn[4]};
+  int which = 0;
+  float4* last = nullptr;
+  uint32_t launches = 1;
+  for (int step = 1; step <= dp.filter_size; step *= 2) {
+    launch_atrous(env, cam, kp, in, c->d_dn[1], c->d_dn[2], bufs[which], step);
+    last = bufs[which];
+    in = last;
+    which ^= 1;
+    ++launches;
+  }
+  prof_end(c);
+  PT_CUDA(cudaGetLastError());
+  c->stats.kernel_launches += launches;
+  c->final_rgb = last;
+  prof_collect(c);
+  return PT_OK;
+}
+
+int pt_resolve_rgba8(pt_ctx* c, int kind, void* dst, int dst_is_device)
+{
+  if (!c || !dst) return fail(PT_ERR_INVALID, "pt_resolve_rgba8: null argument");
+  if (kind < 0 || kind > 4) return fail(PT_ERR_INVALID, "unknown buffer kind");
+  if (kind == PT_BUF_DENOISED && !c->final_rgb) return fail(PT_ERR_INVALID, "no denoised buffer");
+  PT_CUDA(cudaSetDevice(c->scene->device));
+  const LaunchEnv env{c->stream, c->sms};
+  uchar4* target = dst_is_device ? (uchar4*)dst : c->d_rgba;
+  prof_begin(c, TAG_RESOLVE);
+  launch_resolve_rgba8(env, kind, c->d_sums, c->d_sums + c->pixels, c->final_rgb,
+                       c->final_rgb != nullptr, c->pixels, target);
+  prof_end(c);
+  PT_CUDA(cudaGetLastError());
+  c->stats.kernel_launches += 1;
+  if (!dst_is_device) {
+    PT_CUDA(cudaMemcpyAsync(dst, c->d_rgba, (size_t)c->pixels * 4, cudaMemcpyDeviceToHost, c->stream));
+  }
+  // send_to_preview ends with cudaDeviceSynchronize (path_tracer.cu:519)
+  PT_CUDA(cudaStreamSynchronize(c->stream));
+  prof_collect(c);
+  return PT_OK;
+}
+
+int pt_download_f32(pt_ctx* c, int kind, float* dst)
+{
+  if (!c || !dst) return fail(PT_ERR_INVALID, "pt_download_f32: null argument");
+  if (kind < 0 || kind > 4) return fail(PT_ERR_INVALID, "unknown buffer kind");
+  if (kind == PT_BUF_DENOISED && !c->final_rgb) return fail(PT_ERR_INVALID, "no denoised buffer");
+  PT_CUDA(cudaSetDevice(c->scene->device));
+  const LaunchEnv env{c->stream, c->sms};
+  launch_export_f32(env, kind, c->d_sums, c->d_sums + c->pixels, c->final_rgb,
+                    c->final_rgb != nullptr, c->pixels, c->d_export);
+  PT_CUDA(cudaGetLastError());
+  c->stats.kernel_launches += 1;
+  const size_t n = (size_t)c->pixels * (kind == PT_BUF_DEPTH ? 1 : 3);
+  PT_CUDA(cudaMemcpyAsync(dst, c->d_export, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  PT_CUDA(cudaStreamSynchronize(c->stream));
+  return PT_OK;
+}
+
+int pt_ctx_sums(pt_ctx* c, void** device_ptr, uint64_t* n_floats)
+{
+  if (!c || !device_ptr || !n_floats) return fail(PT_ERR_INVALID, "pt_ctx_sums: null argument");
+  *device_ptr = c->d_sums;
+  *n_floats = (uint64_t)c->pixels * 8;
+  return PT_OK;
+}
+
+int pt_ctx_set_sample_count(pt_ctx* c, int n)
+{
+  if (!c) return fail(PT_ERR_INVALID, "null context");
+  c->iteration = n;
+  return PT_OK;
+}
+
+int pt_ctx_upload_frame(pt_ctx* c, const float* color3, const float* normal3, const float* depth1,
+                        const pt_camera* cam)
+{
+  if (!c || !color3 || !normal3 || !depth1 || !cam)
+    return fail(PT_ERR_INVALID, "pt_ctx_upload_frame: null argument");
+  PT_CUDA(cudaSetDevice(c->scene->device));
+  float* tmp = nullptr;
+  const size_t n = c->pixels;
+  PT_CUDA(cudaMalloc((void**)&tmp, n * 7 * sizeof(float)));
+  cudaError_t e = cudaMemcpyAsync(tmp, color3, n * 12, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(tmp + 3 * n, normal3, n * 12, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(tmp + 6 * n, depth1, n * 4, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) {
+    const LaunchEnv env{c->stream, c->sms};
+    launch_import_frame(env, tmp, tmp + 3 * n, tmp + 6 * n, c->pixels, c->d_sums, c->d_sums + c->pixels);
+    e = cudaStreamSynchronize(c->stream);
+  }
+  cudaFree(tmp);
+  if (e != cudaSuccess) return cuda_fail(e, "upload_frame");
+  c->stats.kernel_launches += 1;
+  c->last_camera = *cam;
+  c->have_camera = true;
+  c->iteration = 1;
+  c->final_rgb = nullptr;
+  return PT_OK;
+}
+
+int pt_get_stats(pt_ctx* c, pt_stats* out)
+{
+  if (!c || !out) return fail(PT_ERR_INVALID, "pt_get_stats: null argument");
+  PT_CUDA(cudaSetDevice(c->scene->device));
+  PT_CUDA(cudaStreamSynchronize(c->stream));
+  unsigned long long rays = 0;
+  PT_CUDA(cudaMemcpy(&rays, c->pb.total_rays, sizeof(rays), cudaMemcpyDeviceToHost));
+  c->stats.rays = rays;
+  c->stats.iterations = (uint32_t)c->iteration;
+  *out = c->stats;
+  return PT_OK;
+}
+
+int pt_reset_stats(pt_ctx* c)
+{
+  if (!c) return fail(PT_ERR_INVALID, "null context");
+  PT_CUDA(cudaSetDevice(c->scene->device));
+  PT_CUDA(cudaStreamSynchronize(c->stream));
+  PT_CUDA(cudaMemset(c->pb.total_rays, 0, sizeof(unsigned long long)));
+  c->stats = pt_stats{};
+  return PT_OK;
+}
+
+// -------------------------------------------------------------- trace batch
+int pt_trace_batch(const pt_scene* sc, const float* rays8, uint64_t n, pt_hit* hits_out)
+{
+  if (!sc || (!rays8 && n) || (!hits_out && n)) return fail(PT_ERR_INVALID, "pt_trace_batch: null argument");
+  if (n == 0) return PT_OK;
+  if (n > (1ull << 30)) return fail(PT_ERR_INVALID, "ray batch too large");
+  static_assert(sizeof(HitRecord) == sizeof(pt_hit), "hit record layout");
+  PT_CUDA(cudaSetDevice(sc->device));
+  float4* d_rays = nullptr;
+  HitRecord* d_hits = nullptr;
+  cudaError_t e = cudaMalloc((void**)&d_rays, n * 32);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_hits, n * sizeof(HitRecord));
+  if (e == cudaSuccess) e = cudaMemcpy(d_rays, rays8, n * 32, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, sc->device);
+    const LaunchEnv env{nullptr, prop.multiProcessorCount};
+    launch_trace_batch(env, sc->dev, d_rays, (uint32_t)n, d_hits);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(hits_out, d_hits, n * sizeof(HitRecord), cudaMemcpyDeviceToHost);
+  cudaFree(d_rays);
+  cudaFree(d_hits);
+  if (e != cudaSuccess) return cuda_fail(e, "pt_trace_batch");
+  return PT_OK;
+}
+
+} // extern "C"

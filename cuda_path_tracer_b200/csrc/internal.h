@@ -1,0 +1,90 @@
+// internal.h — host-side structures behind the opaque C-ABI handles.
+#pragma once
+#include "../../include/b200pt.h"
+#include "kernels.h"
+
+#include <string>
+#include <vector>
+
+namespace pt {
+
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define PT_CUDA(call)                                                                            \
+  do {                                                                                           \
+    cudaError_t e__ = (call);                                                                    \
+    if (e__ != cudaSuccess) return ::pt::cuda_fail(e__, #call);                                  \
+  } while (0)
+
+// host math mirroring the glm calls the reference makes (column-major mat4)
+struct Mat4 {
+  float m[16];
+};
+Mat4 mat4_identity();
+Mat4 mat4_mul(const Mat4& a, const Mat4& b);
+Mat4 mat4_translate(float x, float y, float z);
+Mat4 mat4_scale(float x, float y, float z);
+Mat4 mat4_rotate(float angle_rad, float ax, float ay, float az);
+Mat4 mat4_inverse(const Mat4& a);
+bool mat4_decompose_trs(const Mat4& a, float pos[3], float quat_wxyz[4]);
+void mat4_from_camera(const pt_camera& cam, float out12[12]);
+DevCamera make_dev_camera(const pt_camera& cam, uint32_t w, uint32_t h);
+
+// parsed scene file (scene_io.cpp)
+struct SceneFile {
+  std::vector<float> positions;
+  std::vector<uint32_t> indices;
+  std::vector<pt_object> objects;
+  std::vector<pt_sphere> spheres;
+  std::vector<pt_material> materials;
+  pt_camera camera;
+  int width = 0, height = 0, spp = 1;
+};
+int load_scene_file(const char* json_path, SceneFile& out);
+int load_obj_file(const char* path, std::vector<float>& positions, std::vector<uint32_t>& indices);
+
+} // namespace pt
+
+struct pt_scene {
+  int device = 0;
+  pt::DevScene dev{};
+  void* d_nodes = nullptr;
+  void* d_tris = nullptr;
+  void* d_spheres = nullptr;
+  void* d_materials = nullptr;
+  pt_scene_info info{};
+};
+
+struct pt_ctx {
+  const pt_scene* scene = nullptr;
+  uint32_t width = 0, height = 0, pixels = 0;
+  pt_params params{};
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sms = 148;
+  int iteration = 0;
+  uint32_t samples_per_pass = 1;
+
+  pt::PassBuffers pb{};
+  void* d_state = nullptr;    // one slab for the six PathState planes
+  void* d_counters = nullptr; // counters + work cursors (one memset per pass)
+  size_t counters_bytes = 0;
+  uint32_t* h_counts = nullptr; // pinned look-behind copies of the bounce counters
+  std::vector<cudaEvent_t> bounce_events;
+
+  float4* d_sums = nullptr; // [0,pixels) colour sums + count, [pixels,2*pixels) normal+depth sums
+  // denoiser planes (allocated on first use)
+  float4* d_dn[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  float4* final_rgb = nullptr; // last denoise output, or nullptr => colour mean
+  uchar4* d_rgba = nullptr;
+  float* d_export = nullptr;
+
+  pt_camera last_camera{};
+  bool have_camera = false;
+
+  pt_stats stats{};
+  std::vector<cudaEvent_t> prof_events; // profile=1: pairs, tagged
+  std::vector<int> prof_tags;
+};

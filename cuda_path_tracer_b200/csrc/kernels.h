@@ -1,0 +1,75 @@
+// kernels.h — host-callable launchers of the sm_100a kernels (kernels.cu).
+#pragma once
+#include "common.cuh"
+
+namespace pt {
+
+struct LaunchEnv {
+  cudaStream_t stream;
+  int sms; // multiprocessor count; persistent grids are sized sms * resident CTAs
+};
+
+// Per-pass device scratch owned by the context.
+struct PassBuffers {
+  PathState ps;
+  uint32_t* queue[2];  // ping-pong path-id queues
+  uint32_t* counters;  // [0 .. max_depth]   live paths entering bounce b
+  uint32_t* work;      // [0 .. 2*max_depth+1] persistent-kernel work-fetch cursors
+  uint8_t* flags;      // stable-compaction alive flags (PT_RNG_SLOT_RESEED only)
+  uint32_t* block_sums; // stable-compaction block counts / offsets
+  unsigned long long* total_rays; // device-side ray counter
+  uint32_t capacity;   // paths
+};
+
+// bounce 0: raygen fused into extend. n_items = samples * tiles * 32.
+void launch_extend_first(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb,
+                         const PassParams& pp, uint32_t n_items);
+// bounce b >= 1: extend over queue `q` whose length is counters[b] (device side).
+void launch_extend(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb,
+                   const PassParams& pp, int q, uint32_t bounce);
+// shade bounce b reading queue q (implicit tile order when bounce == 0), appending
+// survivors to queue q^1 and counters[bounce+1].
+void launch_shade(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb,
+                  const PassParams& pp, int q, uint32_t bounce, uint32_t n_items_first,
+                  bool last_bounce);
+// stable compaction (slot-reseed mode): flags -> queue q^1, counters[bounce+1].
+void launch_stable_compact(const LaunchEnv& env, const PassBuffers& pb, const PassParams& pp,
+                           int q, uint32_t bounce);
+// per-pixel sum of the pass's samples into the running sums; also folds the
+// bounce counters into total_rays.
+void launch_accumulate(const LaunchEnv& env, const PassBuffers& pb, const PassParams& pp,
+                       float4* sum_color, float4* sum_gbuf, uint32_t max_depth);
+
+void launch_resolve_rgba8(const LaunchEnv& env, int kind, const float4* sum_color,
+                          const float4* sum_gbuf, const float4* final_rgb, bool final_is_mean,
+                          uint32_t pixels, uchar4* out);
+void launch_export_f32(const LaunchEnv& env, int kind, const float4* sum_color,
+                       const float4* sum_gbuf, const float4* final_rgb, bool final_is_mean,
+                       uint32_t pixels, float* out);
+void launch_import_frame(const LaunchEnv& env, const float* color3, const float* normal3,
+                         const float* depth1, uint32_t pixels, float4* sum_color,
+                         float4* sum_gbuf);
+
+struct DenoiseParams {
+  float c_phi, n_phi, p_phi;
+  int clamp_fix;
+};
+// mean colour / normal / world position planes from the running sums
+void launch_denoise_prepare(const LaunchEnv& env, const DevCamera& cam, const float4* sum_color,
+                            const float4* sum_gbuf, float4* color0, float4* normal_depth,
+                            float4* position);
+void launch_atrous(const LaunchEnv& env, const DevCamera& cam, const DenoiseParams& dp,
+                   const float4* color_in, const float4* normal_depth, const float4* position,
+                   float4* color_out, int step_width);
+
+// closest-hit parity hook
+struct HitRecord {
+  float t, px, py, pz, nx, ny, nz;
+  uint32_t material, side;
+  int32_t object, prim;
+  uint32_t pad;
+};
+void launch_trace_batch(const LaunchEnv& env, const DevScene& sc, const float4* rays,
+                        uint32_t n, HitRecord* out);
+
+} // namespace pt

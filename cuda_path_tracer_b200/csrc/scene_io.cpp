@@ -1,0 +1,482 @@
+// scene_io.cpp — reader for the reference's scene-JSON + OBJ input format.
+//
+// Grammar and semantics follow src/lib/assets/json_parser.cpp:40-224 (materials,
+// surfaces, transform command lists, camera, sampler), scene_description.cpp
+// (alphabetical material table :59-66, first-mesh-only :95) and
+// assets/model_loader.cpp:11-44 (Assimp: first mesh, triangulated, de-indexed).
+// The JSON reader below is a small self-contained recursive-descent parser;
+// nlohmann/json and Assimp are not dependencies.
+#include "internal.h"
+
+#include <algorithm>
+#include <charconv>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <filesystem>
+#include <map>
+#include <memory>
+
+namespace pt {
+namespace {
+
+// ------------------------------------------------------------- mini JSON
+struct JValue;
+using JPtr = std::shared_ptr<JValue>;
+struct JValue {
+  enum Kind { Null, Bool, Num, Str, Arr, Obj } kind = Null;
+  bool b = false;
+  double num = 0.0;
+  std::string str;
+  std::vector<JPtr> arr;
+  std::vector<std::pair<std::string, JPtr>> obj;
+  const JValue* find(const std::string& k) const
+  {
+    for (auto& kv : obj)
+      if (kv.first == k) return kv.second.get();
+    return nullptr;
+  }
+};
+
+struct JParser {
+  const char* p;
+  const char* end;
+  std::string err;
+  void ws()
+  {
+    while (p < end && (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r')) ++p;
+  }
+  bool fail(const std::string& m)
+  {
+    if (err.empty()) err = m;
+    return false;
+  }
+  bool parse_string(std::string& out)
+  {
+    if (p >= end || *p != '"') return fail("expected string");
+    ++p;
+    while (p < end && *p != '"') {
+      if (*p == '\\') {
+        ++p;
+        if (p >= end) return fail("bad escape");
+        switch (*p) {
+        case 'n': out += '\n'; break;
+        case 't': out += '\t'; break;
+        case 'r': out += '\r'; break;
+        case 'b': out += '\b'; break;
+        case 'f': out += '\f'; break;
+        case 'u': {
+          if (end - p < 5) return fail("bad \\u escape");
+          unsigned cp = (unsigned)std::strtoul(std::string(p + 1, p + 5).c_str(), nullptr, 16);
+          if (cp < 0x80) {
+            out += (char)cp;
+          } else if (cp < 0x800) {
+            out += (char)(0xC0 | (cp >> 6));
+            out += (char)(0x80 | (cp & 0x3F));
+          } else {
+            out += (char)(0xE0 | (cp >> 12));
+            out += (char)(0x80 | ((cp >> 6) & 0x3F));
+            out += (char)(0x80 | (cp & 0x3F));
+          }
+          p += 4;
+          break;
+        }
+        default: out += *p;
+        }
+        ++p;
+      } else {
+        out += *p++;
+      }
+    }
+    if (p >= end) return fail("unterminated string");
+    ++p;
+    return true;
+  }
+  bool parse(JPtr& out)
+  {
+    ws();
+    if (p >= end) return fail("unexpected end of JSON");
+    out = std::make_shared<JValue>();
+    const char c = *p;
+    if (c == '{') {
+      out->kind = JValue::Obj;
+      ++p;
+      ws();
+      if (p < end && *p == '}') {
+        ++p;
+        return true;
+      }
+      for (;;) {
+        ws();
+        std::string key;
+        if (!parse_string(key)) return false;
+        ws();
+        if (p >= end || *p != ':') return fail("expected ':'");
+        ++p;
+        JPtr v;
+        if (!parse(v)) return false;
+        out->obj.emplace_back(std::move(key), v);
+        ws();
+        if (p < end && *p == ',') {
+          ++p;
+          continue;
+        }
+        if (p < end && *p == '}') {
+          ++p;
+          return true;
+        }
+        return fail("expected ',' or '}'");
+      }
+    }
+    if (c == '[') {
+      out->kind = JValue::Arr;
+      ++p;
+      ws();
+      if (p < end && *p == ']') {
+        ++p;
+        return true;
+      }
+      for (;;) {
+        JPtr v;
+        if (!parse(v)) return false;
+        out->arr.push_back(v);
+        ws();
+        if (p < end && *p == ',') {
+          ++p;
+          continue;
+        }
+        if (p < end && *p == ']') {
+          ++p;
+          return true;
+        }
+        return fail("expected ',' or ']'");
+      }
+    }
+    if (c == '"') {
+      out->kind = JValue::Str;
+      return parse_string(out->str);
+    }
+    if (!std::strncmp(p, "true", std::min<size_t>(4, end - p)) && end - p >= 4) {
+      out->kind = JValue::Bool;
+      out->b = true;
+      p += 4;
+      return true;
+    }
+    if (!std::strncmp(p, "false", std::min<size_t>(5, end - p)) && end - p >= 5) {
+      out->kind = JValue::Bool;
+      p += 5;
+      return true;
+    }
+    if (!std::strncmp(p, "null", std::min<size_t>(4, end - p)) && end - p >= 4) {
+      p += 4;
+      return true;
+    }
+    char* e = nullptr;
+    const double v = std::strtod(p, &e);
+    if (e == p) return fail("unexpected character in JSON");
+    out->kind = JValue::Num;
+    out->num = v;
+    p = e;
+    return true;
+  }
+};
+
+bool read_file(const std::string& path, std::string& out)
+{
+  FILE* f = std::fopen(path.c_str(), "rb");
+  if (!f) return false;
+  std::fseek(f, 0, SEEK_END);
+  const long n = std::ftell(f);
+  std::fseek(f, 0, SEEK_SET);
+  out.resize(n > 0 ? (size_t)n : 0);
+  const size_t got = n > 0 ? std::fread(&out[0], 1, (size_t)n, f) : 0;
+  std::fclose(f);
+  return got == out.size();
+}
+
+struct ParseError {
+  std::string msg;
+};
+
+float num(const JValue* v, const char* what)
+{
+  if (!v || v->kind != JValue::Num) throw ParseError{std::string("Json Parser: expected number for ") + what};
+  return (float)v->num;
+}
+void vec3(const JValue* v, float out[3])
+{
+  if (!v || v->kind != JValue::Arr || v->arr.size() != 3) throw ParseError{"Json Parser: vec3 need to be 3d"};
+  for (int i = 0; i < 3; ++i) out[i] = num(v->arr[i].get(), "vec3 component");
+}
+std::string str(const JValue* v, const char* what)
+{
+  if (!v || v->kind != JValue::Str) throw ParseError{std::string("Json Parser: expected string for ") + what};
+  return v->str;
+}
+
+// adl_serializer<glm::mat4>::from_json (json_parser.cpp:40-76)
+Mat4 transform_command(const JValue& j)
+{
+  if (j.kind != JValue::Obj) throw ParseError{"Json parser: Unrecognized transform command"};
+  if (const JValue* t = j.find("translate")) {
+    float v[3];
+    vec3(t, v);
+    return mat4_translate(v[0], v[1], v[2]);
+  }
+  if (const JValue* s = j.find("scale")) {
+    if (s->kind == JValue::Num) {
+      const float f = (float)s->num;
+      return mat4_scale(f, f, f);
+    }
+    float v[3];
+    vec3(s, v);
+    return mat4_scale(v[0], v[1], v[2]);
+  }
+  if (const JValue* r = j.find("rotate")) {
+    const float angle = num(r, "rotate") * 0.01745329251994329576923690768489f; // glm::radians
+    float ax[3];
+    vec3(j.find("axis"), ax);
+    return mat4_rotate(angle, ax[0], ax[1], ax[2]);
+  }
+  if (j.find("from") && j.find("at") && j.find("up")) {
+    float from[3], at[3], up[3];
+    vec3(j.find("from"), from);
+    vec3(j.find("at"), at);
+    vec3(j.find("up"), up);
+    auto norm = [](float* v) {
+      const float s = 1.0f / std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+      v[0] *= s, v[1] *= s, v[2] *= s;
+    };
+    auto cross = [](const float* a, const float* b, float* o) {
+      o[0] = a[1] * b[2] - b[1] * a[2];
+      o[1] = a[2] * b[0] - b[2] * a[0];
+      o[2] = a[0] * b[1] - b[0] * a[1];
+    };
+    float dir[3] = {from[0] - at[0], from[1] - at[1], from[2] - at[2]};
+    norm(dir);
+    float left[3], new_up[3];
+    cross(up, dir, left);
+    norm(left);
+    cross(dir, left, new_up);
+    norm(new_up);
+    Mat4 m = mat4_identity();
+    for (int i = 0; i < 3; ++i) {
+      m.m[0 + i] = left[i];
+      m.m[4 + i] = new_up[i];
+      m.m[8 + i] = dir[i];
+      m.m[12 + i] = from[i];
+    }
+    return m;
+  }
+  throw ParseError{"Json parser: Unrecognized transform command"};
+}
+
+// adl_serializer<Transform>::from_json (json_parser.cpp:78-95): M = Mi * M
+Mat4 read_transform(const JValue* j)
+{
+  if (!j) throw ParseError{"Json Parser: surface without transform"};
+  Mat4 mat = mat4_identity();
+  if (j->kind == JValue::Obj) {
+    mat = transform_command(*j);
+  } else if (j->kind == JValue::Arr) {
+    for (auto& e : j->arr) mat = mat4_mul(transform_command(*e), mat);
+  } else {
+    throw ParseError{"Json Parser: Transform must be either an object or an array!"};
+  }
+  return mat;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------- OBJ
+// Assimp semantics kept: first mesh only (faces up to the first o/g/usemtl
+// statement that follows a face), polygons fan-triangulated, one vertex per
+// face corner (positions has 3T entries, indices = 0,1,2,...).
+int load_obj_file(const char* path, std::vector<float>& positions, std::vector<uint32_t>& indices)
+{
+  std::string text;
+  if (!read_file(path, text)) return fail(PT_ERR_IO, std::string("Unable to load ") + path);
+  std::vector<float> verts;
+  verts.reserve(text.size() / 24);
+  positions.clear();
+  indices.clear();
+  const char* p = text.data();
+  const char* end = p + text.size();
+  bool have_faces = false, stop = false;
+  std::vector<long long> corner;
+  auto skip_sp = [&](const char*& q) {
+    while (q < end && (*q == ' ' || *q == '\t')) ++q;
+  };
+  while (p < end && !stop) {
+    const char* line_end = (const char*)std::memchr(p, '\n', end - p);
+    if (!line_end) line_end = end;
+    const char* q = p;
+    skip_sp(q);
+    if (q < line_end) {
+      if (q[0] == 'v' && q + 1 < line_end && (q[1] == ' ' || q[1] == '\t')) {
+        ++q;
+        float v[3] = {0.f, 0.f, 0.f};
+        for (int i = 0; i < 3; ++i) {
+          skip_sp(q);
+          if (q < line_end && *q == '+') ++q;
+          auto r = std::from_chars(q, line_end, v[i]);
+          if (r.ec != std::errc()) return fail(PT_ERR_PARSE, std::string("bad vertex in ") + path);
+          q = r.ptr;
+        }
+        verts.push_back(v[0]);
+        verts.push_back(v[1]);
+        verts.push_back(v[2]);
+      } else if (q[0] == 'f' && q + 1 < line_end && (q[1] == ' ' || q[1] == '\t')) {
+        ++q;
+        corner.clear();
+        const long long nv = (long long)(verts.size() / 3);
+        for (;;) {
+          skip_sp(q);
+          if (q >= line_end || *q == '\r' || *q == '#') break;
+          long long idx = 0;
+          auto r = std::from_chars(q, line_end, idx);
+          if (r.ec != std::errc()) return fail(PT_ERR_PARSE, std::string("bad face in ") + path);
+          q = r.ptr;
+          while (q < line_end && *q != ' ' && *q != '\t' && *q != '\r') ++q; // skip /vt/vn
+          if (idx < 0) idx = nv + idx; else idx -= 1;
+          if (idx < 0 || idx >= nv) return fail(PT_ERR_PARSE, std::string("face index out of range in ") + path);
+          corner.push_back(idx);
+        }
+        if (corner.size() >= 3) {
+          have_faces = true;
+          for (size_t k = 1; k + 1 < corner.size(); ++k) {
+            const long long tri[3] = {corner[0], corner[k], corner[k + 1]};
+            for (int c = 0; c < 3; ++c) {
+              indices.push_back((uint32_t)(positions.size() / 3));
+              positions.push_back(verts[3 * tri[c] + 0]);
+              positions.push_back(verts[3 * tri[c] + 1]);
+              positions.push_back(verts[3 * tri[c] + 2]);
+            }
+          }
+        }
+      } else if (have_faces && (q[0] == 'o' || q[0] == 'g' || !std::strncmp(q, "usemtl", 6))) {
+        stop = true; // aiScene::mMeshes[0] only (model_loader.cpp:22)
+      }
+    }
+    p = line_end + 1;
+  }
+  if (indices.empty()) return fail(PT_ERR_PARSE, std::string("Unable to load ") + path);
+  return PT_OK;
+}
+
+// ------------------------------------------------------------ scene JSON
+int load_scene_file(const char* json_path, SceneFile& out)
+{
+  std::string text;
+  if (!read_file(json_path, text))
+    return fail(PT_ERR_IO, std::string("Json Parser: Cannot open file ") + json_path);
+  JParser jp{text.data(), text.data() + text.size(), {}};
+  JPtr root;
+  if (!jp.parse(root) || root->kind != JValue::Obj)
+    return fail(PT_ERR_PARSE, "Json Parser: " + (jp.err.empty() ? std::string("root is not an object") : jp.err));
+
+  namespace fs = std::filesystem;
+  const fs::path file_dir = fs::path(json_path).parent_path();
+  try {
+    // read_materials (json_parser.cpp:101-122); GPU table order = std::map order
+    // (scene_description.cpp:59-66); duplicates keep the first (try_emplace :151-154)
+    const JValue* mats = root->find("materials");
+    if (!mats || mats->kind != JValue::Arr) throw ParseError{"Json Parser: materials is not array!"};
+    std::map<std::string, pt_material> mat_map;
+    for (auto& mj : mats->arr) {
+      const std::string name = str(mj->find("name"), "material name");
+      const std::string type = str(mj->find("type"), "material type");
+      pt_material m{};
+      if (type == "lambertian") {
+        m.type = PT_MAT_DIFFUSE;
+        vec3(mj->find("albedo"), m.albedo);
+      } else if (type == "dielectric") {
+        m.type = PT_MAT_DIELECTRIC;
+        m.refraction_index = num(mj->find("refraction_index"), "refraction_index");
+      } else if (type == "metal") {
+        m.type = PT_MAT_METAL;
+        vec3(mj->find("albedo"), m.albedo);
+        m.fuzz = num(mj->find("fuzz"), "fuzz");
+      } else {
+        throw ParseError{"Json Parser: Unsupported material type " + type};
+      }
+      mat_map.emplace(name, m);
+    }
+    std::map<std::string, uint32_t> mat_index;
+    for (auto& kv : mat_map) {
+      mat_index[kv.first] = (uint32_t)out.materials.size();
+      out.materials.push_back(kv.second);
+    }
+
+    // read_surfaces (json_parser.cpp:133-159)
+    const JValue* surfaces = root->find("surfaces");
+    if (!surfaces || surfaces->kind != JValue::Arr) throw ParseError{"Json Parser: surfaces is not array"};
+    std::map<std::string, int> mesh_paths; // canonical path -> seen
+    for (auto& sj : surfaces->arr) {
+      const std::string type = str(sj->find("type"), "surface type");
+      const std::string material = str(sj->find("material"), "surface material");
+      auto mit = mat_index.find(material);
+      if (mit == mat_index.end()) throw ParseError{"Cannot find material " + material};
+      pt_object ob{};
+      ob.material = mit->second;
+      const Mat4 m = read_transform(sj->find("transform"));
+      const Mat4 inv = mat4_inverse(m);
+      std::memcpy(ob.m, m.m, sizeof(ob.m));
+      std::memcpy(ob.inv, inv.m, sizeof(ob.inv));
+      if (type == "sphere") {
+        ob.type = PT_OBJ_SPHERE;
+        ob.prim_index = (uint32_t)out.spheres.size();
+        pt_sphere s{};
+        s.radius = num(sj->find("radius"), "radius");
+        out.spheres.push_back(s);
+      } else if (type == "mesh") {
+        ob.type = PT_OBJ_MESH;
+        const std::string filename = str(sj->find("filename"), "mesh filename");
+        std::error_code ec;
+        const fs::path canon = fs::canonical(file_dir / filename, ec);
+        if (ec) throw ParseError{"Unable to load " + (file_dir / filename).string()};
+        mesh_paths[canon.string()] = 1;
+      } else {
+        throw ParseError{"Json Parser: Not supported surface type " + type};
+      }
+      out.objects.push_back(ob);
+    }
+    if (!mesh_paths.empty()) {
+      // Only the alphabetically-first mesh is uploaded and every mesh object
+      // instances it (scene_description.cpp:95, scene.hpp:33-39).
+      if (mesh_paths.size() > 1)
+        std::fprintf(stderr,
+                     "warning: %zu meshes referenced; like the reference only the first (%s) is used\n",
+                     mesh_paths.size(), mesh_paths.begin()->first.c_str());
+      int rc = load_obj_file(mesh_paths.begin()->first.c_str(), out.positions, out.indices);
+      if (rc != PT_OK) return rc;
+    }
+
+    // camera (json_parser.cpp:187-209)
+    const JValue* cam = root->find("camera");
+    if (!cam || cam->kind != JValue::Obj) throw ParseError{"Json Parser: Camera is not an object!"};
+    out.camera = pt_camera{{0.f, 0.f, 0.f}, {1.f, 0.f, 0.f, 0.f}, 1.5707963267948966f};
+    if (const JValue* t = cam->find("transform")) {
+      const Mat4 m = read_transform(t);
+      if (!mat4_decompose_trs(m, out.camera.position, out.camera.rotation))
+        throw ParseError{"Json parser: failed to decompose camera transformation!"};
+    }
+    out.camera.vfov = num(cam->find("vfov"), "vfov") * 0.01745329251994329576923690768489f;
+    if (const JValue* r = cam->find("resolution")) {
+      if (r->kind != JValue::Arr || r->arr.size() != 2) throw ParseError{"Json Parser: resolution need to be 2d"};
+      out.width = (int)num(r->arr[0].get(), "resolution");
+      out.height = (int)num(r->arr[1].get(), "resolution");
+    }
+    out.spp = 1;
+    if (const JValue* s = root->find("sampler")) {
+      if (s->kind != JValue::Obj) throw ParseError{"Json Parser: Sampler is not an object!"};
+      out.spp = (int)num(s->find("samples"), "samples");
+    }
+  } catch (const ParseError& e) {
+    return fail(PT_ERR_PARSE, e.msg);
+  }
+  return PT_OK;
+}
+
+} // namespace pt

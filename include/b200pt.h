@@ -1,0 +1,284 @@
+/*
+ * b200pt.h — C ABI of the B200-native wavefront path tracer.
+ *
+ * This is the drop-in boundary for the hot path of LesleyLai/cuda-path-tracer
+ * (raygen -> BVH traversal -> triangle/sphere intersection -> shading/scatter ->
+ * path compaction -> accumulate, plus the Edge-Avoiding A-Trous denoiser).
+ * The reference has no FFI layer: its seam is the C++ class `PathTracer`
+ * (src/lib/path_tracer.hpp:60-99) fed by `SceneDescription::build_scene()`
+ * (src/lib/scene_description.hpp:48).  Every entry point below names the
+ * reference member it replaces.  Plain pointers and sizes only; no C++ or
+ * torch types cross this boundary; no entry point calls exit() or throws
+ * (the reference's panic()/CUDA_CHECK exit, src/lib/prelude.cpp:5-10).
+ *
+ * Conventions
+ *   - matrices are 4x4 column-major floats (glm::mat4 memory order);
+ *   - quaternions are (w, x, y, z) (glm::quat constructor order, camera.hpp:19);
+ *   - image buffers are row-major, pixel index = x + y*width, row 0 on top
+ *     (src/lib/cuda_utils/indices.cuh:20-26);
+ *   - every function returns a pt_status; pt_last_error() gives the message.
+ */
+#ifndef B200PT_H
+#define B200PT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define PT_API
+#else
+#define PT_API __attribute__((visibility("default")))
+#endif
+
+typedef enum pt_status {
+  PT_OK = 0,
+  PT_ERR_INVALID = 1, /* bad argument / unsupported scene */
+  PT_ERR_CUDA = 2,    /* a CUDA runtime call failed */
+  PT_ERR_IO = 3,      /* file could not be opened / written */
+  PT_ERR_PARSE = 4,   /* scene JSON / OBJ grammar error */
+  PT_ERR_NOMEM = 5
+} pt_status;
+
+/* Material::Type order of the reference (src/lib/material.hpp:20). */
+typedef enum pt_material_type {
+  PT_MAT_DIFFUSE = 0,
+  PT_MAT_METAL = 1,
+  PT_MAT_DIELECTRIC = 2
+} pt_material_type;
+
+/* ObjectType order of the reference (src/lib/scene.hpp:12). */
+typedef enum pt_object_type { PT_OBJ_SPHERE = 0, PT_OBJ_MESH = 1 } pt_object_type;
+
+/* GPUMethod of the reference (src/lib/path_tracer.hpp:58) names the two RNG
+ * disciplines; both are run here by the same wavefront kernels.
+ *   PT_RNG_PIXEL_STREAM  one minstd stream per (pixel, iteration), continuous
+ *                        over bounces == reference megakernel mode
+ *                        (path_tracer.cu:239-264).  Default.
+ *   PT_RNG_SLOT_RESEED   re-seeded every bounce from the *compacted slot index*
+ *                        and discard(bounce) == reference streaming mode
+ *                        (path_tracer.cu:300-301); uses a stable compaction so
+ *                        slots equal thrust::stable_partition's. */
+typedef enum pt_rng_mode { PT_RNG_PIXEL_STREAM = 0, PT_RNG_SLOT_RESEED = 1 } pt_rng_mode;
+
+/* DisplayBufferType of the reference (src/lib/path_tracer.hpp:19) + denoised. */
+typedef enum pt_buffer_kind {
+  PT_BUF_FINAL = 0, /* last path_trace / denoise result (path_trace_result_buffer_) */
+  PT_BUF_COLOR = 1,
+  PT_BUF_NORMAL = 2,
+  PT_BUF_DEPTH = 3,
+  PT_BUF_DENOISED = 4
+} pt_buffer_kind;
+
+typedef struct pt_material {
+  int32_t type; /* pt_material_type */
+  float albedo[3];
+  float fuzz;             /* metal */
+  float refraction_index; /* dielectric */
+} pt_material;
+
+typedef struct pt_sphere {
+  float center[3];
+  float radius;
+} pt_sphere;
+
+/* One entry per scene object == GPUObject (src/lib/scene.hpp:14-20) plus the
+ * material-table index the reference keeps in object_material_indices. */
+typedef struct pt_object {
+  int32_t type;        /* pt_object_type */
+  uint32_t prim_index; /* sphere: index into spheres[]; mesh: ignored (one mesh) */
+  uint32_t material;   /* index into materials[] */
+  float m[16];         /* object -> world */
+  float inv[16];       /* world -> object */
+} pt_object;
+
+/* Flat scene description == what SceneDescription::build_scene() uploads
+ * (src/lib/scene_description.cpp:12-117).  All arrays are host memory and are
+ * copied during pt_scene_create; the caller may free them afterwards. */
+typedef struct pt_scene_desc {
+  const float* positions; /* 3*n_vertices */
+  uint64_t n_vertices;
+  const uint32_t* indices; /* n_indices = 3*triangles */
+  uint64_t n_indices;
+  const pt_object* objects;
+  uint32_t n_objects;
+  const pt_sphere* spheres;
+  uint32_t n_spheres;
+  const pt_material* materials;
+  uint32_t n_materials;
+} pt_scene_desc;
+
+/* Camera (src/lib/camera.hpp:17-23). vfov in radians. */
+typedef struct pt_camera {
+  float position[3];
+  float rotation[4]; /* w,x,y,z */
+  float vfov;
+} pt_camera;
+
+typedef struct pt_params {
+  int32_t max_depth;      /* reference: static constexpr max_bounces = 50 (path_tracer.cu:27) */
+  int32_t rng_mode;       /* pt_rng_mode */
+  int32_t max_iterations; /* PathTracer::max_iterations; <=0 means unlimited */
+  int32_t samples_per_pass; /* 0 = auto: batch several iterations into one wavefront */
+  int32_t profile;        /* 1 = time every kernel with CUDA events (pt_get_stats) */
+  int32_t sort_rays;      /* reserved */
+  int32_t reserved[2];
+} pt_params;
+
+/* EdgeAvoidingATrousDenoiser fields (denoising/edge_avoiding_a_trous_denoiser.hpp:9-12). */
+typedef struct pt_denoise_params {
+  int32_t filter_size;   /* default 10 -> steps 1,2,4,8 */
+  float color_weight;    /* 0.45 */
+  float normal_weight;   /* 0.30 */
+  float position_weight; /* 0.25 */
+  int32_t clamp_fix;     /* 0 = reference tap clamp [0,W]x[0,H] (aliasing kept, reads past
+                            the last row are replaced by the last row); 1 = clamp to W-1,H-1 */
+  int32_t reserved[3];
+} pt_denoise_params;
+
+/* Closest-hit record of pt_trace_batch: the fields of Intersection
+ * (src/lib/intersection.hpp:8-14) plus primitive ids for the parity tests. */
+typedef struct pt_hit {
+  float t; /* < 0: miss */
+  float point[3];
+  float normal[3];
+  uint32_t material;
+  uint32_t side;   /* 0 front, 1 back */
+  int32_t object;  /* object index, -1 on miss */
+  int32_t prim;    /* triangle index in the input index buffer /3, -1 for spheres */
+  uint32_t pad;
+} pt_hit;
+
+typedef struct pt_stats {
+  uint64_t rays;          /* sum over passes and bounces of live paths entering extend */
+  uint64_t samples;       /* pixel-samples rendered */
+  uint32_t iterations;    /* PathTracer::iteration() */
+  uint32_t passes;
+  uint64_t kernel_launches;
+  double ms_raygen_extend0;
+  double ms_extend; /* sum over launches, profile=1 only */
+  double ms_shade;
+  double ms_compact;
+  double ms_accumulate;
+  double ms_denoise;
+  double ms_resolve;
+  uint64_t n_extend_launches;
+  uint64_t n_shade_launches;
+  uint32_t max_bounce_reached;
+  uint32_t reserved;
+} pt_stats;
+
+typedef struct pt_scene_info {
+  uint64_t n_triangles;       /* input triangles */
+  uint64_t n_world_triangles; /* after baking every mesh instance to world space */
+  uint64_t n_bvh_nodes;
+  uint32_t bvh_depth;
+  uint32_t n_objects, n_spheres, n_materials;
+  double build_ms;  /* host BVH build */
+  double upload_ms; /* H2D */
+  uint64_t device_bytes;
+} pt_scene_info;
+
+/* Result of loading a reference scene file (assets/json_parser.cpp:174-224). */
+typedef struct pt_scene_file_info {
+  pt_camera camera;
+  int32_t width, height;
+  int32_t spp;
+  double load_ms;
+} pt_scene_file_info;
+
+typedef struct pt_scene pt_scene;
+typedef struct pt_ctx pt_ctx;
+
+PT_API const char* pt_last_error(void);
+PT_API int pt_version(void);
+
+/* --- scene: replaces SceneDescription::build_scene + bvh_from_mesh
+ *     (scene_description.cpp:12-117, accelerators/bvh.cpp:211-253) ------------- */
+PT_API int pt_scene_create(const pt_scene_desc* desc, int device, pt_scene** out);
+PT_API int pt_scene_destroy(pt_scene* scene);
+PT_API int pt_scene_get_info(const pt_scene* scene, pt_scene_info* info);
+
+/* replaces read_scene/scene_from_json/load_obj (assets/scene_parser.cpp:6-22,
+ * assets/json_parser.cpp:174-224, assets/model_loader.cpp:11-44). */
+PT_API int pt_scene_load_file(const char* json_path, int device, pt_scene** out,
+                              pt_scene_file_info* info);
+
+/* --- integrator context: replaces class PathTracer -------------------------- */
+PT_API void pt_params_default(pt_params* p);
+PT_API void pt_denoise_params_default(pt_denoise_params* p);
+
+/* PathTracer::create_buffers (path_tracer.cu:559-564). `stream` may be NULL
+ * (the context creates its own non-blocking stream) or a cudaStream_t. */
+PT_API int pt_ctx_create(const pt_scene* scene, uint32_t width, uint32_t height,
+                         const pt_params* params, void* stream, pt_ctx** out);
+PT_API int pt_ctx_destroy(pt_ctx* ctx);
+/* PathTracer::resize_image (path_tracer.cu:527-545): reallocates and restarts. */
+PT_API int pt_ctx_resize(pt_ctx* ctx, uint32_t width, uint32_t height);
+/* PathTracer::restart (path_tracer.cu:522-525). */
+PT_API int pt_ctx_restart(pt_ctx* ctx);
+/* PathTracer::iteration(). */
+PT_API int pt_ctx_iteration(const pt_ctx* ctx);
+PT_API int pt_ctx_set_max_iterations(pt_ctx* ctx, int max_iterations);
+PT_API int pt_ctx_set_stream(pt_ctx* ctx, void* stream);
+
+/* PathTracer::path_trace (path_tracer.cu:389-477): one sample per pixel per
+ * call, no-op once iteration() >= max_iterations.  Asynchronous. */
+PT_API int pt_path_trace(pt_ctx* ctx, const pt_camera* camera);
+/* The CLI loop `for i<spp: path_trace` (cli.cpp:96-99) as one call: renders
+ * iterations [iteration(), iteration()+n) batching several per wavefront. */
+PT_API int pt_render(pt_ctx* ctx, const pt_camera* camera, int n_iterations);
+/* Same, for an explicit iteration range (multi-GPU sample-range sharding):
+ * accumulates iterations [first, first+n) into the running sums. */
+PT_API int pt_render_range(pt_ctx* ctx, const pt_camera* camera, int first_iteration,
+                           int n_iterations);
+PT_API int pt_sync(pt_ctx* ctx);
+
+/* PathTracer::denoise -> EdgeAvoidingATrousDenoiser::denoise
+ * (path_tracer.cu:479-485, denoising/...denoiser.cu:88-116). */
+PT_API int pt_denoise(pt_ctx* ctx, const pt_denoise_params* params);
+
+/* PathTracer::send_to_preview (path_tracer.cu:487-520): tonemap `kind` to
+ * RGBA8 into dst (width*height*4 bytes; device pointer if dst_is_device). */
+PT_API int pt_resolve_rgba8(pt_ctx* ctx, int kind, void* dst, int dst_is_device);
+/* Raw float view of a frame buffer (means, like the reference's buffers):
+ * COLOR/NORMAL/FINAL/DENOISED -> 3 floats per pixel, DEPTH -> 1 float. */
+PT_API int pt_download_f32(pt_ctx* ctx, int kind, float* dst_host);
+
+/* Multi-GPU sample-range sharding: the running SUMS (float4 colour.rgb+count,
+ * float4 normal.xyz+depth per pixel; 32 B/pixel) live in one device buffer that
+ * a collective can reduce in place.  pt_ctx_sums returns its device pointer and
+ * size in floats; pt_ctx_set_sample_count tells the context how many samples
+ * the (reduced) sums now hold. */
+PT_API int pt_ctx_sums(pt_ctx* ctx, void** device_ptr, uint64_t* n_floats);
+PT_API int pt_ctx_set_sample_count(pt_ctx* ctx, int n_samples);
+/* Load externally produced colour / normal / depth means as the frame state
+ * (denoiser parity tests feed identical inputs to both implementations). */
+PT_API int pt_ctx_upload_frame(pt_ctx* ctx, const float* color3, const float* normal3,
+                               const float* depth1, const pt_camera* camera);
+
+PT_API int pt_get_stats(pt_ctx* ctx, pt_stats* stats);
+PT_API int pt_reset_stats(pt_ctx* ctx);
+
+/* --- parity hook: closest hit of a ray batch == ray_scene_intersection_test
+ *     (path_tracer.cu:110-128).  rays8 = n x {ox,oy,oz,t_min,dx,dy,dz,t_max}
+ *     (Ray, src/lib/ray.hpp:8-20), host memory in, host memory out. */
+PT_API int pt_trace_batch(const pt_scene* scene, const float* rays8, uint64_t n,
+                          pt_hit* hits_out);
+
+/* --- image output: replaces write_image_file (src/lib/image.cpp:9-22) ------- */
+PT_API int pt_write_png_rgba8(const char* path, const void* rgba8_host, uint32_t width,
+                              uint32_t height);
+
+/* The whole `cuda_pt [-o out.png] [--spp N] <scene>` run (src/main.cpp:9-25,
+ * src/cli/cli.cpp:62-115) as a function; the cuda_pt executable is a thin
+ * wrapper around it. Returns the process exit code. */
+PT_API int pt_cli_main(int argc, char** argv);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200PT_H */
