@@ -109,6 +109,7 @@ SYMBOLS = {
     "pt_download_f32": (C.c_int, [VP, C.c_int, VP]),
     "pt_ctx_sums": (C.c_int, [VP, C.POINTER(VP), C.POINTER(C.c_uint64)]),
     "pt_ctx_set_sample_count": (C.c_int, [VP, C.c_int]),
+    "pt_ctx_bind_sums": (C.c_int, [VP, VP]),
     "pt_ctx_upload_frame": (C.c_int, [VP, VP, VP, VP, C.POINTER(pt_camera)]),
     "pt_get_stats": (C.c_int, [VP, C.POINTER(pt_stats)]),
     "pt_reset_stats": (C.c_int, [VP]),

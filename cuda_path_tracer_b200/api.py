@@ -206,6 +206,9 @@ class PathTracer:
         check(load_library().pt_ctx_sums(self._ctx, C.byref(p), C.byref(n)))
         return p.value, n.value
 
+    def bind_sums(self, device_ptr: int | None):
+        check(load_library().pt_ctx_bind_sums(self._ctx, C.c_void_p(device_ptr or 0)))
+
     def set_sample_count(self, n: int):
         check(load_library().pt_ctx_set_sample_count(self._ctx, int(n)))
 

@@ -277,7 +277,8 @@ static void free_image_buffers(pt_ctx* c)
   cudaFree(c->pb.queue[1]);
   cudaFree(c->pb.flags);
   cudaFree(c->pb.block_sums);
-  cudaFree(c->d_sums);
+  if (c->own_sums) cudaFree(c->d_sums);
+  c->own_sums = true;
   for (auto& p : c->d_dn) {
     cudaFree(p);
     p = nullptr;
@@ -566,7 +567,6 @@ static int render_pass(pt_ctx* c, const pt_camera& cam, uint32_t first_iteration
   c->stats.kernel_launches += launched;
   c->stats.passes += 1;
   c->stats.samples += (uint64_t)samples * c->pixels;
-  prof_collect(c);
   return PT_OK;
 }
 
@@ -640,7 +640,6 @@ int pt_denoise(pt_ctx* c, const pt_denoise_params* dp_in)
   PT_CUDA(cudaGetLastError());
   c->stats.kernel_launches += launches;
   c->final_rgb = last;
-  prof_collect(c);
   return PT_OK;
 }
 
@@ -692,6 +691,24 @@ int pt_ctx_sums(pt_ctx* c, void** device_ptr, uint64_t* n_floats)
   return PT_OK;
 }
 
+int pt_ctx_bind_sums(pt_ctx* c, void* device_ptr)
+{
+  if (!c) return fail(PT_ERR_INVALID, "null context");
+  PT_CUDA(cudaSetDevice(c->scene->device));
+  PT_CUDA(cudaStreamSynchronize(c->stream));
+  if (device_ptr) {
+    if (c->own_sums) cudaFree(c->d_sums);
+    c->d_sums = (float4*)device_ptr;
+    c->own_sums = false;
+  } else if (!c->own_sums) {
+    c->d_sums = nullptr;
+    PT_CUDA(cudaMalloc((void**)&c->d_sums, (size_t)c->pixels * sizeof(float4) * 2));
+    c->own_sums = true;
+    PT_CUDA(cudaMemsetAsync(c->d_sums, 0, (size_t)c->pixels * sizeof(float4) * 2, c->stream));
+  }
+  return PT_OK;
+}
+
 int pt_ctx_set_sample_count(pt_ctx* c, int n)
 {
   if (!c) return fail(PT_ERR_INVALID, "null context");
@@ -731,6 +748,7 @@ int pt_get_stats(pt_ctx* c, pt_stats* out)
   if (!c || !out) return fail(PT_ERR_INVALID, "pt_get_stats: null argument");
   PT_CUDA(cudaSetDevice(c->scene->device));
   PT_CUDA(cudaStreamSynchronize(c->stream));
+  prof_collect(c);
   unsigned long long rays = 0;
   PT_CUDA(cudaMemcpy(&rays, c->pb.total_rays, sizeof(rays), cudaMemcpyDeviceToHost));
   c->stats.rays = rays;
@@ -745,6 +763,7 @@ int pt_reset_stats(pt_ctx* c)
   PT_CUDA(cudaSetDevice(c->scene->device));
   PT_CUDA(cudaStreamSynchronize(c->stream));
   PT_CUDA(cudaMemset(c->pb.total_rays, 0, sizeof(unsigned long long)));
+  prof_collect(c);
   c->stats = pt_stats{};
   return PT_OK;
 }

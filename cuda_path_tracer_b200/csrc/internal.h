@@ -74,6 +74,7 @@ struct pt_ctx {
   uint32_t* h_counts = nullptr; // pinned look-behind copies of the bounce counters
   std::vector<cudaEvent_t> bounce_events;
 
+  bool own_sums = true;
   float4* d_sums = nullptr; // [0,pixels) colour sums + count, [pixels,2*pixels) normal+depth sums
   // denoiser planes (allocated on first use)
   float4* d_dn[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};

@@ -255,6 +255,10 @@ PT_API int pt_download_f32(pt_ctx* ctx, int kind, float* dst_host);
  * the (reduced) sums now hold. */
 PT_API int pt_ctx_sums(pt_ctx* ctx, void** device_ptr, uint64_t* n_floats);
 PT_API int pt_ctx_set_sample_count(pt_ctx* ctx, int n_samples);
+/* Make the context accumulate into a caller-owned device buffer of
+ * width*height*8 floats (e.g. a torch tensor that NCCL reduces in place);
+ * NULL returns to a context-owned buffer.  The caller zeroes its buffer. */
+PT_API int pt_ctx_bind_sums(pt_ctx* ctx, void* device_ptr);
 /* Load externally produced colour / normal / depth means as the frame state
  * (denoiser parity tests feed identical inputs to both implementations). */
 PT_API int pt_ctx_upload_frame(pt_ctx* ctx, const float* color3, const float* normal3,

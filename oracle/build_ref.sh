@@ -1,0 +1,46 @@
+#!/usr/bin/env bash
+# build_ref.sh — compile the REFERENCE (LesleyLai/cuda-path-tracer) from the sources where they
+# lie under /root/reference into oracle/_ref/ (git-ignored; travels to the GPU box).
+#   oracle/_ref/libref_host.so  g++   host code: BVH builder, intersection routines, transforms
+#   oracle/_ref/libref_cuda.so  nvcc  sm_100: the reference's kernels + PathTracer class
+# The reference's own build (CMake + Conan) is not run: its dependencies (glm, assimp, stb,
+# cxxopts, fmt, spdlog) are absent and there is no network.  glm/fmt/spdlog are replaced by the
+# minimal stand-ins in oracle/ref_shim; the asset/CLI layer (assimp, cxxopts, stb) is not built —
+# scenes reach the reference through SceneDescription's public add_* API (ref_cuda_wrap.cu).
+# No reference source is copied into the repository: one file, path_tracer.cu, is read through
+# a patched temporary copy (three sed edits below); everything else is #included in place.
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+REF="${REFERENCE_DIR:-/root/reference}"
+OUT="$HERE/_ref"
+if [ ! -d "$REF/src/lib" ]; then
+  echo "build_ref.sh: $REF not present (GPU box): using prebuilt $OUT" >&2
+  exit 0
+fi
+mkdir -p "$OUT"
+TMP="$(mktemp -d /tmp/b200pt_ref.XXXXXX)"
+trap 'rm -rf "$TMP"' EXIT
+CXX="${REF_CXX:-/usr/bin/g++}"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+
+# ---- host library (runs anywhere): pins oracle/oracle.c against the real implementation
+"$CXX" -std=c++20 -O2 -fPIC -shared -fvisibility=hidden \
+  -I "$HERE/ref_shim" -I "$REF/src/lib" -I "$REF/src" \
+  -o "$OUT/libref_host.so" "$HERE/ref_host_wrap.cpp"
+
+# ---- CUDA library: the reference's kernels and PathTracer, recompiled for sm_100
+sed -e 's/i < max_bounces \&\& paths_count > 0/i < g_ref_max_bounces \&\& paths_count > 0/' \
+    -e 's/for (int i = 0; i < max_bounces; ++i) {/for (int i = 0; i < c_ref_max_bounces; ++i) {/' \
+    -e 's/StaticStack<unsigned int, 24> node_stack;/StaticStack<unsigned int, REF_STACK_SIZE> node_stack;/' \
+    -e 's/^        const PathsView paths_view{paths_, paths_count};$/        const PathsView paths_view{paths_, paths_count}; g_ref_ray_count += paths_count;/' \
+    "$REF/src/lib/path_tracer.cu" > "$TMP/path_tracer.cu"
+for pat in g_ref_max_bounces c_ref_max_bounces REF_STACK_SIZE g_ref_ray_count; do
+  grep -q "$pat" "$TMP/path_tracer.cu" || { echo "build_ref.sh: patch '$pat' did not apply" >&2; exit 1; }
+done
+# the reference's flags (cmake/compiler.cmake:65-72) + the arch it never sets (src/lib/CMakeLists.txt:69)
+"$NVCC" -std=c++20 -O3 -DNDEBUG -arch=sm_100 -rdc=true --expt-relaxed-constexpr --extended-lambda -lineinfo \
+  -Xcompiler -fPIC,-fvisibility=hidden -shared \
+  -DREF_PATCHED_PATH_TRACER="\"$TMP/path_tracer.cu\"" -DREF_STACK_SIZE="${REF_STACK_SIZE:-64}" \
+  -I "$HERE/ref_shim" -I "$REF/src/lib" -I "$REF/src" \
+  -o "$OUT/libref_cuda.so" "$HERE/ref_cuda_wrap.cu"
+echo "built $OUT/libref_host.so $OUT/libref_cuda.so"

@@ -441,14 +441,31 @@ static int bb_split_sah(bbuild* B, uint32_t* leaves, size_t n, aabb_t cb, int ax
       min_cost = cost[i];
       min_bucket = i;
     }
-  /* std::ranges::partition by bucket <= min_bucket (stable variant; order is irrelevant) */
-  uint32_t* tmp = (uint32_t*)malloc(n * sizeof(uint32_t));
-  size_t nl = 0, nr = 0;
-  for (size_t i = 0; i < n; ++i)
-    if (bucket_of(B, cb, axis, leaves[i]) <= min_bucket) leaves[nl++] = leaves[i];
-    else tmp[nr++] = leaves[i];
-  memcpy(leaves + nl, tmp, nr * sizeof(uint32_t));
-  free(tmp);
+  /* std::ranges::partition (bvh.cpp:170-175).  The order it leaves inside each half decides
+     which of two equal-centroid leaves becomes the left sibling further down, so libstdc++'s
+     bidirectional algorithm (bits/ranges_algo.h, the classic two-pointer Hoare scheme) is
+     restated: advance `first` over elements satisfying the predicate, retreat `tail` over
+     elements failing it, swap, repeat. */
+  size_t first = 0, tail = n;
+  for (;;) {
+    for (;;) {
+      if (first == tail) goto partitioned;
+      if (bucket_of(B, cb, axis, leaves[first]) <= min_bucket) ++first;
+      else break;
+    }
+    --tail;
+    for (;;) {
+      if (first == tail) goto partitioned;
+      if (!(bucket_of(B, cb, axis, leaves[tail]) <= min_bucket)) --tail;
+      else break;
+    }
+    uint32_t sw = leaves[first];
+    leaves[first] = leaves[tail];
+    leaves[tail] = sw;
+    ++first;
+  }
+partitioned:;
+  const size_t nl = first, nr = n - first;
   if (nl == 0 || nr == 0) return -1; /* reference: panic("Shouldn't happen!") bvh.cpp:84-85 */
   int l = bb_build(B, leaves, nl);
   int r = bb_build(B, leaves + nl, nr);
@@ -475,17 +492,48 @@ static int bb_build(bbuild* B, uint32_t* leaves, size_t n)
     return bb_new_inner(B, li, ri);
   }
   if (n <= 4) {
-    /* nth_element at n/2 on the centroid coordinate: insertion sort gives the same split */
-    for (size_t i = 1; i < n; ++i) {
+    /* std::ranges::nth_element at n/2 keyed on the centroid coordinate (bvh.cpp:96-101).
+       libstdc++'s introselect for these sizes (bits/stl_algo.h): while more than 3 elements
+       remain, one median-of-three pivot partition round; then insertion sort of what is left.
+       Restated so that equal keys end up in libstdc++'s order. */
+#define KEY(i) comp(aabb_center(B->leaf_aabb[leaves[i]]), axis)
+#define SWAPL(a, b) do { uint32_t t__ = leaves[a]; leaves[a] = leaves[b]; leaves[b] = t__; } while (0)
+    size_t lo = 0, hi = n;
+    const size_t nth = n / 2;
+    while (hi - lo > 3) {
+      /* __move_median_to_first(lo, lo+1, mid, hi-1) */
+      const size_t a = lo + 1, b = lo + (hi - lo) / 2, c = hi - 1;
+      if (KEY(a) < KEY(b)) {
+        if (KEY(b) < KEY(c)) SWAPL(lo, b);
+        else if (KEY(a) < KEY(c)) SWAPL(lo, c);
+        else SWAPL(lo, a);
+      } else if (KEY(a) < KEY(c)) SWAPL(lo, a);
+      else if (KEY(b) < KEY(c)) SWAPL(lo, c);
+      else SWAPL(lo, b);
+      /* __unguarded_partition(lo+1, hi, pivot = lo) */
+      size_t f = lo + 1, l = hi;
+      for (;;) {
+        while (KEY(f) < KEY(lo)) ++f;
+        --l;
+        while (KEY(lo) < KEY(l)) --l;
+        if (!(f < l)) break;
+        SWAPL(f, l);
+        ++f;
+      }
+      if (f <= nth) lo = f; else hi = f;
+    }
+    for (size_t i = lo + 1; i < hi; ++i) { /* __insertion_sort(lo, hi) */
       uint32_t k = leaves[i];
       float kv = comp(aabb_center(B->leaf_aabb[k]), axis);
       size_t j = i;
-      while (j > 0 && comp(aabb_center(B->leaf_aabb[leaves[j - 1]]), axis) > kv) {
+      while (j > lo && kv < comp(aabb_center(B->leaf_aabb[leaves[j - 1]]), axis)) {
         leaves[j] = leaves[j - 1];
         --j;
       }
       leaves[j] = k;
     }
+#undef KEY
+#undef SWAPL
     size_t half = n / 2;
     int l = bb_build(B, leaves, half);
     int r = bb_build(B, leaves + half, n - half);
