@@ -24,7 +24,8 @@ CXX="${REF_CXX:-/usr/bin/g++}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 
 # ---- host library (runs anywhere): pins oracle/oracle.c against the real implementation
-"$CXX" -std=c++20 -O2 -fPIC -shared -fvisibility=hidden \
+# -mfma -ffp-contract=fast: same contraction policy as the oracle and as nvcc on the device
+"$CXX" -std=c++20 -O2 -mfma -ffp-contract=fast -fPIC -shared -fvisibility=hidden \
   -I "$HERE/ref_shim" -I "$REF/src/lib" -I "$REF/src" \
   -o "$OUT/libref_host.so" "$HERE/ref_host_wrap.cpp"
 
