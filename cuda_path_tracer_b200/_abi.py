@@ -91,6 +91,9 @@ SYMBOLS = {
     "pt_scene_destroy": (C.c_int, [VP]),
     "pt_scene_get_info": (C.c_int, [VP, C.POINTER(pt_scene_info)]),
     "pt_scene_load_file": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(VP), C.POINTER(pt_scene_file_info)]),
+    "pt_scene_file_read": (C.c_int, [C.c_char_p, C.POINTER(VP), C.POINTER(pt_scene_desc),
+                                     C.POINTER(pt_scene_file_info)]),
+    "pt_scene_file_free": (C.c_int, [VP]),
     "pt_params_default": (None, [C.POINTER(pt_params)]),
     "pt_denoise_params_default": (None, [C.POINTER(pt_denoise_params)]),
     "pt_ctx_create": (C.c_int, [VP, C.c_uint32, C.c_uint32, C.POINTER(pt_params), VP, C.POINTER(VP)]),

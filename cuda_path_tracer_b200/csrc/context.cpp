@@ -238,6 +238,51 @@ int pt_scene_get_info(const pt_scene* sc, pt_scene_info* info)
   return PT_OK;
 }
 
+static void desc_from_file(const SceneFile& sf, pt_scene_desc& d)
+{
+  d = pt_scene_desc{};
+  d.positions = sf.positions.data();
+  d.n_vertices = sf.positions.size() / 3;
+  d.indices = sf.indices.data();
+  d.n_indices = sf.indices.size();
+  d.objects = sf.objects.data();
+  d.n_objects = (uint32_t)sf.objects.size();
+  d.spheres = sf.spheres.data();
+  d.n_spheres = (uint32_t)sf.spheres.size();
+  d.materials = sf.materials.data();
+  d.n_materials = (uint32_t)sf.materials.size();
+}
+
+int pt_scene_file_read(const char* json_path, pt_scene_file** out, pt_scene_desc* desc,
+                       pt_scene_file_info* info)
+{
+  if (!json_path || !out || !desc) return fail(PT_ERR_INVALID, "pt_scene_file_read: null argument");
+  *out = nullptr;
+  const double t0 = now_ms();
+  auto* f = new pt_scene_file();
+  const int rc = load_scene_file(json_path, f->sf);
+  if (rc != PT_OK) {
+    delete f;
+    return rc;
+  }
+  desc_from_file(f->sf, *desc);
+  if (info) {
+    info->camera = f->sf.camera;
+    info->width = f->sf.width;
+    info->height = f->sf.height;
+    info->spp = f->sf.spp;
+    info->load_ms = now_ms() - t0;
+  }
+  *out = f;
+  return PT_OK;
+}
+
+int pt_scene_file_free(pt_scene_file* f)
+{
+  delete f;
+  return PT_OK;
+}
+
 int pt_scene_load_file(const char* json_path, int device, pt_scene** out, pt_scene_file_info* info)
 {
   if (!json_path || !out) return fail(PT_ERR_INVALID, "pt_scene_load_file: null argument");
@@ -778,19 +823,23 @@ int pt_trace_batch(const pt_scene* sc, const float* rays8, uint64_t n, pt_hit* h
   PT_CUDA(cudaSetDevice(sc->device));
   float4* d_rays = nullptr;
   HitRecord* d_hits = nullptr;
+  uint32_t* d_work = nullptr;
   cudaError_t e = cudaMalloc((void**)&d_rays, n * 32);
   if (e == cudaSuccess) e = cudaMalloc((void**)&d_hits, n * sizeof(HitRecord));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_work, sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMemset(d_work, 0, sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMemcpy(d_rays, rays8, n * 32, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
-    cudaDeviceProp prop;
-    cudaGetDeviceProperties(&prop, sc->device);
-    const LaunchEnv env{nullptr, prop.multiProcessorCount};
-    launch_trace_batch(env, sc->dev, d_rays, (uint32_t)n, d_hits);
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, sc->device);
+    const LaunchEnv env{nullptr, sms};
+    launch_trace_batch(env, sc->dev, d_rays, d_work, (uint32_t)n, d_hits);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpy(hits_out, d_hits, n * sizeof(HitRecord), cudaMemcpyDeviceToHost);
   cudaFree(d_rays);
   cudaFree(d_hits);
+  cudaFree(d_work);
   if (e != cudaSuccess) return cuda_fail(e, "pt_trace_batch");
   return PT_OK;
 }

@@ -47,6 +47,10 @@ int load_obj_file(const char* path, std::vector<float>& positions, std::vector<u
 
 } // namespace pt
 
+struct pt_scene_file {
+  pt::SceneFile sf;
+};
+
 struct pt_scene {
   int device = 0;
   pt::DevScene dev{};

@@ -98,131 +98,146 @@ PT_D bool sphere_test(const DevSphere* __restrict__ sp, f3 o, f3 d, float tmin, 
 }
 
 // ---------------------------------------------------------------- traversal
-// Closest hit over spheres + the world-space BVH.  Result-equivalent to the
-// reference's un-culled traversal (a culled subtree cannot hold a nearer
-// accepted hit); exact-tie winners may differ (reference: last tested wins).
-PT_D bool trace_closest(const DevScene& sc, f3 o, f3 d, float tmin, float tmax, Hit& h)
-{
-  bool hit = false;
-  float tbest = tmax;
+// Closest hit over spheres + the world-space BVH, result-equivalent to the reference's
+// un-culled traversal (a culled subtree cannot hold a nearer accepted hit); exact-tie
+// winners may differ (reference: last tested wins).  The traversal is written as a
+// resumable per-lane state machine (init / step / finish) so that a persistent warp can
+// retire finished lanes and refill them with new rays while the others keep walking.
+struct Trav {
+  f3 o, d;
+  float tmin, tbest;
+  float idx, idy, idz, odx, ody, odz;
+  int node; // current node, PT_SENTINEL when done
+  int sp;
+  int best;   // best triangle slot or -1
+  bool hit;   // a sphere tested before the mesh was hit (record in `h`)
+  Hit h;
+};
 
+PT_D void trav_init(const DevScene& sc, Trav& T, f3 o, f3 d, float tmin, float tmax, int* stack)
+{
+  T.o = o;
+  T.d = d;
+  T.tmin = tmin;
+  T.tbest = tmax;
+  T.hit = false;
+  T.best = -1;
   for (uint32_t i = 0; i < sc.n_spheres_before; ++i) {
-    if (sphere_test(sc.spheres + i, o, d, tmin, tbest, h)) {
-      hit = true;
-      tbest = h.t;
+    if (sphere_test(sc.spheres + i, o, d, tmin, T.tbest, T.h)) {
+      T.hit = true;
+      T.tbest = T.h.t;
     }
   }
+  const float ooeps = 8.271806125530277e-25f; // 2^-80
+  T.idx = 1.0f / (fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x));
+  T.idy = 1.0f / (fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y));
+  T.idz = 1.0f / (fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z));
+  T.odx = o.x * T.idx;
+  T.ody = o.y * T.idy;
+  T.odz = o.z * T.idz;
+  stack[0] = PT_SENTINEL;
+  T.sp = 1;
+  T.node = sc.n_tris != 0 ? 0 : PT_SENTINEL;
+}
 
-  if (sc.n_tris != 0) {
-    const float ooeps = 8.271806125530277e-25f; // 2^-80
-    const float idx = 1.0f / (fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x));
-    const float idy = 1.0f / (fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y));
-    const float idz = 1.0f / (fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z));
-    const float odx = o.x * idx, ody = o.y * idy, odz = o.z * idz;
-
-    int stack[PT_STACK];
-    int sp = 0;
-    stack[sp++] = PT_SENTINEL;
-    int node = 0;
-    int best = -1;
-
-    while (node != PT_SENTINEL) {
-      // ---- inner nodes
-      while (node >= 0 && node != PT_SENTINEL) {
-        const float4* np = sc.nodes + (size_t)node * 4;
-        const float4 n0 = ldg4(np + 0);
-        const float4 n1 = ldg4(np + 1);
-        const float4 n2 = ldg4(np + 2);
-        const float4 n3 = ldg4(np + 3);
-        const float c0lox = n0.x * idx - odx, c0hix = n0.y * idx - odx;
-        const float c0loy = n0.z * idy - ody, c0hiy = n0.w * idy - ody;
-        const float c0loz = n2.x * idz - odz, c0hiz = n2.y * idz - odz;
-        const float c1lox = n1.x * idx - odx, c1hix = n1.y * idx - odx;
-        const float c1loy = n1.z * idy - ody, c1hiy = n1.w * idy - ody;
-        const float c1loz = n2.z * idz - odz, c1hiz = n2.w * idz - odz;
-        const float c0min =
-            fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), tmin));
-        const float c0max =
-            fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), tbest));
-        const float c1min =
-            fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), tmin));
-        const float c1max =
-            fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), tbest));
-        // robust slab comparison (Ize 2013): widen the far side by 2 ulp
-        const bool trav0 = c0max * 1.0000004f >= c0min;
-        const bool trav1 = c1max * 1.0000004f >= c1min;
-        const int c0 = __float_as_int(n3.x);
-        const int c1 = __float_as_int(n3.y);
-        if (!trav0 && !trav1) {
-          node = stack[--sp];
-        } else {
-          node = trav0 ? c0 : c1;
-          if (trav0 && trav1) {
-            int other = c1;
-            if (c1min < c0min) {
-              other = c0;
-              node = c1;
-            }
-            stack[sp++] = other;
-          }
+// One node visit: an inner node (two slab tests, ordered descent, far child pushed) or a
+// leaf (<= 4 Moller-Trumbore tests in the reference's operation order, intersections.cuh:49-85).
+PT_D void trav_step(const DevScene& sc, Trav& T, int* stack)
+{
+  if (T.node >= 0) {
+    const float4* np = sc.nodes + (size_t)T.node * 4;
+    const float4 n0 = ldg4(np + 0);
+    const float4 n1 = ldg4(np + 1);
+    const float4 n2 = ldg4(np + 2);
+    const float4 n3 = ldg4(np + 3);
+    const float c0lox = n0.x * T.idx - T.odx, c0hix = n0.y * T.idx - T.odx;
+    const float c0loy = n0.z * T.idy - T.ody, c0hiy = n0.w * T.idy - T.ody;
+    const float c0loz = n2.x * T.idz - T.odz, c0hiz = n2.y * T.idz - T.odz;
+    const float c1lox = n1.x * T.idx - T.odx, c1hix = n1.y * T.idx - T.odx;
+    const float c1loy = n1.z * T.idy - T.ody, c1hiy = n1.w * T.idy - T.ody;
+    const float c1loz = n2.z * T.idz - T.odz, c1hiz = n2.w * T.idz - T.odz;
+    const float c0min =
+        fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), T.tmin));
+    const float c0max =
+        fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), T.tbest));
+    const float c1min =
+        fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), T.tmin));
+    const float c1max =
+        fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), T.tbest));
+    // robust slab comparison (Ize 2013): widen the far side by 2 ulp
+    const bool trav0 = c0max * 1.0000004f >= c0min;
+    const bool trav1 = c1max * 1.0000004f >= c1min;
+    const int c0 = __float_as_int(n3.x);
+    const int c1 = __float_as_int(n3.y);
+    if (!trav0 && !trav1) {
+      T.node = stack[--T.sp];
+    } else {
+      T.node = trav0 ? c0 : c1;
+      if (trav0 && trav1) {
+        int other = c1;
+        if (c1min < c0min) {
+          other = c0;
+          T.node = c1;
         }
-      }
-      // ---- leaf
-      if (node < 0) {
-        const uint32_t code = (uint32_t)(~node);
-        const uint32_t first = code >> 3;
-        const uint32_t count = (code & 7u) + 1u;
-        for (uint32_t k = 0; k < count; ++k) {
-          const float4* tp = sc.tris + (size_t)(first + k) * 3;
-          const float4 t0 = ldg4(tp + 0);
-          const float4 t1 = ldg4(tp + 1);
-          const float4 t2 = ldg4(tp + 2);
-          // Moller-Trumbore in the reference's operation order (intersections.cuh:49-85)
-          const f3 e1 = xyz(t1), e2 = xyz(t2);
-          const f3 hh = cross3(d, e2);
-          const float a = dot3(e1, hh);
-          if (a > -0.0000001f && a < 0.0000001f) continue;
-          const float f = 1.0f / a;
-          const f3 s = o - xyz(t0);
-          const float u = f * dot3(s, hh);
-          if (u < 0.0f || u > 1.0f) continue;
-          const f3 q = cross3(s, e1);
-          const float v = f * dot3(d, q);
-          if (v < 0.0f || u + v > 1.0f) continue;
-          const float t = f * dot3(e2, q);
-          if (!(t >= tmin && t <= tbest)) continue;
-          tbest = t;
-          best = (int)(first + k);
-        }
-        node = stack[--sp];
+        stack[T.sp++] = other;
       }
     }
-
-    if (best >= 0) {
-      const float4* tp = sc.tris + (size_t)best * 3;
+  } else {
+    const uint32_t code = (uint32_t)(~T.node);
+    const uint32_t first = code >> 3;
+    const uint32_t count = (code & 7u) + 1u;
+    for (uint32_t k = 0; k < count; ++k) {
+      const float4* tp = sc.tris + (size_t)(first + k) * 3;
       const float4 t0 = ldg4(tp + 0);
       const float4 t1 = ldg4(tp + 1);
       const float4 t2 = ldg4(tp + 2);
-      const f3 outward = normalize3(cross3(xyz(t1), xyz(t2))); // triangle_normal
-      const bool front = dot3(d, outward) < 0.0f;
-      h.t = tbest;
-      h.p = o + d * tbest; // ray(t)
-      h.n = front ? outward : -outward;
-      h.side = front ? 0u : 1u;
-      h.prim = __float_as_int(t0.w);
-      h.object = __float_as_int(t1.w);
-      h.material = (uint32_t)__float_as_int(t2.w);
-      hit = true;
+      const f3 e1 = xyz(t1), e2 = xyz(t2);
+      const f3 hh = cross3(T.d, e2);
+      const float a = dot3(e1, hh);
+      if (a > -0.0000001f && a < 0.0000001f) continue;
+      const float f = 1.0f / a;
+      const f3 s = T.o - xyz(t0);
+      const float u = f * dot3(s, hh);
+      if (u < 0.0f || u > 1.0f) continue;
+      const f3 q = cross3(s, e1);
+      const float v = f * dot3(T.d, q);
+      if (v < 0.0f || u + v > 1.0f) continue;
+      const float t = f * dot3(e2, q);
+      if (!(t >= T.tmin && t <= T.tbest)) continue;
+      T.tbest = t;
+      T.best = (int)(first + k);
     }
+    T.node = stack[--T.sp];
   }
+}
 
+// Builds the Intersection of the winning primitive (triangle_normal + face side,
+// intersections.cuh:43-85) and tests the spheres that follow the first mesh object.
+PT_D bool trav_finish(const DevScene& sc, Trav& T)
+{
+  if (T.best >= 0) {
+    const float4* tp = sc.tris + (size_t)T.best * 3;
+    const float4 t0 = ldg4(tp + 0);
+    const float4 t1 = ldg4(tp + 1);
+    const float4 t2 = ldg4(tp + 2);
+    const f3 outward = normalize3(cross3(xyz(t1), xyz(t2)));
+    const bool front = dot3(T.d, outward) < 0.0f;
+    T.h.t = T.tbest;
+    T.h.p = T.o + T.d * T.tbest; // ray(t)
+    T.h.n = front ? outward : -outward;
+    T.h.side = front ? 0u : 1u;
+    T.h.prim = __float_as_int(t0.w);
+    T.h.object = __float_as_int(t1.w);
+    T.h.material = (uint32_t)__float_as_int(t2.w);
+    T.hit = true;
+  }
   for (uint32_t i = sc.n_spheres_before; i < sc.n_spheres; ++i) {
-    if (sphere_test(sc.spheres + i, o, d, tmin, tbest, h)) {
-      hit = true;
-      tbest = h.t;
+    if (sphere_test(sc.spheres + i, T.o, T.d, T.tmin, T.tbest, T.h)) {
+      T.hit = true;
+      T.tbest = T.h.t;
     }
   }
-  return hit;
+  return T.hit;
 }
 
 // ------------------------------------------------------ bounce-0 index map
@@ -243,62 +258,124 @@ PT_D bool first_item(const PassParams& pp, uint32_t idx, uint32_t& pid, uint32_t
 }
 
 // =================================================================== extend
+// Persistent warps (grid = SMs x resident CTAs).  Each lane owns one ray at a time.  Work is
+// fetched from a device-side cursor with ONE atomic per refill for all idle lanes of the warp;
+// lanes that finish early are retired and refilled as soon as fewer than EXT_REFILL lanes are
+// still walking, so the warp stays populated although per-ray traversal lengths vary by orders
+// of magnitude (sky rays leave after the root; silhouette rays visit dozens of nodes).
 #define EXT_THREADS 128
-#define EXT_BLOCKS_PER_SM 4
+#define EXT_MIN_BLOCKS 8
+#define EXT_REFILL 22
 
-template <bool FIRST>
-__global__ void __launch_bounds__(EXT_THREADS, EXT_BLOCKS_PER_SM)
+enum { SRC_FIRST = 0, SRC_QUEUE = 1, SRC_BATCH = 2 };
+
+template <int SRC>
+__global__ void __launch_bounds__(EXT_THREADS, EXT_MIN_BLOCKS)
 extend_kernel(const DevScene sc, const PathState ps, const PassParams pp,
               const uint32_t* __restrict__ queue, const uint32_t* __restrict__ n_ptr,
-              uint32_t n_first, uint32_t* __restrict__ work)
+              uint32_t n_host, uint32_t* __restrict__ work, const float4* __restrict__ batch_rays,
+              HitRecord* __restrict__ batch_out)
 {
-  const uint32_t n = FIRST ? n_first : *n_ptr;
+  const uint32_t n = SRC == SRC_QUEUE ? *n_ptr : n_host;
   const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  int stack[PT_STACK];
+  Trav T;
+  T.node = PT_SENTINEL;
+  bool has = false;
+  bool exhausted = false; // warp-uniform
+  uint32_t pid = 0;
+
   for (;;) {
-    // warp-level persistent work fetch: one atomic per 32 rays
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(work, 32u);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= n) break;
-    const uint32_t idx = base + lane;
-    if (idx >= n) continue;
-
-    uint32_t pid;
-    f3 o, d;
-    float tmin, tmax;
-    if (FIRST) {
-      uint32_t x, y, s;
-      if (!first_item(pp, idx, pid, x, y, s)) continue;
-      // raygen_kernel (ray_gen.cu:11-32)
-      const uint32_t pixel = y * pp.cam.width + x;
-      uint32_t rng = minstd_seed(wang_hash(wang_hash(pixel) ^ (pp.first_iteration + s)));
-      const float fx = (float)x + minstd_uniform(rng);
-      const float fy = (float)y + minstd_uniform(rng);
-      camera_ray(pp.cam, fx, fy, o, d);
-      tmin = 1e-4f;
-      tmax = FLT_MAX;
-      ps.ray_o[pid] = mk4(o, tmin);
-      ps.ray_d[pid] = mk4(d, tmax);
-      ps.thr[pid] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(rng));
-    } else {
-      pid = queue[idx];
-      const float4 ro = ps.ray_o[pid];
-      const float4 rd = ps.ray_d[pid];
-      o = xyz(ro);
-      d = xyz(rd);
-      tmin = ro.w;
-      tmax = rd.w;
+    // ---- refill idle lanes: one atomic per warp
+    const uint32_t need = __ballot_sync(0xffffffffu, !has);
+    if (need != 0u && !exhausted) {
+      const uint32_t cnt = (uint32_t)__popc(need);
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(work, cnt);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (base + cnt >= n) exhausted = true;
+      if (!has) {
+        const uint32_t idx = base + (uint32_t)__popc(need & lt_mask);
+        if (idx < n) {
+          f3 o, d;
+          float tmin, tmax;
+          bool valid = true;
+          if (SRC == SRC_FIRST) {
+            uint32_t x, y, s;
+            valid = first_item(pp, idx, pid, x, y, s);
+            if (valid) {
+              // raygen_kernel (ray_gen.cu:11-32)
+              const uint32_t pixel = y * pp.cam.width + x;
+              uint32_t rng = minstd_seed(wang_hash(wang_hash(pixel) ^ (pp.first_iteration + s)));
+              const float fx = (float)x + minstd_uniform(rng);
+              const float fy = (float)y + minstd_uniform(rng);
+              camera_ray(pp.cam, fx, fy, o, d);
+              tmin = 1e-4f;
+              tmax = FLT_MAX;
+              ps.ray_o[pid] = mk4(o, tmin);
+              ps.ray_d[pid] = mk4(d, tmax);
+              ps.thr[pid] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(rng));
+            }
+          } else if (SRC == SRC_QUEUE) {
+            pid = queue[idx];
+            const float4 ro = ps.ray_o[pid];
+            const float4 rd = ps.ray_d[pid];
+            o = xyz(ro), d = xyz(rd);
+            tmin = ro.w, tmax = rd.w;
+          } else {
+            pid = idx;
+            const float4 ro = batch_rays[2 * (size_t)idx], rd = batch_rays[2 * (size_t)idx + 1];
+            o = xyz(ro), d = xyz(rd);
+            tmin = ro.w, tmax = rd.w;
+          }
+          if (valid) {
+            trav_init(sc, T, o, d, tmin, tmax, stack);
+            has = true;
+          }
+        }
+      }
     }
-
-    Hit h;
-    if (trace_closest(sc, o, d, tmin, tmax, h)) {
-      ps.hit_a[pid] = make_float4(h.t, h.p.x, h.p.y, h.p.z);
-      ps.hit_b[pid] = mk4(h.n, __uint_as_float(h.material | (h.side << 31)));
-    } else {
-      ps.hit_a[pid] = make_float4(-1.0f, 0.f, 0.f, 0.f);
+    if (__ballot_sync(0xffffffffu, has) == 0u) {
+      if (exhausted) break;
+      continue;
+    }
+    // ---- walk until too few lanes are still busy (all of them once the queue is drained)
+    const int threshold = exhausted ? 1 : EXT_REFILL;
+    for (;;) {
+      const bool busy = has && T.node != PT_SENTINEL;
+      if (__popc(__ballot_sync(0xffffffffu, busy)) < threshold) break;
+      if (busy) trav_step(sc, T, stack);
+    }
+    // ---- retire finished lanes
+    if (has && T.node == PT_SENTINEL) {
+      const bool hit = trav_finish(sc, T);
+      if (SRC == SRC_BATCH) {
+        HitRecord r;
+        if (hit) {
+          r.t = T.h.t;
+          r.px = T.h.p.x, r.py = T.h.p.y, r.pz = T.h.p.z;
+          r.nx = T.h.n.x, r.ny = T.h.n.y, r.nz = T.h.n.z;
+          r.material = T.h.material, r.side = T.h.side;
+          r.object = T.h.object, r.prim = T.h.prim;
+        } else {
+          r.t = -1.0f;
+          r.px = r.py = r.pz = r.nx = r.ny = r.nz = 0.f;
+          r.material = 0, r.side = 0, r.object = -1, r.prim = -1;
+        }
+        r.pad = 0;
+        batch_out[pid] = r;
+      } else if (hit) {
+        ps.hit_a[pid] = make_float4(T.h.t, T.h.p.x, T.h.p.y, T.h.p.z);
+        ps.hit_b[pid] = mk4(T.h.n, __uint_as_float(T.h.material | (T.h.side << 31)));
+      } else {
+        ps.hit_a[pid] = make_float4(-1.0f, 0.f, 0.f, 0.f);
+      }
+      has = false;
     }
   }
 }
+
 
 // ==================================================================== shade
 #define SHD_THREADS 256
@@ -725,53 +802,38 @@ atrous_kernel(const DevCamera cam, const DenoiseParams dp, const float4* __restr
   color_out[p] = make_float4(sum.x / cum_w, sum.y / cum_w, sum.z / cum_w, 0.f);
 }
 
-// ============================================================== trace batch
-__global__ void __launch_bounds__(EXT_THREADS, EXT_BLOCKS_PER_SM)
-trace_batch_kernel(const DevScene sc, const float4* __restrict__ rays, uint32_t n,
-                   HitRecord* __restrict__ out)
-{
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float4 ro = rays[2 * (size_t)i], rd = rays[2 * (size_t)i + 1];
-  Hit h;
-  HitRecord r;
-  if (trace_closest(sc, xyz(ro), xyz(rd), ro.w, rd.w, h)) {
-    r.t = h.t;
-    r.px = h.p.x, r.py = h.p.y, r.pz = h.p.z;
-    r.nx = h.n.x, r.ny = h.n.y, r.nz = h.n.z;
-    r.material = h.material;
-    r.side = h.side;
-    r.object = h.object;
-    r.prim = h.prim;
-  } else {
-    r.t = -1.0f;
-    r.px = r.py = r.pz = r.nx = r.ny = r.nz = 0.f;
-    r.material = 0;
-    r.side = 0;
-    r.object = -1;
-    r.prim = -1;
-  }
-  r.pad = 0;
-  out[i] = r;
-}
-
 // ================================================================ launchers
 static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+
+// persistent grid: SMs x the number of CTAs the kernel can keep resident per SM
+template <int SRC> static uint32_t extend_grid(const LaunchEnv& env)
+{
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extend_kernel<SRC>, EXT_THREADS, 0) !=
+            cudaSuccess ||
+        nb <= 0)
+      nb = EXT_MIN_BLOCKS;
+    per_sm = nb;
+  }
+  return (uint32_t)(env.sms * per_sm);
+}
 
 void launch_extend_first(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb,
                          const PassParams& pp, uint32_t n_items)
 {
-  const uint32_t grid = min((uint32_t)(env.sms * EXT_BLOCKS_PER_SM), cdiv(n_items, EXT_THREADS));
-  extend_kernel<true><<<grid, EXT_THREADS, 0, env.stream>>>(sc, pb.ps, pp, nullptr, nullptr,
-                                                            n_items, pb.work + 0);
+  const uint32_t grid = min(extend_grid<SRC_FIRST>(env), cdiv(n_items, EXT_THREADS));
+  extend_kernel<SRC_FIRST><<<grid, EXT_THREADS, 0, env.stream>>>(
+      sc, pb.ps, pp, nullptr, nullptr, n_items, pb.work + 0, nullptr, nullptr);
 }
 
 void launch_extend(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb,
                    const PassParams& pp, int q, uint32_t bounce)
 {
-  const uint32_t grid = env.sms * EXT_BLOCKS_PER_SM;
-  extend_kernel<false><<<grid, EXT_THREADS, 0, env.stream>>>(
-      sc, pb.ps, pp, pb.queue[q], pb.counters + bounce, 0u, pb.work + bounce);
+  const uint32_t grid = extend_grid<SRC_QUEUE>(env);
+  extend_kernel<SRC_QUEUE><<<grid, EXT_THREADS, 0, env.stream>>>(
+      sc, pb.ps, pp, pb.queue[q], pb.counters + bounce, 0u, pb.work + bounce, nullptr, nullptr);
 }
 
 void launch_shade(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb,
@@ -853,10 +915,13 @@ void launch_atrous(const LaunchEnv& env, const DevCamera& cam, const DenoisePara
                                               color_out, step_width);
 }
 
-void launch_trace_batch(const LaunchEnv& env, const DevScene& sc, const float4* rays,
+void launch_trace_batch(const LaunchEnv& env, const DevScene& sc, const float4* rays, uint32_t* work,
                         uint32_t n, HitRecord* out)
 {
-  trace_batch_kernel<<<cdiv(n, EXT_THREADS), EXT_THREADS, 0, env.stream>>>(sc, rays, n, out);
+  // the parity hook runs the SAME persistent traversal kernel as the renderer
+  const uint32_t grid = min(extend_grid<SRC_BATCH>(env), cdiv(n, EXT_THREADS));
+  extend_kernel<SRC_BATCH><<<grid, EXT_THREADS, 0, env.stream>>>(
+      sc, PathState{}, PassParams{}, nullptr, nullptr, n, work, rays, out);
 }
 
 } // namespace pt

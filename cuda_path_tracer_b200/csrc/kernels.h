@@ -69,7 +69,7 @@ struct HitRecord {
   int32_t object, prim;
   uint32_t pad;
 };
-void launch_trace_batch(const LaunchEnv& env, const DevScene& sc, const float4* rays,
+void launch_trace_batch(const LaunchEnv& env, const DevScene& sc, const float4* rays, uint32_t* work,
                         uint32_t n, HitRecord* out);
 
 } // namespace pt

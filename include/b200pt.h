@@ -207,6 +207,14 @@ PT_API int pt_scene_get_info(const pt_scene* scene, pt_scene_info* info);
 PT_API int pt_scene_load_file(const char* json_path, int device, pt_scene** out,
                               pt_scene_file_info* info);
 
+/* Host-only half of the above (no CUDA call): parse a scene file into the flat
+ * description.  *desc points into memory owned by the returned handle; free it
+ * with pt_scene_file_free.  == scene_from_json (assets/json_parser.cpp:174-224). */
+typedef struct pt_scene_file pt_scene_file;
+PT_API int pt_scene_file_read(const char* json_path, pt_scene_file** out, pt_scene_desc* desc,
+                              pt_scene_file_info* info);
+PT_API int pt_scene_file_free(pt_scene_file* f);
+
 /* --- integrator context: replaces class PathTracer -------------------------- */
 PT_API void pt_params_default(pt_params* p);
 PT_API void pt_denoise_params_default(pt_denoise_params* p);

@@ -1,0 +1,184 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/b200pt.h declares,
+the host scene reader (JSON + OBJ) follows the reference's grammar, host transform math."""
+import ctypes as C
+import json
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+import cuda_path_tracer_b200 as pt
+from cuda_path_tracer_b200 import _abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "b200pt.h")).read()
+    declared = set(re.findall(r"PT_API\s+[\w\s\*]+?\b(pt_\w+)\s*\(", hdr))
+    assert len(declared) >= 30
+    lib = pt.load_library()
+    for name in declared:
+        assert hasattr(lib, name), f"libb200pt.so does not export {name}"
+    assert declared == set(_abi.SYMBOLS), declared ^ set(_abi.SYMBOLS)
+    assert lib.pt_version() >= 100
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(_abi.pt_hit) == 48
+    assert C.sizeof(_abi.pt_camera) == 32
+    assert C.sizeof(_abi.pt_material) == 24
+    assert C.sizeof(_abi.pt_object) == 12 + 128
+    p = _abi.pt_params()
+    pt.load_library().pt_params_default(C.byref(p))
+    assert p.max_depth == 50 and p.rng_mode == 0          # max_bounces = 50 (path_tracer.cu:27)
+    d = _abi.pt_denoise_params()
+    pt.load_library().pt_denoise_params_default(C.byref(d))
+    assert (d.filter_size, round(d.color_weight, 2), round(d.normal_weight, 2), round(d.position_weight, 2)) == \
+        (10, 0.45, 0.30, 0.25)                             # edge_avoiding_a_trous_denoiser.hpp:9-12
+
+
+def test_no_compute_without_gpu_fails_loudly():
+    """The product must not fall back to a CPU path: without a device, scene creation errors."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(pt.PTError):
+        pt.Scene.from_description(pt.three_balls(8, 8))
+
+
+def _read(path):
+    lib = pt.load_library()
+    h = C.c_void_p()
+    desc = _abi.pt_scene_desc()
+    info = _abi.pt_scene_file_info()
+    rc = lib.pt_scene_file_read(path.encode(), C.byref(h), C.byref(desc), C.byref(info))
+    return rc, h, desc, info
+
+
+def _write_scene(tmp_path, scene_json, mesh=None):
+    (tmp_path / "scenes").mkdir(exist_ok=True)
+    (tmp_path / "models").mkdir(exist_ok=True)
+    if mesh is not None:
+        pt.write_obj(str(tmp_path / "models" / "bunny.obj"), mesh)
+    p = tmp_path / "scenes" / "scene.json"
+    p.write_text(json.dumps(scene_json))
+    return str(p)
+
+
+BUNNY_JSON = {
+    "camera": {"vfov": 60, "resolution": [1920, 1080]},
+    "sampler": {"type": "independent", "samples": 10},
+    "background": [1, 1, 1],
+    "materials": [{"type": "lambertian", "name": "ground", "albedo": [0.8, 0.8, 0.8]},
+                  {"type": "lambertian", "name": "bunny", "albedo": [0.8, 0.8, 0.5]},
+                  {"type": "lambertian", "name": "bunny2", "albedo": [0.6, 0.4, 0.8]}],
+    "surfaces": [{"type": "sphere", "transform": {"translate": [0.0, -100.5, -1.0]}, "radius": 100.0,
+                  "material": "ground"},
+                 {"type": "mesh", "filename": "../models/bunny.obj",
+                  "transform": {"translate": [1.0, -0.5, -2.0]}, "material": "bunny"},
+                 {"type": "mesh", "filename": "../models/bunny.obj",
+                  "transform": [{"scale": 0.5}, {"translate": [-1.0, -0.5, -2.0]}], "material": "bunny2"}],
+}
+
+
+def test_scene_json_matches_reference_semantics(tmp_path):
+    """assets/scenes/bunny.json through the host reader == the Python SceneDescription mirror:
+    alphabetical material table, transform lists composed left to right, de-indexed OBJ."""
+    mesh = pt.bunny_like(1)
+    rc, h, d, info = _read(_write_scene(tmp_path, BUNNY_JSON, mesh))
+    assert rc == 0, pt.load_library().pt_last_error()
+    assert (info.width, info.height, info.spp) == (1920, 1080, 10)
+    assert math.isclose(info.camera.vfov, math.radians(60), rel_tol=1e-6)
+    assert list(info.camera.rotation) == [1, 0, 0, 0] and list(info.camera.position) == [0, 0, 0]
+    assert d.n_materials == 3 and d.n_objects == 3 and d.n_spheres == 1
+    # std::map order: bunny, bunny2, ground
+    assert [round(d.materials[i].albedo[2], 2) for i in range(3)] == [0.5, 0.8, 0.8]
+    assert [d.objects[i].material for i in range(3)] == [2, 0, 1]
+    assert d.n_indices == mesh.indices.size and d.n_vertices == mesh.positions.shape[0]
+    pos = np.ctypeslib.as_array(d.positions, shape=(d.n_vertices * 3,)).reshape(-1, 3)
+    assert np.allclose(pos, mesh.positions, rtol=1e-6, atol=1e-7)
+    ref = pt.bunny_scene(mesh)
+    rd, keep = ref.to_desc()
+    for i in range(3):
+        assert np.allclose(list(d.objects[i].m), list(rd.objects[i].m), atol=1e-6)
+        assert np.allclose(list(d.objects[i].inv), list(rd.objects[i].inv), atol=1e-5)
+        assert d.objects[i].type == rd.objects[i].type
+    pt.load_library().pt_scene_file_free(h)
+
+
+def test_camera_transform_decomposition(tmp_path):
+    """ajax-white.json style {from, at, up} camera -> position + quaternion (glm::decompose)."""
+    js = dict(BUNNY_JSON)
+    js["camera"] = {"transform": {"from": [6, 5.5, 0], "at": [0, 3.5, 0], "up": [0, 1, 0]}, "vfov": 80,
+                    "resolution": [720, 1280]}
+    rc, h, d, info = _read(_write_scene(tmp_path, js, pt.bunny_like(0)))
+    assert rc == 0
+    assert np.allclose(list(info.camera.position), [6, 5.5, 0], atol=1e-6)
+    ref = pt.Camera.look_at((6, 5.5, 0), (0, 3.5, 0), (0, 1, 0), 80)
+    q, qr = np.array(list(info.camera.rotation)), np.array(ref.rotation)
+    assert np.allclose(q, qr, atol=1e-5) or np.allclose(q, -qr, atol=1e-5)
+    js["camera"] = {"transform": [{"rotate": 90, "axis": [0, 1, 0]}, {"translate": [0, 0, 4]}], "vfov": 45,
+                    "resolution": [8, 8]}
+    rc, h2, d2, info2 = _read(_write_scene(tmp_path, js, pt.bunny_like(0)))
+    assert rc == 0 and np.allclose(list(info2.camera.position), [0, 0, 4], atol=1e-6)
+    assert np.allclose(np.abs(list(info2.camera.rotation)), [math.sqrt(.5), 0, math.sqrt(.5), 0], atol=1e-6)
+
+
+def test_scene_reader_errors(tmp_path):
+    lib = pt.load_library()
+    bad = dict(BUNNY_JSON)
+    bad["camera"] = {"transform": {"o": [0, 0, 4]}, "vfov": 45}     # three_balls.json:3-9 is rejected
+    rc, *_ = _read(_write_scene(tmp_path, bad, pt.bunny_like(0)))
+    assert rc == 4 and b"Unrecognized transform" in lib.pt_last_error()
+    bad = dict(BUNNY_JSON)
+    bad["materials"] = [{"type": "plastic", "name": "x"}]
+    rc, *_ = _read(_write_scene(tmp_path, bad, pt.bunny_like(0)))
+    assert rc == 4 and b"Unsupported material type" in lib.pt_last_error()
+    rc, *_ = _read(str(tmp_path / "nope.json"))
+    assert rc == 3
+    (tmp_path / "scenes" / "broken.json").write_text("{ \"camera\": ")
+    rc, *_ = _read(str(tmp_path / "scenes" / "broken.json"))
+    assert rc == 4
+
+
+def test_obj_reader_polygons_negative_indices_and_first_mesh(tmp_path):
+    (tmp_path / "scenes").mkdir()
+    (tmp_path / "models").mkdir()
+    (tmp_path / "models" / "bunny.obj").write_text(
+        "# quad + triangle, then a second object that must be ignored (aiScene::mMeshes[0])\n"
+        "v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvn 0 0 1\n"
+        "f 1//1 2//1 3//1 4//1\nf -4 -3 -2\no second\nv 5 5 5\nf 1 2 5\n")
+    (tmp_path / "scenes" / "scene.json").write_text(json.dumps(BUNNY_JSON))
+    rc, h, d, info = _read(str(tmp_path / "scenes" / "scene.json"))
+    assert rc == 0
+    assert d.n_indices == 9 and d.n_vertices == 9          # fan-triangulated quad + 1 triangle
+    pos = np.ctypeslib.as_array(d.positions, shape=(27,)).reshape(-1, 3)
+    assert np.array_equal(pos[3:6], [[0, 0, 0], [1, 1, 0], [0, 1, 0]])
+    assert np.array_equal(pos[6:9], [[0, 0, 0], [1, 0, 0], [1, 1, 0]])
+
+
+def test_png_writer_roundtrip(tmp_path):
+    from PIL import Image
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, size=(37, 53, 4), dtype=np.uint8)
+    path = str(tmp_path / "out.png")
+    pt.write_image_file(path, img)
+    back = np.asarray(Image.open(path))
+    assert back.shape == img.shape and np.array_equal(back, img)
+
+
+def test_python_scene_description_mirror():
+    s = pt.three_balls(64, 64)
+    d, keep = s.to_desc()
+    # alphabetical: blue, dielectric, ground, metal
+    assert [d.materials[i].type for i in range(4)] == [0, 2, 0, 1]
+    assert [d.objects[i].material for i in range(4)] == [2, 0, 1, 3]
+    m = pt.compose(pt.scale(0.5), pt.translate((-1.0, -0.5, -2.0)))
+    assert np.allclose(m @ np.array([2, 2, 2, 1], dtype=np.float32), [0, 0.5, -1, 1])
+    s.add_material("ground", pt.Material.lambertian((0, 0, 0)))      # duplicate keeps the first
+    assert s.materials["ground"].albedo == (0.8, 0.8, 0.0)
+    with pytest.raises(KeyError):
+        s.add_sphere(1.0, pt.translate((0, 0, 0)), "missing")
