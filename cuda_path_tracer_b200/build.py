@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200pt.so")
 EXE = os.path.join(HERE, "cuda_pt")
 
-SOURCES = ["kernels.cu", "context.cpp", "bvh_build.cpp", "hostmath.cpp", "scene_io.cpp", "cli.cpp"]
+SOURCES = ["wavefront.cu", "image_kernels.cu", "context.cpp", "bvh_build.cpp", "hostmath.cpp", "scene_io.cpp", "cli.cpp"]
 HEADERS = ["common.cuh", "kernels.h", "internal.h", "bvh_build.h", "../../include/b200pt.h"]
 
 NVCC_FLAGS = [

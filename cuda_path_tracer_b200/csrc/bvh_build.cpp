@@ -258,6 +258,12 @@ void build_bvh(const std::vector<BuildTri>& tris, FlatBVH& out)
 
   // ---- flatten: inner nodes in DFS pre-order, triangles in leaf order
   const bool root_is_leaf = B.nodes[root].count != 0;
+  for (int a = 0; a < 3; ++a) {
+    // padded twice: the classification test must never reject a ray a child box accepts
+    const float lo = B.nodes[root].box.lo[a], hi = B.nodes[root].box.hi[a];
+    out.root_lo[a] = pad_lo(pad_lo(lo, hi), hi);
+    out.root_hi[a] = pad_hi(lo, pad_hi(lo, hi));
+  }
   const bool need_null = root_is_leaf;
   out.n_tris = (uint32_t)n + (need_null ? 1u : 0u);
   out.tris.resize((size_t)out.n_tris * 12);

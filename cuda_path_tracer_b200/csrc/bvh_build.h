@@ -21,6 +21,7 @@ struct FlatBVH {
   uint32_t n_tris = 0; // including the trailing null triangle, if any
   uint32_t depth = 0;
   double sah_cost = 0.0;
+  float root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0}; // padded bounds of everything
 };
 
 // Binned-SAH (16 bins x 3 axes) top-down build, <= 4 triangles per leaf,

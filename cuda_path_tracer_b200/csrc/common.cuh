@@ -61,7 +61,11 @@ PT_HD uint32_t minstd_seed(uint32_t s)
 }
 PT_HD uint32_t minstd_next(uint32_t x)
 {
-  return (uint32_t)(((uint64_t)x * 48271ull) % 2147483647ull);
+  // (48271 x) mod (2^31 - 1) without a 64-bit division: 2^31 == 1 (mod M), so the product
+  // p = hi * 2^31 + lo reduces to hi + lo, minus M once if needed.  Exact.
+  const uint64_t p = (uint64_t)x * 48271ull;
+  uint32_t r = (uint32_t)(p & 0x7fffffffull) + (uint32_t)(p >> 31);
+  return r >= 2147483647u ? r - 2147483647u : r;
 }
 // thrust::uniform_real_distribution<float>(0,1): float(x - min) / (1 + float(max - min))
 // with min = 1, max = 2^31 - 2  ->  float(x - 1) / 2147483648.f
@@ -156,21 +160,25 @@ struct DevScene {
   uint32_t n_spheres_before; // spheres[0..n_before) precede the first mesh object
   uint32_t n_nodes;
   uint32_t n_tris;
+  float root_lo[3], root_hi[3]; // padded bounds of the whole mesh BVH (classification)
 };
 
-// Hit record written by extend and consumed by shade: 32 B.
-//   hit_a = (t | <0 miss, point.xyz)   hit_b = (normal.xyz, bits(material | side<<31))
-// Path state, all indexed by path id = sample_in_pass * pixels + pixel:
-//   ray_o = (origin.xyz, t_min)   ray_d = (direction.xyz, t_max)
-//   thr   = (throughput.rgb, bits(rng state))
-//   gbuf  = (first-hit normal.xyz, first-hit t)
+// Path state, all indexed by path id = sample_in_pass * pixels + pixel (64 B/path):
+//   ray[2*id]   = (origin.xyz, t_min)  ray[2*id+1] = (direction.xyz, t_max)
+//                 interleaved so that one gathered ray is ONE aligned 32-byte sector
+//   thr[id]     = (throughput.rgb, bits(rng state))
+//   gbuf[id]    = (first-hit normal.xyz, first-hit t)
+//   aux[id]     = intersection word: x = bits(t of the closest hit so far, else t_max),
+//                 y = code: bit31 triangle (low bits = triangle slot), bit30 "spheres after the
+//                 mesh still untested", else sphere index + 1, 0 = nothing hit;
+//                 z = BVH node at which traversal starts (classification walks the top levels).
+//                 Written by classification, refined by traverse, consumed by shade — it
+//                 replaces the reference's 48-byte Intersection record (intersection.hpp:8-14).
 struct PathState {
-  float4* ray_o;
-  float4* ray_d;
+  float4* ray;
   float4* thr;
-  float4* hit_a;
-  float4* hit_b;
   float4* gbuf;
+  uint4* aux;
 };
 
 // One wavefront pass = `samples` consecutive iterations of every pixel.

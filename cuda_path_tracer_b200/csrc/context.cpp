@@ -206,6 +206,10 @@ int pt_scene_create(const pt_scene_desc* desc, int device, pt_scene** out)
   sc->dev.n_spheres_before = (uint32_t)sph_before.size();
   sc->dev.n_nodes = bvh.n_nodes;
   sc->dev.n_tris = bvh.n_tris;
+  for (int a = 0; a < 3; ++a) {
+    sc->dev.root_lo[a] = bvh.root_lo[a];
+    sc->dev.root_hi[a] = bvh.root_hi[a];
+  }
   sc->info.n_triangles = n_tri;
   sc->info.n_world_triangles = n_world;
   sc->info.n_bvh_nodes = bvh.n_nodes;
@@ -320,6 +324,8 @@ static void free_image_buffers(pt_ctx* c)
   cudaFree(c->d_state);
   cudaFree(c->pb.queue[0]);
   cudaFree(c->pb.queue[1]);
+  cudaFree(c->pb.tq);
+  c->pb.tq = nullptr;
   cudaFree(c->pb.flags);
   cudaFree(c->pb.block_sums);
   if (c->own_sums) cudaFree(c->d_sums);
@@ -360,16 +366,15 @@ static int alloc_image_buffers(pt_ctx* c, uint32_t width, uint32_t height)
   const size_t cap = (size_t)c->pixels * spp_pass;
   if (cap > (1ull << 30)) return fail(PT_ERR_INVALID, "wavefront too large");
   c->pb.capacity = (uint32_t)cap;
-  PT_CUDA(cudaMalloc(&c->d_state, cap * sizeof(float4) * 6));
+  PT_CUDA(cudaMalloc(&c->d_state, cap * (sizeof(float4) * 4 + sizeof(uint4))));
   float4* base = (float4*)c->d_state;
-  c->pb.ps.ray_o = base + 0 * cap;
-  c->pb.ps.ray_d = base + 1 * cap;
+  c->pb.ps.ray = base + 0 * cap; // 2 float4 per path, interleaved
   c->pb.ps.thr = base + 2 * cap;
-  c->pb.ps.hit_a = base + 3 * cap;
-  c->pb.ps.hit_b = base + 4 * cap;
-  c->pb.ps.gbuf = base + 5 * cap;
+  c->pb.ps.gbuf = base + 3 * cap;
+  c->pb.ps.aux = (uint4*)(base + 4 * cap);
   PT_CUDA(cudaMalloc((void**)&c->pb.queue[0], cap * 4));
   PT_CUDA(cudaMalloc((void**)&c->pb.queue[1], cap * 4));
+  PT_CUDA(cudaMalloc((void**)&c->pb.tq, cap * 4));
   if (c->params.rng_mode == PT_RNG_SLOT_RESEED) {
     PT_CUDA(cudaMalloc((void**)&c->pb.flags, cap));
     PT_CUDA(cudaMalloc((void**)&c->pb.block_sums, ((cap + 2047) / 2048 + 1) * 4));
@@ -419,12 +424,13 @@ int pt_ctx_create(const pt_scene* scene, uint32_t width, uint32_t height, const 
     c->own_stream = true;
   }
   const size_t n_ctr = (size_t)p.max_depth + 2;
-  c->counters_bytes = n_ctr * 2 * sizeof(uint32_t);
+  c->counters_bytes = n_ctr * 3 * sizeof(uint32_t);
   int rc = PT_OK;
   do {
     if ((e = cudaMalloc(&c->d_counters, c->counters_bytes + 16)) != cudaSuccess) break;
     c->pb.counters = (uint32_t*)c->d_counters;
     c->pb.work = c->pb.counters + n_ctr;
+    c->pb.tcounters = c->pb.counters + 2 * n_ctr;
     c->pb.total_rays = (unsigned long long*)((char*)c->d_counters + ((c->counters_bytes + 7) & ~7ull));
     if ((e = cudaMemset(c->d_counters, 0, c->counters_bytes + 16)) != cudaSuccess) break;
     if ((e = cudaHostAlloc((void**)&c->h_counts, n_ctr * sizeof(uint32_t), cudaHostAllocDefault)) !=
@@ -579,17 +585,20 @@ static int render_pass(pt_ctx* c, const pt_camera& cam, uint32_t first_iteration
     const bool last = b + 1 == max_depth;
     if (b == 0) {
       prof_begin(c, TAG_EXT0);
-      launch_extend_first(env, c->scene->dev, c->pb, pp, n0);
+      launch_raygen(env, c->scene->dev, c->pb, pp, n0);
       prof_end(c);
-    } else {
+      launched += 1;
+    }
+    if (c->scene->dev.n_tris != 0) {
       prof_begin(c, TAG_EXT);
-      launch_extend(env, c->scene->dev, c->pb, pp, q, b);
+      launch_traverse(env, c->scene->dev, c->pb, b);
       prof_end(c);
+      launched += 1;
     }
     prof_begin(c, TAG_SHADE);
     launch_shade(env, c->scene->dev, c->pb, pp, q, b, n0, last);
     prof_end(c);
-    launched += 2;
+    launched += 1;
     if (stable && !last) {
       prof_begin(c, TAG_COMPACT);
       launch_stable_compact(env, c->pb, pp, q, b);

@@ -1,0 +1,368 @@
+// image_kernels.cu — per-pixel kernels: stable compaction (streaming-compat mode),
+// accumulate, resolve/tonemap, frame import/export, A-Trous denoiser.
+//   accumulate  final_gather                                 (reference path_tracer.cu:203-219, 317-330)
+//   resolve     preview kernels / linear_to_gamma            (path_tracer.cu:221-225, 334-385)
+//   atrous      denoising_kernel                             (denoising/...denoiser.cu:24-86)
+#include "kernels.h"
+
+#include <float.h>
+
+namespace pt {
+
+PT_D float4 ldg4(const float4* p) { return __ldg(p); }
+PT_D float4 mk4(f3 v, float w) { return make_float4(v.x, v.y, v.z, w); }
+
+// ========================================================= stable compaction
+// PT_RNG_SLOT_RESEED only: reproduces thrust::stable_partition's order of the
+// live paths (path_tracer.cu:454-457) on 4-byte ids instead of 65-byte records.
+#define SC_THREADS 256
+#define SC_ITEMS 2048 // per block
+
+__global__ void __launch_bounds__(SC_THREADS)
+sc_count_kernel(const uint8_t* __restrict__ flags, const uint32_t* __restrict__ n_ptr,
+                uint32_t n_first, uint32_t* __restrict__ block_sums)
+{
+  const uint32_t n = n_ptr ? *n_ptr : n_first;
+  const uint32_t begin = blockIdx.x * SC_ITEMS;
+  uint32_t c = 0;
+  for (uint32_t i = begin + threadIdx.x; i < begin + SC_ITEMS && i < n; i += SC_THREADS)
+    c += flags[i];
+  __shared__ uint32_t warp_sums[SC_THREADS / 32];
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t s = 0;
+    for (int w = 0; w < SC_THREADS / 32; ++w) s += warp_sums[w];
+    block_sums[blockIdx.x] = s;
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+sc_scan_kernel(uint32_t* __restrict__ block_sums, uint32_t n_blocks,
+               uint32_t* __restrict__ total_out)
+{
+  // single block exclusive scan, chunks of 1024
+  __shared__ uint32_t sh[1024];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < n_blocks; base += 1024) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = i < n_blocks ? block_sums[i] : 0u;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (uint32_t o = 1; o < 1024; o <<= 1) {
+      uint32_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0u;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    const uint32_t incl = sh[threadIdx.x];
+    if (i < n_blocks) block_sums[i] = carry + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(SC_THREADS)
+sc_scatter_kernel(const uint8_t* __restrict__ flags, const uint32_t* __restrict__ n_ptr,
+                  uint32_t n_first, const uint32_t* __restrict__ block_offsets,
+                  const uint32_t* __restrict__ queue, uint32_t* __restrict__ next_queue)
+{
+  const uint32_t n = n_ptr ? *n_ptr : n_first;
+  const uint32_t begin = blockIdx.x * SC_ITEMS;
+  __shared__ uint32_t warp_sums[SC_THREADS / 32];
+  __shared__ uint32_t running;
+  if (threadIdx.x == 0) running = block_offsets[blockIdx.x];
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  for (uint32_t chunk = begin; chunk < begin + SC_ITEMS; chunk += SC_THREADS) {
+    const uint32_t i = chunk + threadIdx.x;
+    const bool f = i < n && flags[i] != 0;
+    const uint32_t mask = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) warp_sums[warp] = __popc(mask);
+    __syncthreads();
+    uint32_t off = running;
+    for (uint32_t w = 0; w < warp; ++w) off += warp_sums[w];
+    if (f) next_queue[off + __popc(mask & ((1u << lane) - 1u))] = queue ? queue[i] : i;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t s = 0;
+      for (int w = 0; w < SC_THREADS / 32; ++w) s += warp_sums[w];
+      running += s;
+    }
+    __syncthreads();
+  }
+}
+
+// =============================================================== accumulate
+__global__ void __launch_bounds__(256)
+accumulate_kernel(const PathState ps, const PassParams pp, float4* __restrict__ sum_color,
+                  float4* __restrict__ sum_gbuf, uint32_t* __restrict__ counters,
+                  uint32_t n_first, uint32_t max_depth,
+                  unsigned long long* __restrict__ total_rays)
+{
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p == 0) {
+    // rays = live paths entering extend, summed over bounces (counters[0] is host-known)
+    unsigned long long r = (unsigned long long)pp.pixels * pp.samples;
+    for (uint32_t b = 1; b < max_depth; ++b) r += counters[b];
+    *total_rays += r;
+  }
+  if (p >= pp.pixels) return;
+  float4 c = sum_color[p];
+  float4 g = sum_gbuf[p];
+  for (uint32_t s = 0; s < pp.samples; ++s) {
+    const float4 t = ps.thr[(size_t)s * pp.pixels + p];
+    const float4 gb = ps.gbuf[(size_t)s * pp.pixels + p];
+    c.x += t.x;
+    c.y += t.y;
+    c.z += t.z;
+    g.x += gb.x;
+    g.y += gb.y;
+    g.z += gb.z;
+    g.w += gb.w;
+  }
+  c.w += (float)pp.samples;
+  sum_color[p] = c;
+  sum_gbuf[p] = g;
+}
+
+// ================================================================== resolve
+PT_D unsigned char to_255(float v)
+{
+  // static_cast<unsigned char>(glm::clamp(v, 0.f, 1.f) * 255.99f)
+  return (unsigned char)(fminf(fmaxf(v, 0.0f), 1.0f) * 255.99f);
+}
+
+PT_D f3 fetch_kind(int kind, const float4* sum_color, const float4* sum_gbuf,
+                   const float4* final_rgb, bool final_is_mean, uint32_t p, float& depth)
+{
+  const float4 c = sum_color[p];
+  const float inv_dummy = c.w; // sample count
+  depth = 0.f;
+  if (kind == 0 && final_is_mean) { // FINAL after denoise
+    const float4 f = final_rgb[p];
+    return mk3(f.x, f.y, f.z);
+  }
+  if (kind == 4) {
+    const float4 f = final_rgb[p];
+    return mk3(f.x, f.y, f.z);
+  }
+  if (kind == 0 || kind == 1) return mk3(c.x / inv_dummy, c.y / inv_dummy, c.z / inv_dummy);
+  const float4 g = sum_gbuf[p];
+  depth = g.w / inv_dummy;
+  return mk3(g.x / inv_dummy, g.y / inv_dummy, g.z / inv_dummy);
+}
+
+__global__ void __launch_bounds__(256)
+resolve_kernel(int kind, const float4* __restrict__ sum_color, const float4* __restrict__ sum_gbuf,
+               const float4* __restrict__ final_rgb, bool final_is_mean, uint32_t pixels,
+               uchar4* __restrict__ out)
+{
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= pixels) return;
+  float depth;
+  f3 c = fetch_kind(kind, sum_color, sum_gbuf, final_rgb, final_is_mean, p, depth);
+  unsigned char alpha = 255;
+  if (kind == 2) c = c * 0.5f + mk3(0.5f, 0.5f, 0.5f); // neg1_1_to_0_1
+  if (kind == 3) {                                     // preview_depth_kernel: 1/depth, alpha 1
+    c = mk3(1.0f / depth, 1.0f / depth, 1.0f / depth);
+    alpha = 1;
+  }
+  const float g = 1.0f / 2.2f;
+  c = mk3(powf(c.x, g), powf(c.y, g), powf(c.z, g)); // linear_to_gamma
+  out[p] = make_uchar4(to_255(c.x), to_255(c.y), to_255(c.z), alpha);
+}
+
+__global__ void __launch_bounds__(256)
+export_kernel(int kind, const float4* __restrict__ sum_color, const float4* __restrict__ sum_gbuf,
+              const float4* __restrict__ final_rgb, bool final_is_mean, uint32_t pixels,
+              float* __restrict__ out)
+{
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= pixels) return;
+  float depth;
+  const f3 c = fetch_kind(kind, sum_color, sum_gbuf, final_rgb, final_is_mean, p, depth);
+  if (kind == 3) {
+    out[p] = depth;
+  } else {
+    out[3 * (size_t)p + 0] = c.x;
+    out[3 * (size_t)p + 1] = c.y;
+    out[3 * (size_t)p + 2] = c.z;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+import_kernel(const float* __restrict__ color3, const float* __restrict__ normal3,
+              const float* __restrict__ depth1, uint32_t pixels, float4* __restrict__ sum_color,
+              float4* __restrict__ sum_gbuf)
+{
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= pixels) return;
+  sum_color[p] = make_float4(color3[3 * (size_t)p], color3[3 * (size_t)p + 1],
+                             color3[3 * (size_t)p + 2], 1.0f);
+  sum_gbuf[p] = make_float4(normal3[3 * (size_t)p], normal3[3 * (size_t)p + 1],
+                            normal3[3 * (size_t)p + 2], depth1[p]);
+}
+
+// ================================================================== denoise
+// Pre-pass: per-pixel means and the world position the reference rebuilds per
+// tap as generate_ray(camera, x+0.5, y+0.5)(depth) (denoiser.cu:44-45,71-72).
+__global__ void __launch_bounds__(256)
+denoise_prepare_kernel(const DevCamera cam, const float4* __restrict__ sum_color,
+                       const float4* __restrict__ sum_gbuf, float4* __restrict__ color0,
+                       float4* __restrict__ normal_depth, float4* __restrict__ position)
+{
+  const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t y = blockIdx.y;
+  if (x >= cam.width) return;
+  const uint32_t p = y * cam.width + x;
+  const float4 c = sum_color[p];
+  const float4 g = sum_gbuf[p];
+  const float n = c.w;
+  const float depth = g.w / n;
+  color0[p] = make_float4(c.x / n, c.y / n, c.z / n, 0.f);
+  normal_depth[p] = make_float4(g.x / n, g.y / n, g.z / n, depth);
+  f3 o, d;
+  camera_ray(cam, (float)x + 0.5f, (float)y + 0.5f, o, d);
+  position[p] = mk4(o + d * depth, 0.f);
+}
+
+// One a-trous iteration, reference arithmetic (denoiser.cu:24-86).  The tap
+// weight is kernel[min(|dx|,|dy|)] with kernel = {3/8, 1/4, 1/16}; the three
+// edge-stopping weights use exp() clamped to 1.  Taps are clamped to [0,W]x[0,H]
+// inclusive like the reference: u == W aliases pixel (0, v+1) while its
+// position is still rebuilt from the ray through (W+0.5, v+0.5); reads that
+// would fall past the end of the buffer (undefined in the reference) use the
+// last row / last pixel instead.  clamp_fix selects the sane W-1/H-1 clamp.
+__global__ void __launch_bounds__(256)
+atrous_kernel(const DevCamera cam, const DenoiseParams dp, const float4* __restrict__ color_in,
+              const float4* __restrict__ normal_depth, const float4* __restrict__ position,
+              float4* __restrict__ color_out, int step)
+{
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int W = (int)cam.width, H = (int)cam.height;
+  if (x >= W || y >= H) return;
+  const int p = y * W + x;
+  const float4 cv = ldg4(color_in + p);
+  const float4 nv = ldg4(normal_depth + p);
+  const float4 pv = ldg4(position + p);
+  const float kern[3] = {3.f / 8.f, 1.f / 4.f, 1.f / 16.f};
+  const float step2 = (float)(step * step);
+  const int umax = dp.clamp_fix ? W - 1 : W;
+  const int vmax = dp.clamp_fix ? H - 1 : H;
+  f3 sum = mk3(0.f, 0.f, 0.f);
+  float cum_w = 0.f;
+#pragma unroll
+  for (int dy = -2; dy <= 2; ++dy) {
+#pragma unroll
+    for (int dx = -2; dx <= 2; ++dx) {
+      const int u = min(max(x + dx * step, 0), umax);
+      const int v = min(max(y + dy * step, 0), vmax);
+      int q = u + v * W;
+      f3 ptmp;
+      float4 ct, nt;
+      if (u < W && v < H) {
+        ct = ldg4(color_in + q);
+        nt = ldg4(normal_depth + q);
+        const float4 pt4 = ldg4(position + q);
+        ptmp = mk3(pt4.x, pt4.y, pt4.z);
+      } else {
+        if (q >= W * H) q = min(u, W - 1) + (H - 1) * W;
+        ct = ldg4(color_in + q);
+        nt = ldg4(normal_depth + q);
+        f3 o, d;
+        camera_ray(cam, (float)u + 0.5f, (float)v + 0.5f, o, d);
+        ptmp = o + d * nt.w;
+      }
+      f3 t = mk3(cv.x - ct.x, cv.y - ct.y, cv.z - ct.z);
+      float dist2 = dot3(t, t);
+      const float c_w = fminf(expf(-dist2 / dp.c_phi), 1.0f);
+      t = mk3(nv.x - nt.x, nv.y - nt.y, nv.z - nt.z);
+      dist2 = fmaxf(dot3(t, t) / step2, 0.0f);
+      const float n_w = fminf(expf(-dist2 / dp.n_phi), 1.0f);
+      t = mk3(pv.x - ptmp.x, pv.y - ptmp.y, pv.z - ptmp.z);
+      dist2 = dot3(t, t);
+      const float p_w = fminf(expf(-dist2 / dp.p_phi), 1.0f);
+      const float weight = c_w * n_w * p_w;
+      const int ki = min(abs(dx), abs(dy));
+      sum = sum + mk3(ct.x, ct.y, ct.z) * weight * kern[ki];
+      cum_w += weight * kern[ki];
+    }
+  }
+  color_out[p] = make_float4(sum.x / cum_w, sum.y / cum_w, sum.z / cum_w, 0.f);
+}
+
+
+// ================================================================ launchers
+static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+
+void launch_stable_compact(const LaunchEnv& env, const PassBuffers& pb, const PassParams& pp,
+                           int q, uint32_t bounce)
+{
+  const uint32_t n_blocks = cdiv(pb.capacity, SC_ITEMS);
+  const uint32_t* n_ptr = bounce == 0 ? nullptr : pb.counters + bounce;
+  const uint32_t n_first = pp.pixels; // slot == pixel index at bounce 0
+  sc_count_kernel<<<n_blocks, SC_THREADS, 0, env.stream>>>(pb.flags, n_ptr, n_first,
+                                                           pb.block_sums);
+  sc_scan_kernel<<<1, 1024, 0, env.stream>>>(pb.block_sums, n_blocks, pb.counters + bounce + 1);
+  sc_scatter_kernel<<<n_blocks, SC_THREADS, 0, env.stream>>>(
+      pb.flags, n_ptr, n_first, pb.block_sums, bounce == 0 ? nullptr : pb.queue[q],
+      pb.queue[q ^ 1]);
+}
+
+void launch_accumulate(const LaunchEnv& env, const PassBuffers& pb, const PassParams& pp,
+                       float4* sum_color, float4* sum_gbuf, uint32_t max_depth)
+{
+  accumulate_kernel<<<cdiv(pp.pixels, 256), 256, 0, env.stream>>>(
+      pb.ps, pp, sum_color, sum_gbuf, pb.counters, 0u, max_depth, pb.total_rays);
+}
+
+void launch_resolve_rgba8(const LaunchEnv& env, int kind, const float4* sum_color,
+                          const float4* sum_gbuf, const float4* final_rgb, bool final_is_mean,
+                          uint32_t pixels, uchar4* out)
+{
+  resolve_kernel<<<cdiv(pixels, 256), 256, 0, env.stream>>>(kind, sum_color, sum_gbuf, final_rgb,
+                                                            final_is_mean, pixels, out);
+}
+
+void launch_export_f32(const LaunchEnv& env, int kind, const float4* sum_color,
+                       const float4* sum_gbuf, const float4* final_rgb, bool final_is_mean,
+                       uint32_t pixels, float* out)
+{
+  export_kernel<<<cdiv(pixels, 256), 256, 0, env.stream>>>(kind, sum_color, sum_gbuf, final_rgb,
+                                                           final_is_mean, pixels, out);
+}
+
+void launch_import_frame(const LaunchEnv& env, const float* color3, const float* normal3,
+                         const float* depth1, uint32_t pixels, float4* sum_color,
+                         float4* sum_gbuf)
+{
+  import_kernel<<<cdiv(pixels, 256), 256, 0, env.stream>>>(color3, normal3, depth1, pixels,
+                                                           sum_color, sum_gbuf);
+}
+
+void launch_denoise_prepare(const LaunchEnv& env, const DevCamera& cam, const float4* sum_color,
+                            const float4* sum_gbuf, float4* color0, float4* normal_depth,
+                            float4* position)
+{
+  dim3 grid(cdiv(cam.width, 256), cam.height);
+  denoise_prepare_kernel<<<grid, 256, 0, env.stream>>>(cam, sum_color, sum_gbuf, color0,
+                                                       normal_depth, position);
+}
+
+void launch_atrous(const LaunchEnv& env, const DevCamera& cam, const DenoiseParams& dp,
+                   const float4* color_in, const float4* normal_depth, const float4* position,
+                   float4* color_out, int step_width)
+{
+  dim3 grid(cdiv(cam.width, 32), cdiv(cam.height, 8));
+  atrous_kernel<<<grid, 256, 0, env.stream>>>(cam, dp, color_in, normal_depth, position,
+                                              color_out, step_width);
+}
+
+} // namespace pt

@@ -12,23 +12,26 @@ struct LaunchEnv {
 // Per-pass device scratch owned by the context.
 struct PassBuffers {
   PathState ps;
-  uint32_t* queue[2];  // ping-pong path-id queues
+  uint32_t* queue[2];  // ping-pong path-id queues (all live paths of a bounce)
+  uint32_t* tq;        // traverse queue: paths whose ray enters the mesh BVH this bounce
   uint32_t* counters;  // [0 .. max_depth]   live paths entering bounce b
-  uint32_t* work;      // [0 .. 2*max_depth+1] persistent-kernel work-fetch cursors
+  uint32_t* tcounters; // [0 .. max_depth]   length of the traverse queue of bounce b
+  uint32_t* work;      // [0 .. max_depth]   persistent-kernel work-fetch cursors
   uint8_t* flags;      // stable-compaction alive flags (PT_RNG_SLOT_RESEED only)
   uint32_t* block_sums; // stable-compaction block counts / offsets
   unsigned long long* total_rays; // device-side ray counter
   uint32_t capacity;   // paths
 };
 
-// bounce 0: raygen fused into extend. n_items = samples * tiles * 32.
-void launch_extend_first(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb,
-                         const PassParams& pp, uint32_t n_items);
-// bounce b >= 1: extend over queue `q` whose length is counters[b] (device side).
-void launch_extend(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb,
-                   const PassParams& pp, int q, uint32_t bounce);
-// shade bounce b reading queue q (implicit tile order when bounce == 0), appending
-// survivors to queue q^1 and counters[bounce+1].
+// bounce 0: raygen + classification of the primary rays (fills the traverse queue).
+void launch_raygen(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb,
+                   const PassParams& pp, uint32_t n_items);
+// BVH traversal of the traverse queue of `bounce` (length tcounters[bounce], device side).
+void launch_traverse(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb,
+                     uint32_t bounce);
+// shade bounce b over queue q (implicit tile order when bounce == 0): hit rebuild, material,
+// scatter, classification of the new ray; survivors -> queue q^1 / counters[b+1] (or flags for
+// the stable compaction), BVH candidates -> tq / tcounters[b+1].
 void launch_shade(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb,
                   const PassParams& pp, int q, uint32_t bounce, uint32_t n_items_first,
                   bool last_bounce);

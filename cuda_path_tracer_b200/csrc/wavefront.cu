@@ -1,0 +1,746 @@
+// wavefront.cu — hand-written sm_100a kernels of the per-bounce wavefront.
+//
+// One bounce = two launches, both free of host synchronisation:
+//
+//   traverse_kernel   BVH traversal ONLY, over the queue of rays whose slab test against the
+//                     mesh root box succeeded ("complex" rays).  Persistent warps, lane-level
+//                     refill with one atomic per warp, culled + ordered walk of 64-byte two-box
+//                     nodes over world-space baked triangles.  Replaces the mesh branch of
+//                     ray_scene_intersection_test (reference path_tracer.cu:36-76).
+//   shade_kernel      full-warp kernel over ALL live paths of the bounce: rebuilds the hit
+//                     (triangle / sphere / miss), evaluate_material + sky + G-buffer
+//                     (path_tracer.cu:29-34, 138-201, 292-315), writes the scattered ray, then
+//                     CLASSIFIES it for the next bounce (sphere tests, path_tracer.cu:87-98, and
+//                     the root-box test) and appends the path id to the next queue — and to the
+//                     traverse queue if it needs the BVH — with warp-aggregated atomics
+//                     (replaces thrust::stable_partition, path_tracer.cu:433-457).
+//   raygen_kernel     bounce 0: raygen_kernel/generate_ray (ray_gen.cu:11-61) + classification.
+//
+// Why the split: ncu showed the fused extend+shade kernel issue-bound with 9-10 of 32 lanes
+// active (profiles/r1_bounce_v2_*): in open scenes most rays never enter the BVH, and their
+// sphere tests + shading ran in the partially filled retire/refill phases of a warp whose other
+// lanes were long-running mesh rays.  Now everything that is not traversal runs at full warp
+// occupancy, and only rays that touch the mesh pay for the persistent machinery.
+#include "kernels.h"
+
+#include <float.h>
+#include <stdlib.h>
+
+namespace pt {
+
+// =================================================================== helpers
+PT_D f3 xyz(const float4& v) { return mk3(v.x, v.y, v.z); }
+PT_D float4 mk4(f3 v, float w) { return make_float4(v.x, v.y, v.z, w); }
+PT_D float4 ldg4(const float4* p) { return __ldg(p); }
+
+struct Hit {
+  float t;
+  f3 p;
+  f3 n;
+  uint32_t material;
+  uint32_t side;
+  int32_t object;
+  int32_t prim;
+};
+
+// aux code word (see PathState::aux)
+#define AUX_TRI 0x80000000u     // low bits = triangle slot; the traversal found it
+#define AUX_PENDING 0x40000000u // spheres that follow the first mesh object are still untested
+#define AUX_VALUE 0x3fffffffu   // sphere index + 1, or 0 = nothing hit so far
+
+// ------------------------------------------------------------- sphere test
+// ray_object_intersection_test, sphere branch (path_tracer.cu:87-98) with
+// inverse_transform_ray (transform.hpp:50-58) and ray_sphere_intersection_test
+// (intersections.cuh:7-41).  The quirks are kept: the object-space direction is
+// re-normalised while t_min/t_max stay world-space; the reported t is the
+// world-space distance; the normal is transformed by the inverse transpose and
+// not re-normalised.
+PT_D bool sphere_test(const DevSphere* __restrict__ sp, f3 o, f3 d, float tmin, float tmax,
+                      Hit& h)
+{
+  const float* I = sp->inv;
+  // transform_point(inverse): affine, w == 1 exactly
+  f3 oo;
+  oo.x = (I[0] * o.x + I[1] * o.y) + (I[2] * o.z + I[3]);
+  oo.y = (I[4] * o.x + I[5] * o.y) + (I[6] * o.z + I[7]);
+  oo.z = (I[8] * o.x + I[9] * o.y) + (I[10] * o.z + I[11]);
+  f3 dd;
+  dd.x = (I[0] * d.x + I[1] * d.y) + (I[2] * d.z);
+  dd.y = (I[4] * d.x + I[5] * d.y) + (I[6] * d.z);
+  dd.z = (I[8] * d.x + I[9] * d.y) + (I[10] * d.z);
+  dd = normalize3(dd);
+
+  const f3 center = mk3(sp->cx, sp->cy, sp->cz);
+  const float radius = sp->radius;
+  const f3 oc = oo - center;
+  const float a = dot3(dd, dd);
+  const float b = 2.0f * dot3(dd, oc);
+  const float c = dot3(oc, oc) - radius * radius;
+  const float disc = b * b - 4.0f * a * c;
+  if (disc < 0.0f) return false;
+  const float sq = sqrtf(disc);
+  const float t1 = (-b - sq) / (2.0f * a);
+  const float t2 = (-b + sq) / (2.0f * a);
+  float t;
+  if (t1 >= tmin && t1 <= tmax) {
+    t = t1;
+  } else if (t2 >= tmin && t2 <= tmax) {
+    t = t2;
+  } else {
+    return false;
+  }
+  const f3 po = oo + dd * t;
+  const f3 outward = (po - center) / radius;
+  const bool front = dot3(dd, outward) < 0.0f;
+  const f3 no = front ? outward : -outward;
+
+  const float* M = sp->m;
+  f3 pw;
+  pw.x = (M[0] * po.x + M[1] * po.y) + (M[2] * po.z + M[3]);
+  pw.y = (M[4] * po.x + M[5] * po.y) + (M[6] * po.z + M[7]);
+  pw.z = (M[8] * po.x + M[9] * po.y) + (M[10] * po.z + M[11]);
+  // transpose(inverse) * normal  ==  columns of the row-major inverse
+  f3 nw;
+  nw.x = (I[0] * no.x + I[4] * no.y) + (I[8] * no.z);
+  nw.y = (I[1] * no.x + I[5] * no.y) + (I[9] * no.z);
+  nw.z = (I[2] * no.x + I[6] * no.y) + (I[10] * no.z);
+
+  h.t = length3(pw - o); // glm::distance(ray.origin, point)
+  h.p = pw;
+  h.n = nw;
+  h.side = front ? 0u : 1u;
+  h.material = sp->material;
+  h.object = sp->object;
+  h.prim = -1;
+  return true;
+}
+
+// Only the t of a sphere hit (classification keeps 8 bytes per path, the full record is
+// rebuilt by shade with the same arithmetic).
+PT_D bool sphere_t(const DevSphere* __restrict__ sp, f3 o, f3 d, float tmin, float tmax, float& t)
+{
+  Hit h;
+  const bool r = sphere_test(sp, o, d, tmin, tmax, h);
+  t = h.t;
+  return r;
+}
+
+PT_D float safe_inv(float x)
+{
+  const float ooeps = 8.271806125530277e-25f; // 2^-80
+  return 1.0f / (fabsf(x) > ooeps ? x : copysignf(ooeps, x));
+}
+
+// ----------------------------------------------------------- classification
+// The part of ray_scene_intersection_test (path_tracer.cu:110-128) that does not need the
+// BVH stack: the spheres preceding the first mesh object, then a stack-free walk of the top of
+// the BVH.  A ray whose walk dies out is "simple": the remaining spheres are tested right away
+// and its intersection is final.  Otherwise it is queued for traverse_kernel (AUX_PENDING set)
+// together with the node the walk stopped at.
+// Slab tests of both children of an inner node against the segment [tmin, tbest]
+// (the same arithmetic as trav_inner).
+PT_D void node_test(const DevScene& sc, int node, f3 id, f3 od, float tmin, float tbest, bool& t0,
+                    bool& t1, int& c0, int& c1, float& c0min, float& c1min)
+{
+  const float4* np = sc.nodes + (size_t)node * 4;
+  const float4 n0 = ldg4(np + 0);
+  const float4 n1 = ldg4(np + 1);
+  const float4 n2 = ldg4(np + 2);
+  const float4 n3 = ldg4(np + 3);
+  const float c0lox = n0.x * id.x - od.x, c0hix = n0.y * id.x - od.x;
+  const float c0loy = n0.z * id.y - od.y, c0hiy = n0.w * id.y - od.y;
+  const float c0loz = n2.x * id.z - od.z, c0hiz = n2.y * id.z - od.z;
+  const float c1lox = n1.x * id.x - od.x, c1hix = n1.y * id.x - od.x;
+  const float c1loy = n1.z * id.y - od.y, c1hiy = n1.w * id.y - od.y;
+  const float c1loz = n2.z * id.z - od.z, c1hiz = n2.w * id.z - od.z;
+  c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), tmin));
+  const float c0max =
+      fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), tbest));
+  c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), tmin));
+  const float c1max =
+      fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), tbest));
+  // robust slab comparison (Ize 2013): widen the far side by 2 ulp
+  t0 = c0max * 1.0000004f >= c0min;
+  t1 = c1max * 1.0000004f >= c1min;
+  c0 = __float_as_int(n3.x);
+  c1 = __float_as_int(n3.y);
+}
+
+#define PREFIX_MAX 6
+PT_D bool classify(const DevScene& sc, f3 o, f3 d, float tmin, float tmax, float& tbest,
+                   uint32_t& code, int& start)
+{
+  tbest = tmax;
+  code = 0u;
+  start = 0;
+  for (uint32_t i = 0; i < sc.n_spheres_before; ++i) {
+    float t;
+    if (sphere_t(sc.spheres + i, o, d, tmin, tbest, t)) {
+      code = i + 1u;
+      tbest = t;
+    }
+  }
+  bool complex_ray = false;
+  if (sc.n_tris != 0u) {
+    // Walk the hot top of the tree while at most one child box is hit: such a prefix needs no
+    // stack, runs here at full warp occupancy, and lets a ray that only grazes the outer boxes
+    // never reach the traversal queue.  Traversal starts where the walk stopped.
+    const f3 id = mk3(safe_inv(d.x), safe_inv(d.y), safe_inv(d.z));
+    const f3 od = mk3(o.x * id.x, o.y * id.y, o.z * id.z);
+    int node = 0;
+    complex_ray = true;
+#pragma unroll 1
+    for (int it = 0; it < PREFIX_MAX; ++it) {
+      bool t0, t1;
+      int c0, c1;
+      float m0, m1;
+      node_test(sc, node, id, od, tmin, tbest, t0, t1, c0, c1, m0, m1);
+      if (!t0 && !t1) {
+        complex_ray = false;
+        break;
+      }
+      if (t0 && t1) break;
+      node = t0 ? c0 : c1;
+      if (node < 0) break; // a leaf: traversal starts (and ends) there
+    }
+    start = node;
+  }
+  if (complex_ray) {
+    code |= AUX_PENDING;
+  } else {
+    for (uint32_t i = sc.n_spheres_before; i < sc.n_spheres; ++i) {
+      float t;
+      if (sphere_t(sc.spheres + i, o, d, tmin, tbest, t)) {
+        code = i + 1u;
+        tbest = t;
+      }
+    }
+  }
+  return complex_ray;
+}
+
+// Rebuilds the Intersection (intersection.hpp:8-14) from the 8-byte aux word.
+PT_D bool resolve_hit(const DevScene& sc, f3 o, f3 d, float tmin, float t_aux, uint32_t code, Hit& h)
+{
+  bool hit = false;
+  float tbest = t_aux;
+  if (code & AUX_TRI) {
+    const float4* tp = sc.tris + (size_t)(code & AUX_VALUE) * 3;
+    const float4 t0 = ldg4(tp + 0);
+    const float4 t1 = ldg4(tp + 1);
+    const float4 t2 = ldg4(tp + 2);
+    const f3 outward = normalize3(cross3(xyz(t1), xyz(t2))); // triangle_normal (intersections.cuh:43-47)
+    const bool front = dot3(d, outward) < 0.0f;
+    h.t = t_aux;
+    h.p = o + d * t_aux; // ray(t)
+    h.n = front ? outward : -outward;
+    h.side = front ? 0u : 1u;
+    h.prim = __float_as_int(t0.w);
+    h.object = __float_as_int(t1.w);
+    h.material = (uint32_t)__float_as_int(t2.w);
+    hit = true;
+  } else if (code & AUX_VALUE) {
+    // same root as when it was accepted: any t_max >= the accepted t selects it again
+    hit = sphere_test(sc.spheres + ((code & AUX_VALUE) - 1u), o, d, tmin, FLT_MAX, h);
+  }
+  if (code & (AUX_TRI | AUX_PENDING)) {
+    for (uint32_t i = sc.n_spheres_before; i < sc.n_spheres; ++i) {
+      if (sphere_test(sc.spheres + i, o, d, tmin, tbest, h)) {
+        hit = true;
+        tbest = h.t;
+      }
+    }
+  }
+  return hit;
+}
+
+// ---------------------------------------------------------------- traversal
+// Resumable per-lane state machine (init / step) so that a persistent warp can retire
+// finished lanes and refill them while the others keep walking.  Result-equivalent to the
+// reference's un-culled traversal (a culled subtree cannot hold a nearer accepted hit);
+// exact-tie winners may differ (reference: last tested wins).
+struct Trav {
+  f3 o, d;
+  float tmin, tbest;
+  float idx, idy, idz, odx, ody, odz;
+  int node; // current node, PT_SENTINEL when done
+  int sp;
+  int best; // best triangle slot or -1
+};
+
+PT_D void trav_init(Trav& T, f3 o, f3 d, float tmin, float tbest, int start, int* stack)
+{
+  T.o = o;
+  T.d = d;
+  T.tmin = tmin;
+  T.tbest = tbest;
+  T.best = -1;
+  T.idx = safe_inv(d.x);
+  T.idy = safe_inv(d.y);
+  T.idz = safe_inv(d.z);
+  T.odx = o.x * T.idx;
+  T.ody = o.y * T.idy;
+  T.odz = o.z * T.idz;
+  stack[0] = PT_SENTINEL;
+  T.sp = 1;
+  T.node = start;
+}
+
+// Inner-node visit: two slab tests against the children's boxes stored in the node, ordered
+// descent (nearer child first), farther child pushed.
+PT_D void trav_inner(const DevScene& sc, Trav& T, int* stack)
+{
+  const float4* np = sc.nodes + (size_t)T.node * 4;
+  const float4 n0 = ldg4(np + 0);
+  const float4 n1 = ldg4(np + 1);
+  const float4 n2 = ldg4(np + 2);
+  const float4 n3 = ldg4(np + 3);
+  const float c0lox = n0.x * T.idx - T.odx, c0hix = n0.y * T.idx - T.odx;
+  const float c0loy = n0.z * T.idy - T.ody, c0hiy = n0.w * T.idy - T.ody;
+  const float c0loz = n2.x * T.idz - T.odz, c0hiz = n2.y * T.idz - T.odz;
+  const float c1lox = n1.x * T.idx - T.odx, c1hix = n1.y * T.idx - T.odx;
+  const float c1loy = n1.z * T.idy - T.ody, c1hiy = n1.w * T.idy - T.ody;
+  const float c1loz = n2.z * T.idz - T.odz, c1hiz = n2.w * T.idz - T.odz;
+  const float c0min =
+      fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), T.tmin));
+  const float c0max =
+      fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), T.tbest));
+  const float c1min =
+      fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), T.tmin));
+  const float c1max =
+      fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), T.tbest));
+  // robust slab comparison (Ize 2013): widen the far side by 2 ulp
+  const bool trav0 = c0max * 1.0000004f >= c0min;
+  const bool trav1 = c1max * 1.0000004f >= c1min;
+  const int c0 = __float_as_int(n3.x);
+  const int c1 = __float_as_int(n3.y);
+  if (!trav0 && !trav1) {
+    T.node = stack[--T.sp];
+  } else {
+    const bool swap = trav1 && (!trav0 || c1min < c0min);
+    T.node = swap ? c1 : c0;
+    if (trav0 && trav1) stack[T.sp++] = swap ? c0 : c1;
+  }
+}
+
+// Leaf visit: <= 4 Moller-Trumbore tests with the reference's operation order for a, f, u, v, t
+// (intersections.cuh:49-85), evaluated branch-free so the lanes of a warp stay converged; the
+// accept conditions are the reference's (EPSILON 1e-7 on the determinant, u,v in [0,1],
+// u+v <= 1, closed t range).
+PT_D void trav_leaf(const DevScene& sc, Trav& T, int* stack)
+{
+  const uint32_t code = (uint32_t)(~T.node);
+  const uint32_t first = code >> 3;
+  const uint32_t count = (code & 7u) + 1u;
+  for (uint32_t k = 0; k < count; ++k) {
+    const float4* tp = sc.tris + (size_t)(first + k) * 3;
+    const float4 t0 = ldg4(tp + 0);
+    const float4 t1 = ldg4(tp + 1);
+    const float4 t2 = ldg4(tp + 2);
+    const f3 e1 = xyz(t1), e2 = xyz(t2);
+    const f3 hh = cross3(T.d, e2);
+    const float a = dot3(e1, hh);
+    const float f = 1.0f / a;
+    const f3 s = T.o - xyz(t0);
+    const float u = f * dot3(s, hh);
+    const f3 q = cross3(s, e1);
+    const float v = f * dot3(T.d, q);
+    const float t = f * dot3(e2, q);
+    const bool ok = !(a > -0.0000001f && a < 0.0000001f) && !(u < 0.0f || u > 1.0f) &&
+                    !(v < 0.0f || u + v > 1.0f) && (t >= T.tmin && t <= T.tbest);
+    if (ok) {
+      T.tbest = t;
+      T.best = (int)(first + k);
+    }
+  }
+  T.node = stack[--T.sp];
+}
+
+// ------------------------------------------------------ bounce-0 index map
+// Work item -> (sample, pixel): one warp covers an 8x4 pixel tile so primary
+// rays of a warp are coherent.  Returns false for padding lanes.
+PT_D bool first_item(const PassParams& pp, uint32_t idx, uint32_t& pid, uint32_t& pixel,
+                     uint32_t& s)
+{
+  const uint32_t per_sample = pp.tiles_x * pp.tiles_y * 32u;
+  s = idx / per_sample;
+  const uint32_t r = idx - s * per_sample;
+  const uint32_t tile = r >> 5, lane = r & 31u;
+  const uint32_t ty = tile / pp.tiles_x, tx = tile - ty * pp.tiles_x;
+  const uint32_t x = tx * 8u + (lane & 7u);
+  const uint32_t y = ty * 4u + (lane >> 3);
+  pixel = y * pp.cam.width + x;
+  pid = s * pp.pixels + pixel;
+  return x < pp.cam.width && y < pp.cam.height && s < pp.samples;
+}
+
+// Appends `pid` of every lane with `push` set: one atomic per warp (ballot + popc prefix).
+PT_D void warp_append(bool push, uint32_t pid, uint32_t* __restrict__ queue,
+                      uint32_t* __restrict__ count, uint32_t lane)
+{
+  const uint32_t mask = __ballot_sync(0xffffffffu, push);
+  if (mask == 0u) return;
+  const int leader = __ffs(mask) - 1;
+  uint32_t base = 0;
+  if ((int)lane == leader) base = atomicAdd(count, (uint32_t)__popc(mask));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (push) queue[base + (uint32_t)__popc(mask & ((1u << lane) - 1u))] = pid;
+}
+
+// =================================================================== raygen
+#define FULL_THREADS 256
+
+__global__ void __launch_bounds__(FULL_THREADS)
+raygen_kernel(const DevScene sc, const PathState ps, const PassParams pp, uint32_t n_items,
+              uint32_t* __restrict__ tq, uint32_t* __restrict__ tq_count)
+{
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t n_round = (n_items + 31u) & ~31u;
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_round; idx += stride) {
+    uint32_t pid = 0, pixel, s;
+    const bool valid = idx < n_items && first_item(pp, idx, pid, pixel, s);
+    bool complex_ray = false;
+    if (valid) {
+      // raygen_kernel (ray_gen.cu:11-32): seed, jitter (x then y), pinhole ray
+      uint32_t rng = minstd_seed(wang_hash(wang_hash(pixel) ^ (pp.first_iteration + s)));
+      const uint32_t y = pixel / pp.cam.width, x = pixel - y * pp.cam.width;
+      const float fx = (float)x + minstd_uniform(rng);
+      const float fy = (float)y + minstd_uniform(rng);
+      f3 o, d;
+      camera_ray(pp.cam, fx, fy, o, d);
+      float tbest;
+      uint32_t code;
+      int start;
+      complex_ray = classify(sc, o, d, 1e-4f, FLT_MAX, tbest, code, start);
+      ps.ray[2 * (size_t)pid] = mk4(o, 1e-4f);
+      ps.ray[2 * (size_t)pid + 1] = mk4(d, FLT_MAX);
+      ps.thr[pid] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(rng));
+      ps.aux[pid] = make_uint4(__float_as_uint(tbest), code, (uint32_t)start, 0u);
+    }
+    warp_append(complex_ray, pid, tq, tq_count, lane);
+  }
+}
+
+// ================================================================= traverse
+// Persistent warps (grid = SMs x resident CTAs).  Each lane owns one ray at a time.  Work is
+// fetched from a device-side cursor with ONE atomic per refill for all idle lanes of the warp;
+// lanes that finish early are retired (8-byte result) and refilled as soon as fewer than
+// EXT_REFILL lanes are still walking, so the warp stays populated although per-ray traversal
+// lengths vary by orders of magnitude.
+#define EXT_THREADS 128
+#define EXT_MIN_BLOCKS 8
+#define EXT_REFILL 16
+#define EXT_INNER_MIN 8
+
+enum { SRC_QUEUE = 1, SRC_BATCH = 2 };
+
+template <int SRC>
+__global__ void __launch_bounds__(EXT_THREADS, EXT_MIN_BLOCKS)
+traverse_kernel(const DevScene sc, const PathState ps, const uint32_t* __restrict__ tq,
+                const uint32_t* __restrict__ n_ptr, uint32_t n_host, uint32_t* __restrict__ work,
+                const float4* __restrict__ batch_rays, HitRecord* __restrict__ batch_out,
+                int refill_min, int inner_min)
+{
+  const uint32_t n = SRC == SRC_QUEUE ? *n_ptr : n_host;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  int stack[PT_STACK];
+  Trav T;
+  T.node = PT_SENTINEL;
+  bool has = false;
+  bool exhausted = false; // warp-uniform
+  uint32_t pid = 0, code = 0;
+
+  for (;;) {
+    // ---- refill idle lanes: one atomic per warp
+    const uint32_t need = __ballot_sync(0xffffffffu, !has);
+    if (need != 0u && !exhausted) {
+      const uint32_t cnt = (uint32_t)__popc(need);
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(work, cnt);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (base + cnt >= n) exhausted = true;
+      if (!has) {
+        const uint32_t idx = base + (uint32_t)__popc(need & lt_mask);
+        if (idx < n) {
+          if (SRC == SRC_QUEUE) {
+            pid = tq[idx];
+            const float4 ro = ps.ray[2 * (size_t)pid];
+            const float4 rd = ps.ray[2 * (size_t)pid + 1];
+            const uint4 ax = ps.aux[pid];
+            trav_init(T, xyz(ro), xyz(rd), ro.w, __uint_as_float(ax.x), (int)ax.z, stack);
+            has = true;
+          } else {
+            pid = idx;
+            const float4 ro = batch_rays[2 * (size_t)idx], rd = batch_rays[2 * (size_t)idx + 1];
+            float tbest;
+            int start;
+            const bool complex_ray = classify(sc, xyz(ro), xyz(rd), ro.w, rd.w, tbest, code, start);
+            trav_init(T, xyz(ro), xyz(rd), ro.w, tbest, start, stack);
+            if (!complex_ray) T.node = PT_SENTINEL;
+            has = true;
+          }
+        }
+      }
+    }
+    if (__ballot_sync(0xffffffffu, has) == 0u) {
+      if (exhausted) break;
+      continue;
+    }
+    // ---- walk until too few lanes are still busy (all of them once the queue is drained).
+    // while-while scheduling: lanes descend inner nodes together until (almost) all of them
+    // stand on a leaf, then the leaves are intersected together — inner and leaf code never
+    // interleave inside a warp, which is what kept 10 of 32 lanes busy in the if/else form.
+    const int threshold = exhausted ? 1 : refill_min;
+    for (;;) {
+      const bool busy = has && T.node != PT_SENTINEL;
+      if (__popc(__ballot_sync(0xffffffffu, busy)) < threshold) break;
+      for (;;) {
+        const bool inner = has && (uint32_t)T.node < (uint32_t)PT_SENTINEL;
+        const uint32_t m_inner = __ballot_sync(0xffffffffu, inner);
+        const uint32_t m_leaf = __ballot_sync(0xffffffffu, has && T.node < 0);
+        if (m_inner == 0u) break;
+        if (__popc(m_inner) < inner_min && m_leaf != 0u) break;
+        if (inner) trav_inner(sc, T, stack);
+      }
+      if (has && T.node < 0) trav_leaf(sc, T, stack);
+    }
+    // ---- retire finished lanes
+    if (has && T.node == PT_SENTINEL) {
+      if (SRC == SRC_QUEUE) {
+        if (T.best >= 0)
+          *reinterpret_cast<uint2*>(ps.aux + pid) =
+              make_uint2(__float_as_uint(T.tbest), AUX_TRI | (uint32_t)T.best);
+      } else {
+        // parity hook (pt_trace_batch): full Intersection + primitive ids
+        if (T.best >= 0) code = AUX_TRI | (uint32_t)T.best;
+        Hit h;
+        HitRecord r;
+        if (resolve_hit(sc, T.o, T.d, T.tmin, T.tbest, code, h)) {
+          r.t = h.t;
+          r.px = h.p.x, r.py = h.p.y, r.pz = h.p.z;
+          r.nx = h.n.x, r.ny = h.n.y, r.nz = h.n.z;
+          r.material = h.material, r.side = h.side;
+          r.object = h.object, r.prim = h.prim;
+        } else {
+          r.t = -1.0f;
+          r.px = r.py = r.pz = r.nx = r.ny = r.nz = 0.f;
+          r.material = 0, r.side = 0, r.object = -1, r.prim = -1;
+        }
+        r.pad = 0;
+        batch_out[pid] = r;
+      }
+      has = false;
+    }
+  }
+}
+
+// ==================================================================== shade
+// random_in_unit_sphere (distributions.cuh:6-19): uniform ON the sphere.
+PT_D f3 random_on_sphere(uint32_t& rng)
+{
+  const float phi = (2.0f * 3.14159265358979323846264338327950288f) * minstd_uniform(rng);
+  const float cos_theta = 2.0f * minstd_uniform(rng) - 1.0f;
+  const float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+  return mk3(cosf(phi) * sin_theta, sinf(phi) * sin_theta, cos_theta);
+}
+
+PT_D float sign1(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
+
+// get_background_color (path_tracer.cu:29-34)
+PT_D f3 sky_color(f3 d)
+{
+  const f3 unit = normalize3(d);
+  const float t = 0.5f * (unit.y + 1.0f);
+  return mk3(0.5f, 0.7f, 1.0f) * (1.0f - t) + mk3(1.0f, 1.0f, 1.0f) * t;
+}
+
+// evaluate_material (path_tracer.cu:138-201): scatters the ray in place and updates the
+// throughput.  Draw order and count per material are the reference's (lambert/metal: 2,
+// dielectric: 1 and only when refraction is possible).
+PT_D void scatter(const DevMaterial& mat, const Hit& h, f3& o, f3& d, float& tmin, f3& color,
+                  uint32_t& rng)
+{
+  const f3 n = h.n;
+  f3 origin = h.p - (1e-4f * sign1(dot3(d, n))) * n;
+  f3 dir;
+  if (mat.type == 0) {
+    f3 sd = normalize3(n + random_on_sphere(rng));
+    if (fabsf(sd.x) < 1e-8f && fabsf(sd.y) < 1e-8f && fabsf(sd.z) < 1e-8f) sd = n;
+    dir = sd;
+    color = color * mk3(mat.r, mat.g, mat.b);
+  } else if (mat.type == 1) {
+    const f3 reflected = d - n * dot3(n, d) * 2.0f; // glm::reflect
+    dir = reflected + mat.param * random_on_sphere(rng);
+    if (dot3(dir, n) > 0.0f) {
+      color = color * mk3(mat.r, mat.g, mat.b);
+    } else {
+      color = mk3(0.f, 0.f, 0.f);
+    }
+  } else {
+    const float ior = mat.param;
+    const float ratio = h.side == 0u ? (1.0f / ior) : ior;
+    const f3 unit = normalize3(d);
+    const float cos_theta = fminf(dot3(-unit, n), 1.0f);
+    const float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+    const bool cannot_refract = ratio * sin_theta > 1.0f;
+    bool reflect_it = cannot_refract;
+    if (!cannot_refract) {
+      // Schlick (path_tracer.cu:130-136); the draw happens only on this branch
+      float r0 = (1.0f - ratio) / (1.0f + ratio);
+      r0 = r0 * r0;
+      const float refl = r0 + (1.0f - r0) * powf(1.0f - cos_theta, 5.0f);
+      reflect_it = refl > minstd_uniform(rng);
+    }
+    if (reflect_it) {
+      dir = unit - n * dot3(n, unit) * 2.0f;
+    } else {
+      // glm::refract
+      const float dv = dot3(n, unit);
+      const float k = 1.0f - ratio * ratio * (1.0f - dv * dv);
+      dir = k >= 0.0f ? (ratio * unit - (ratio * dv + sqrtf(k)) * n) : mk3(0.f, 0.f, 0.f);
+    }
+    origin = h.p;
+    tmin = 1e-5f;
+  }
+  o = origin;
+  d = dir;
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(FULL_THREADS)
+shade_kernel(const DevScene sc, const PathState ps, const PassParams pp,
+             const uint32_t* __restrict__ queue, const uint32_t* __restrict__ n_ptr,
+             uint32_t n_first, uint32_t* __restrict__ next_queue,
+             uint32_t* __restrict__ next_count, uint32_t* __restrict__ tq,
+             uint32_t* __restrict__ tq_count, uint8_t* __restrict__ flags, uint32_t bounce,
+             uint32_t last_bounce)
+{
+  const uint32_t n = FIRST ? n_first : *n_ptr;
+  const uint32_t n_round = (n + 31u) & ~31u;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_round; idx += stride) {
+    bool alive = false, complex_ray = false;
+    uint32_t pid = 0, slot = idx;
+    bool valid = idx < n;
+    if (valid) {
+      if (FIRST) {
+        uint32_t s;
+        valid = first_item(pp, idx, pid, slot, s); // slot = pixel index at bounce 0
+      } else {
+        pid = queue[idx];
+      }
+    }
+    if (valid) {
+      const float4 ro = ps.ray[2 * (size_t)pid];
+      const float4 rd = ps.ray[2 * (size_t)pid + 1];
+      const float4 th = ps.thr[pid];
+      const uint4 ax = ps.aux[pid];
+      f3 o = xyz(ro), d = xyz(rd);
+      float tmin = ro.w;
+      f3 color = xyz(th);
+      uint32_t rng = __float_as_uint(th.w);
+      if (pp.rng_mode == 1u) {
+        // reference streaming mode: re-seed from the compacted slot index and
+        // discard(bounce) (path_tracer.cu:300-301)
+        rng = minstd_discard(minstd_seed(wang_hash(wang_hash(slot) ^ pp.first_iteration)), bounce);
+      }
+      Hit h;
+      if (!resolve_hit(sc, o, d, tmin, __uint_as_float(ax.x), ax.y, h)) {
+        color = color * sky_color(d);
+        if (FIRST) ps.gbuf[pid] = make_float4(-d.x, -d.y, -d.z, 1e6f);
+      } else {
+        if (FIRST) ps.gbuf[pid] = make_float4(h.n.x, h.n.y, h.n.z, h.t);
+        const DevMaterial mat = sc.materials[h.material];
+        scatter(mat, h, o, d, tmin, color, rng);
+        alive = last_bounce == 0u;
+        if (alive) {
+          float tbest;
+          uint32_t code;
+          int start;
+          complex_ray = classify(sc, o, d, tmin, FLT_MAX, tbest, code, start);
+          ps.ray[2 * (size_t)pid] = mk4(o, tmin);
+          ps.ray[2 * (size_t)pid + 1] = mk4(d, FLT_MAX);
+          ps.aux[pid] = make_uint4(__float_as_uint(tbest), code, (uint32_t)start, 0u);
+        }
+      }
+      ps.thr[pid] = mk4(color, __uint_as_float(rng));
+      if (pp.rng_mode == 1u && last_bounce == 0u) flags[slot] = alive ? 1 : 0;
+    }
+    if (last_bounce == 0u) {
+      if (pp.rng_mode != 1u) warp_append(alive, pid, next_queue, next_count, lane);
+      warp_append(complex_ray, pid, tq, tq_count, lane);
+    }
+  }
+}
+
+// ================================================================ launchers
+static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+
+static int tune(const char* name, int dflt)
+{
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+// persistent grid: SMs x the number of CTAs the kernel can keep resident per SM
+template <int SRC> static uint32_t traverse_grid(const LaunchEnv& env)
+{
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, traverse_kernel<SRC>, EXT_THREADS, 0) !=
+            cudaSuccess ||
+        nb <= 0)
+      nb = EXT_MIN_BLOCKS;
+    per_sm = nb;
+  }
+  return (uint32_t)(env.sms * per_sm);
+}
+
+void launch_raygen(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb,
+                   const PassParams& pp, uint32_t n_items)
+{
+  const uint32_t grid = min((uint32_t)env.sms * 8u, cdiv(n_items, FULL_THREADS));
+  raygen_kernel<<<grid, FULL_THREADS, 0, env.stream>>>(sc, pb.ps, pp, n_items, pb.tq,
+                                                       pb.tcounters + 0);
+}
+
+void launch_traverse(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb,
+                     uint32_t bounce)
+{
+  traverse_kernel<SRC_QUEUE><<<traverse_grid<SRC_QUEUE>(env), EXT_THREADS, 0, env.stream>>>(
+      sc, pb.ps, pb.tq, pb.tcounters + bounce, 0u, pb.work + bounce, nullptr, nullptr,
+      tune("PT_REFILL", EXT_REFILL), tune("PT_INNER_MIN", EXT_INNER_MIN));
+}
+
+void launch_shade(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb,
+                  const PassParams& pp, int q, uint32_t bounce, uint32_t n_items_first,
+                  bool last_bounce)
+{
+  const uint32_t grid = (uint32_t)env.sms * 8u;
+  if (bounce == 0) {
+    shade_kernel<true><<<min(grid, cdiv(n_items_first, FULL_THREADS)), FULL_THREADS, 0, env.stream>>>(
+        sc, pb.ps, pp, nullptr, nullptr, n_items_first, pb.queue[q ^ 1], pb.counters + 1, pb.tq,
+        pb.tcounters + 1, pb.flags, 0u, last_bounce ? 1u : 0u);
+  } else {
+    shade_kernel<false><<<grid, FULL_THREADS, 0, env.stream>>>(
+        sc, pb.ps, pp, pb.queue[q], pb.counters + bounce, 0u, pb.queue[q ^ 1],
+        pb.counters + bounce + 1, pb.tq, pb.tcounters + bounce + 1, pb.flags, bounce,
+        last_bounce ? 1u : 0u);
+  }
+}
+
+void launch_trace_batch(const LaunchEnv& env, const DevScene& sc, const float4* rays, uint32_t* work,
+                        uint32_t n, HitRecord* out)
+{
+  // the parity hook runs the SAME classification + persistent traversal code as the renderer
+  const uint32_t grid = min(traverse_grid<SRC_BATCH>(env), cdiv(n, EXT_THREADS));
+  traverse_kernel<SRC_BATCH><<<grid, EXT_THREADS, 0, env.stream>>>(sc, PathState{}, nullptr, nullptr,
+                                                                   n, work, rays, out, EXT_REFILL,
+                                                                   EXT_INNER_MIN);
+}
+
+} // namespace pt
