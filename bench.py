@@ -117,10 +117,15 @@ def cpu_baseline(sd, wl):
     w, h = max(16, wl["w"] // 4), max(16, wl["h"] // 4)
     osc = o.scene(sd)
     t0 = time.perf_counter()
-    _, _, _, rays = osc.render(sd.camera, w, h, 1, wl["depth"])
+    _, _, _, rays = osc.render(sd.camera, w, h, 1, wl["depth"])   # probe: sizes the sample
+    probe = max(time.perf_counter() - t0, 1e-4)
+    spp = int(min(4096, max(1, round(12.0 / probe))))               # ~12 s of CPU work
+    t0 = time.perf_counter()
+    _, _, _, rays = osc.render(sd.camera, w, h, spp, wl["depth"])
     dt = time.perf_counter() - t0
     return {"value": rays / dt * 1e-6, "unit": "Mrays/s", "cores": o.num_threads(), "kind": "port",
-            "sample": f"{w}x{h}, 1 spp, depth {wl['depth']}, {rays} rays in {dt:.2f} s (oracle/liboracle.so)"}
+            "sample": f"{w}x{h}, {spp} spp, depth {wl['depth']}, {rays} rays in {dt:.2f} s "
+                      f"(oracle/liboracle.so, reference algorithm restated in C, OpenMP over pixels)"}
 
 
 def run_reference(args, wl, sd):
@@ -198,7 +203,8 @@ def main():
     W, H, spp, depth = wl["w"], wl["h"], wl["spp"], wl["depth"]
     scene = pt.Scene.from_description(sd, device=local_rank)
     stream = torch.cuda.Stream()
-    tracer = pt.PathTracer(max_depth=depth, profile=True, stream=stream.cuda_stream)
+    tracer = pt.PathTracer(max_depth=depth, profile=True, stream=stream.cuda_stream,
+                           samples_per_pass=int(os.environ.get("PT_SPP_PASS", "0")))
     tracer.max_iterations = 1 << 30
     tracer.create_buffers((W, H), scene)
     sums = torch.zeros(W * H * 8, dtype=torch.float32, device="cuda")
@@ -269,11 +275,11 @@ def main():
     if rank == 0:
         hbm, peak_src = peaks()
         value = rays / (ms * 1e-3) * 1e-6
-        # roofline of the dominant kernel (extend): algorithmic bytes = 48 B per ray
-        # (ray 32 B in + 16 B hit record out) over the summed extend launch time
-        ext_ms = st.ms_extend + st.ms_raygen_extend0
-        n_ext = max(1, int(st.n_extend_launches))
-        achieved = (int(st.rays) * 48) / (ext_ms * 1e-3) * 1e-9 if ext_ms > 0 else None
+        # roofline of the dominant kernel (traverse_kernel): algorithmic bytes = 48 B per ray it
+        # processes (ray 32 B in + 16 B hit record out) over its summed launch time
+        ext_ms = st.ms_extend
+        n_ext = max(1, int(st.n_extend_launches) - int(st.passes))
+        achieved = (int(st.rays_traversed) * 48) / (ext_ms * 1e-3) * 1e-9 if ext_ms > 0 else None
         line = {
             "metric": "Mrays/s (all bounces)", "value": value, "unit": "Mrays/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -294,15 +300,16 @@ def main():
             "gpu_launches": int(st.kernel_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                          "frac": (achieved / hbm) if achieved else None, "traffic": None,
-                         "kernel": "extend_kernel", "launches": n_ext,
+                         "kernel": "traverse_kernel", "launches": n_ext,
+                         "rays_traversed_per_step": int(st.rays_traversed) // args.steps,
                          "avg_launch_ms": ext_ms / n_ext,
                          "extend_share_of_step": ext_ms / ms,
                          "wavefront_bytes_per_ray": 164,
-                         "wavefront_frac": rays * 164 / (ms * 1e-3) * 1e-9 / hbm,
+                         "wavefront_frac": rays / world * 164 / (ms * 1e-3) * 1e-9 / hbm,
                          "peak_source": peak_src,
                          "note": "traversal is latency/divergence bound; see profiles/ for L2 and issue metrics"},
-            "kernel_ms": {"extend0": st.ms_raygen_extend0, "extend": st.ms_extend, "shade": st.ms_shade,
-                          "accumulate": st.ms_accumulate},
+            "kernel_ms": {"raygen_classify": st.ms_raygen_extend0, "traverse": st.ms_extend,
+                          "shade_classify_compact": st.ms_shade, "accumulate": st.ms_accumulate},
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(sd, wl)
@@ -314,8 +321,8 @@ def main():
 
 
 def tracer_state_mb(W, H, tracer):
-    spp_pass = max(1, min(64, (1 << 23) // (W * H)))
-    return int(W * H * spp_pass * 104 / 1e6)
+    spp_pass = int(os.environ.get("PT_SPP_PASS", "0")) or max(1, min(64, (1 << 27) // (W * H)))
+    return int(W * H * spp_pass * 92 / 1e6)
 
 
 if __name__ == "__main__":

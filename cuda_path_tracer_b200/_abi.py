@@ -67,7 +67,7 @@ class pt_stats(C.Structure):
                 ("ms_accumulate", C.c_double), ("ms_denoise", C.c_double),
                 ("ms_resolve", C.c_double), ("n_extend_launches", C.c_uint64),
                 ("n_shade_launches", C.c_uint64), ("max_bounce_reached", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("reserved", C.c_uint32), ("rays_traversed", C.c_uint64)]
 
 
 class pt_scene_info(C.Structure):

@@ -110,7 +110,12 @@ accumulate_kernel(const PathState ps, const PassParams pp, float4* __restrict__ 
     // rays = live paths entering extend, summed over bounces (counters[0] is host-known)
     unsigned long long r = (unsigned long long)pp.pixels * pp.samples;
     for (uint32_t b = 1; b < max_depth; ++b) r += counters[b];
-    *total_rays += r;
+    total_rays[0] += r;
+    // rays that entered the BVH traversal queue (tcounters follow counters and work cursors)
+    const uint32_t* tc = counters + 2 * (max_depth + 2);
+    unsigned long long tr = 0;
+    for (uint32_t b = 0; b < max_depth; ++b) tr += tc[b];
+    total_rays[1] += tr;
   }
   if (p >= pp.pixels) return;
   float4 c = sum_color[p];
@@ -232,72 +237,100 @@ denoise_prepare_kernel(const DevCamera cam, const float4* __restrict__ sum_color
   position[p] = mk4(o + d * depth, 0.f);
 }
 
-// One a-trous iteration, reference arithmetic (denoiser.cu:24-86).  The tap
-// weight is kernel[min(|dx|,|dy|)] with kernel = {3/8, 1/4, 1/16}; the three
-// edge-stopping weights use exp() clamped to 1.  Taps are clamped to [0,W]x[0,H]
-// inclusive like the reference: u == W aliases pixel (0, v+1) while its
-// position is still rebuilt from the ray through (W+0.5, v+0.5); reads that
-// would fall past the end of the buffer (undefined in the reference) use the
-// last row / last pixel instead.  clamp_fix selects the sane W-1/H-1 clamp.
-__global__ void __launch_bounds__(256)
+// One a-trous iteration (denoiser.cu:24-86), register-tiled: a thread produces ATR_R outputs
+// that are `step` rows apart, (x, y0 + r*step), so the 5 x (ATR_R + 4) distinct taps are
+// loaded once and shared (40 float4-triples for 4 outputs instead of 100); a warp covers 32
+// consecutive x, so every tap row is one coalesced 512-byte request.
+//
+// Arithmetic follows the reference with two re-associations that stay far inside the 1e-4
+// parity bound: the three edge-stopping weights min(exp(-a),1)*min(exp(-b),1)*min(exp(-c),1)
+// (a, b, c >= 0, so the clamps never bind) are evaluated as one exp2(-(a+b+c) * log2 e), and
+// colour*weight*kernel is grouped as colour*(weight*kernel).  The tap weight is
+// kernel[min(|dx|,|dy|)] with kernel = {3/8, 1/4, 1/16} as in the reference (not the separable
+// B3 product).  Taps are clamped to [0,W]x[0,H] inclusive like the reference: u == W aliases
+// pixel (0, v+1) while its position is still rebuilt from the ray through (W+0.5, v+0.5);
+// reads that would fall past the end of the buffer (undefined in the reference) use the last
+// row / last pixel instead.  clamp_fix selects the sane W-1/H-1 clamp.
+#define ATR_R 4
+
+__global__ void __launch_bounds__(128)
 atrous_kernel(const DevCamera cam, const DenoiseParams dp, const float4* __restrict__ color_in,
               const float4* __restrict__ normal_depth, const float4* __restrict__ position,
-              float4* __restrict__ color_out, int step)
+              float4* __restrict__ color_out, int step, int n_groups)
 {
-  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
   const int W = (int)cam.width, H = (int)cam.height;
-  if (x >= W || y >= H) return;
-  const int p = y * W + x;
-  const float4 cv = ldg4(color_in + p);
-  const float4 nv = ldg4(normal_depth + p);
-  const float4 pv = ldg4(position + p);
-  const float kern[3] = {3.f / 8.f, 1.f / 4.f, 1.f / 16.f};
-  const float step2 = (float)(step * step);
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int g = blockIdx.y * 4 + (threadIdx.x >> 5); // (phase, group of ATR_R dilated rows)
+  const int ph = g % step, k = g / step;
+  if (x >= W || k >= n_groups) return;
+  const int q0 = k * ATR_R;
+
+  const float log2e = 1.4426950408889634f;
+  const float kc = log2e / dp.c_phi;
+  const float kn = log2e / (dp.n_phi * (float)(step * step));
+  const float kp = log2e / dp.p_phi;
   const int umax = dp.clamp_fix ? W - 1 : W;
   const int vmax = dp.clamp_fix ? H - 1 : H;
-  f3 sum = mk3(0.f, 0.f, 0.f);
-  float cum_w = 0.f;
+
+  f3 cv[ATR_R], nv[ATR_R], pv[ATR_R], sum[ATR_R];
+  float cum[ATR_R];
+  bool valid[ATR_R];
 #pragma unroll
-  for (int dy = -2; dy <= 2; ++dy) {
+  for (int r = 0; r < ATR_R; ++r) {
+    const int y = (q0 + r) * step + ph;
+    valid[r] = y < H;
+    const int p = min(y, H - 1) * W + x;
+    const float4 c = ldg4(color_in + p), n = ldg4(normal_depth + p), q = ldg4(position + p);
+    cv[r] = mk3(c.x, c.y, c.z);
+    nv[r] = mk3(n.x, n.y, n.z);
+    pv[r] = mk3(q.x, q.y, q.z);
+    sum[r] = mk3(0.f, 0.f, 0.f);
+    cum[r] = 0.f;
+  }
+
+#pragma unroll
+  for (int j = -2; j < ATR_R + 2; ++j) {
+    const int v = min(max((q0 + j) * step + ph, 0), vmax);
 #pragma unroll
     for (int dx = -2; dx <= 2; ++dx) {
       const int u = min(max(x + dx * step, 0), umax);
-      const int v = min(max(y + dy * step, 0), vmax);
-      int q = u + v * W;
-      f3 ptmp;
-      float4 ct, nt;
+      int qi = u + v * W;
+      f3 ct, nt, pt3;
       if (u < W && v < H) {
-        ct = ldg4(color_in + q);
-        nt = ldg4(normal_depth + q);
-        const float4 pt4 = ldg4(position + q);
-        ptmp = mk3(pt4.x, pt4.y, pt4.z);
+        const float4 c = ldg4(color_in + qi), n = ldg4(normal_depth + qi), q = ldg4(position + qi);
+        ct = mk3(c.x, c.y, c.z);
+        nt = mk3(n.x, n.y, n.z);
+        pt3 = mk3(q.x, q.y, q.z);
       } else {
-        if (q >= W * H) q = min(u, W - 1) + (H - 1) * W;
-        ct = ldg4(color_in + q);
-        nt = ldg4(normal_depth + q);
+        if (qi >= W * H) qi = min(u, W - 1) + (H - 1) * W;
+        const float4 c = ldg4(color_in + qi), n = ldg4(normal_depth + qi);
+        ct = mk3(c.x, c.y, c.z);
+        nt = mk3(n.x, n.y, n.z);
         f3 o, d;
         camera_ray(cam, (float)u + 0.5f, (float)v + 0.5f, o, d);
-        ptmp = o + d * nt.w;
+        pt3 = o + d * n.w;
       }
-      f3 t = mk3(cv.x - ct.x, cv.y - ct.y, cv.z - ct.z);
-      float dist2 = dot3(t, t);
-      const float c_w = fminf(expf(-dist2 / dp.c_phi), 1.0f);
-      t = mk3(nv.x - nt.x, nv.y - nt.y, nv.z - nt.z);
-      dist2 = fmaxf(dot3(t, t) / step2, 0.0f);
-      const float n_w = fminf(expf(-dist2 / dp.n_phi), 1.0f);
-      t = mk3(pv.x - ptmp.x, pv.y - ptmp.y, pv.z - ptmp.z);
-      dist2 = dot3(t, t);
-      const float p_w = fminf(expf(-dist2 / dp.p_phi), 1.0f);
-      const float weight = c_w * n_w * p_w;
-      const int ki = min(abs(dx), abs(dy));
-      sum = sum + mk3(ct.x, ct.y, ct.z) * weight * kern[ki];
-      cum_w += weight * kern[ki];
+#pragma unroll
+      for (int r = 0; r < ATR_R; ++r) {
+        const int dy = j - r;
+        if (dy < -2 || dy > 2) continue; // compile-time after unrolling
+        const int adx = dx < 0 ? -dx : dx, ady = dy < 0 ? -dy : dy;
+        const float kw = (adx < ady ? adx : ady) == 0 ? 3.f / 8.f : ((adx < ady ? adx : ady) == 1 ? 1.f / 4.f : 1.f / 16.f);
+        const f3 dc = cv[r] - ct, dn = nv[r] - nt, dq = pv[r] - pt3;
+        const float e = dot3(dc, dc) * kc + dot3(dn, dn) * kn + dot3(dq, dq) * kp;
+        const float w = exp2f(-e) * kw;
+        sum[r] = sum[r] + ct * w;
+        cum[r] += w;
+      }
     }
   }
-  color_out[p] = make_float4(sum.x / cum_w, sum.y / cum_w, sum.z / cum_w, 0.f);
+#pragma unroll
+  for (int r = 0; r < ATR_R; ++r) {
+    if (!valid[r]) continue;
+    const int y = (q0 + r) * step + ph;
+    color_out[y * W + x] = make_float4(sum[r].x / cum[r], sum[r].y / cum[r], sum[r].z / cum[r], 0.f);
+  }
 }
-
 
 // ================================================================ launchers
 static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
@@ -360,9 +393,12 @@ void launch_atrous(const LaunchEnv& env, const DevCamera& cam, const DenoisePara
                    const float4* color_in, const float4* normal_depth, const float4* position,
                    float4* color_out, int step_width)
 {
-  dim3 grid(cdiv(cam.width, 32), cdiv(cam.height, 8));
-  atrous_kernel<<<grid, 256, 0, env.stream>>>(cam, dp, color_in, normal_depth, position,
-                                              color_out, step_width);
+  // rows are grouped per phase (y mod step): ATR_R outputs of one thread are `step` apart
+  const uint32_t nq = cdiv(cam.height, (uint32_t)step_width);
+  const uint32_t n_groups = cdiv(nq, ATR_R);
+  dim3 grid(cdiv(cam.width, 32), cdiv(n_groups * (uint32_t)step_width, 4));
+  atrous_kernel<<<grid, 128, 0, env.stream>>>(cam, dp, color_in, normal_depth, position,
+                                              color_out, step_width, (int)n_groups);
 }
 
 } // namespace pt

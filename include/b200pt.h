@@ -158,9 +158,9 @@ typedef struct pt_stats {
   uint32_t iterations;    /* PathTracer::iteration() */
   uint32_t passes;
   uint64_t kernel_launches;
-  double ms_raygen_extend0;
-  double ms_extend; /* sum over launches, profile=1 only */
-  double ms_shade;
+  double ms_raygen_extend0; /* raygen + classification kernel; profile=1 only */
+  double ms_extend;         /* BVH traversal kernel, summed over launches */
+  double ms_shade;          /* shade + scatter + classification + compaction kernel */
   double ms_compact;
   double ms_accumulate;
   double ms_denoise;
@@ -169,6 +169,7 @@ typedef struct pt_stats {
   uint64_t n_shade_launches;
   uint32_t max_bounce_reached;
   uint32_t reserved;
+  uint64_t rays_traversed; /* subset of `rays` that entered the BVH traversal queue */
 } pt_stats;
 
 typedef struct pt_scene_info {
