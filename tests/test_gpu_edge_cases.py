@@ -1,0 +1,165 @@
+"""GPU edge cases: ragged resolutions, degenerate scenes, object-order quirks, transformed
+instances — against the CPU oracle and, where built, the reference's own CUDA kernels."""
+import math
+
+import numpy as np
+import pytest
+
+import cuda_path_tracer_b200 as pt
+from cuda_path_tracer_b200 import DisplayBufferType as DB
+from tests import ref_lib
+from tests.test_gpu_parity import _check_hits, _rays_for, _secondary
+
+pytestmark = pytest.mark.gpu
+
+
+def _render(sd, spp, depth, method=pt.GPUMethod.megakernel):
+    w, h = sd.resolution
+    tr = pt.PathTracer(max_depth=depth)
+    tr.current_gpu_method = method
+    tr.max_iterations = spp
+    tr.create_buffers((w, h), sd)
+    tr.render(sd.camera, spp)
+    return tr.download(DB.color), tr.download(DB.normal), tr.download(DB.depth), int(tr.stats().rays), tr
+
+
+def _image_close(c, rc, frac=0.01):
+    diff = np.abs(c - rc).max(axis=2)
+    assert np.median(diff) < 1e-5
+    assert (diff > 1e-3).mean() < frac, (diff > 1e-3).mean()
+
+
+@pytest.mark.parametrize("w,h", [(33, 17), (8, 4), (7, 3), (2, 2), (257, 65)])
+def test_ragged_resolutions(oracle, w, h):
+    """Widths/heights that are not multiples of the 8x4 warp tile; tiny frames."""
+    sd = pt.three_balls(w, h)
+    rc, rn, rd, rrays = oracle.scene(sd).render(sd.camera, w, h, 2, 6)
+    c, n, d, rays, _ = _render(sd, 2, 6)
+    assert c.shape == (h, w, 3)
+    _image_close(c, rc, frac=0.03)
+    assert abs(rays - rrays) <= max(4, 0.01 * rrays)
+
+
+def _mixed_scene(w=80, h=48):
+    """Object order sphere, mesh, sphere, mesh with rotated / non-uniformly scaled instances,
+    a scaled sphere and all three material types."""
+    s = pt.SceneDescription()
+    s.add_material("a_ground", pt.Material.lambertian((0.7, 0.7, 0.6)))
+    s.add_material("b_metal", pt.Material.metal((0.8, 0.6, 0.2), 0.3))
+    s.add_material("c_glass", pt.Material.dielectric(1.5))
+    s.add_material("d_red", pt.Material.lambertian((0.7, 0.2, 0.2)))
+    s.add_mesh("blob", pt.bunny_like(2))
+    s.add_sphere(100.0, pt.translate((0.0, -100.5, -1.0)), "a_ground")
+    s.add_mesh_object("blob", pt.compose(pt.rotate(40, (0, 1, 0)), pt.scale((0.8, 1.2, 0.8)),
+                                         pt.translate((0.9, -0.5, -2.2))), "b_metal")
+    s.add_sphere(0.5, pt.compose(pt.scale(0.8), pt.translate((-0.2, -0.1, -1.4))), "c_glass")
+    s.add_mesh_object("blob", pt.compose(pt.scale(0.6), pt.rotate(-30, (1, 0, 0)),
+                                         pt.translate((-1.1, -0.4, -2.0))), "d_red")
+    s.camera = pt.Camera((0.0, 0.2, 0.5), (1.0, 0.0, 0.0, 0.0), math.radians(70.0))
+    s.resolution = (w, h)
+    return s
+
+
+def test_mixed_scene_hits_match_oracle(oracle):
+    sd = _mixed_scene()
+    w, h = sd.resolution
+    osc = oracle.scene(sd)
+    scene = pt.Scene.from_description(sd)
+    prim, rng = _rays_for(oracle, sd, w, h, n_random=8000)
+    ref = osc.trace_batch(prim, 0)
+    ours = scene.trace_batch(prim)
+    _check_hits(ours, ref, allow_frac=5e-4)
+    sec = _secondary(prim, ref, rng)
+    # secondary rays with non-unit directions (what a fuzzy metal bounce produces)
+    sec[::3, 4:7] *= 1.3
+    _check_hits(scene.trace_batch(sec), osc.trace_batch(sec, 0), allow_frac=2e-3)
+    assert set(np.unique(ref["object"][ref["t"] > 0])) >= {0, 1, 2, 3}
+
+
+def test_mixed_scene_image_matches_oracle(oracle):
+    sd = _mixed_scene()
+    w, h = sd.resolution
+    rc, rn, rd, rrays = oracle.scene(sd).render(sd.camera, w, h, 3, 10)
+    c, n, d, rays, _ = _render(sd, 3, 10)
+    _image_close(c, rc, frac=0.03)
+    assert abs(rays - rrays) <= 0.01 * rrays
+
+
+@pytest.mark.skipif(not ref_lib.have_ref_cuda(), reason="oracle/_ref/libref_cuda.so not built")
+def test_mixed_scene_matches_reference_cuda(oracle):
+    """Same scene against the reference's kernels: hits, megakernel image, streaming image."""
+    sd = _mixed_scene()
+    w, h = sd.resolution
+    ref = ref_lib.load_ref_cuda()
+    scene = pt.Scene.from_description(sd)
+    rt = ref.tracer(sd, w, h, 10, megakernel=True)
+    prim, rng = _rays_for(oracle, sd, w, h, n_random=8000)
+    theirs, ours = rt.trace_batch(prim), scene.trace_batch(prim)
+    miss = (ours["t"] < 0) != (theirs["t"] < 0)
+    both = (ours["t"] > 0) & (theirs["t"] > 0)
+    rel = np.abs(ours["t"][both] - theirs["t"][both]) / np.abs(theirs["t"][both])
+    assert miss.sum() + (rel > 1e-5).sum() <= 4
+    rt.render_timed(sd.camera, 3, 10)
+    c = _render(sd, 3, 10)[0]
+    _image_close(c, rt.download(1), frac=0.03)
+    rs = ref.tracer(sd, w, h, 10, megakernel=False)
+    _, rrays = rs.render_timed(sd.camera, 2, 10)
+    cs, _, _, rays, _ = _render(sd, 2, 10, method=pt.GPUMethod.streaming)
+    assert np.median(np.abs(cs - rs.download(1)).max(axis=2)) < 1e-5
+    assert abs(rays - rrays) <= 0.01 * rrays
+
+
+def test_single_triangle_and_mesh_only_scenes(oracle):
+    """Root-is-leaf BVH (1 and 3 triangles) and a scene without any sphere."""
+    for n_tri in (1, 3):
+        rng = np.random.default_rng(n_tri)
+        pos = rng.uniform(-1, 1, size=(3 * n_tri, 3)).astype(np.float32)
+        pos[:, 2] -= 3.0
+        s = pt.SceneDescription()
+        s.add_material("m", pt.Material.lambertian((0.5, 0.6, 0.7)))
+        s.add_mesh("t", pt.Mesh(pos, np.arange(3 * n_tri, dtype=np.uint32)))
+        s.add_mesh_object("t", pt.translate((0, 0, 0)), "m")
+        s.camera = pt.Camera((0, 0, 0), (1, 0, 0, 0), math.radians(60))
+        s.resolution = (64, 48)
+        rc, _, rd, rrays = oracle.scene(s).render(s.camera, 64, 48, 2, 4)
+        c, _, d, rays, _ = _render(s, 2, 4)
+        _image_close(c, rc, frac=0.02)
+        assert (rd < 1e5).sum() > 0 and abs(rays - rrays) <= max(2, 0.01 * rrays)
+
+
+def test_depth_one_and_sky_only(oracle):
+    sd = pt.three_balls(48, 32)
+    rc = oracle.scene(sd).render(sd.camera, 48, 32, 2, 1)[0]
+    c, _, _, rays, _ = _render(sd, 2, 1)
+    _image_close(c, rc)
+    assert rays == 48 * 32 * 2
+    # a scene whose only object is behind the camera: every path leaves after one ray
+    s = pt.SceneDescription()
+    s.add_material("m", pt.Material.lambertian((0.5, 0.5, 0.5)))
+    s.add_sphere(0.5, pt.translate((0, 0, 5)), "m")
+    s.camera = pt.Camera()
+    s.resolution = (32, 16)
+    c, n, d, rays, _ = _render(s, 1, 50)
+    assert rays == 32 * 16 and np.all(d == 1e6)
+    assert np.allclose(c, oracle.scene(s).render(s.camera, 32, 16, 1, 50)[0], atol=1e-6)
+
+
+def test_denoiser_on_ragged_frame(oracle):
+    sd = pt.three_balls(75, 41)
+    w, h = sd.resolution
+    rc, rn, rd, _ = oracle.scene(sd).render(sd.camera, w, h, 1, 5)
+    tr = pt.PathTracer(max_depth=5)
+    tr.create_buffers((w, h), sd)
+    tr.upload_frame(rc, rn, rd, sd.camera)
+    # filter 31 taints all 41 rows in reference mode (2*(1+2+4+8+16) = 62), so it is also
+    # checked with the sane clamp, where every pixel is defined
+    for fs, fix in ((3, False), (31, True), (31, False)):
+        tr.atrous_denoiser.filter_size = fs
+        tr.atrous_denoiser.clamp_fix = fix
+        tr.denoise()
+        ours = tr.download(DB.denoised)
+        ref, taint = oracle.denoise(sd.camera, rc, rn, rd, fs, clamp_fix=fix)
+        assert np.abs(ours - ref).max(axis=2)[~taint].max(initial=0.0) <= 1e-4
+        assert np.isfinite(ours).all()
+        if fix:
+            assert not taint.any()
