@@ -584,7 +584,37 @@ static int render_pass(pt_ctx* c, const pt_camera& cam, uint32_t first_iteration
   PT_CUDA(cudaMemsetAsync(c->d_counters, 0, c->counters_bytes, c->stream));
   int q = 0;
   uint32_t launched = 0;
-  for (uint32_t b = 0; b < max_depth; ++b) {
+  if (!stable) {
+    // ---- PT_RNG_PIXEL_STREAM: asynchronous chains.  chain_kernel shades every path in
+    // registers until its next ray needs the BVH; only those rays are queued, traversed and
+    // handed back.  Iteration `it` traverses queue[it & 1] (length tcounters[it]).
+    prof_begin(c, TAG_EXT0);
+    launch_chain(env, c->scene->dev, c->pb, pp, 0, n0, max_depth);
+    prof_end(c);
+    launched += 1;
+    if (c->scene->dev.n_tris != 0) {
+      for (uint32_t it = 0; it < max_depth; ++it) {
+        PT_CUDA(cudaMemcpyAsync(&c->h_counts[it], c->pb.tcounters + it, sizeof(uint32_t),
+                                cudaMemcpyDeviceToHost, c->stream));
+        PT_CUDA(cudaEventRecord(c->bounce_events[it], c->stream));
+        if (it >= kLookBehind) {
+          // look-behind early exit: stop enqueueing iterations once an older queue is known
+          // to have been empty; never blocks the host.
+          const uint32_t probe = it - kLookBehind;
+          if (cudaEventQuery(c->bounce_events[probe]) == cudaSuccess && c->h_counts[probe] == 0) break;
+        }
+        prof_begin(c, TAG_EXT);
+        launch_traverse(env, c->scene->dev, c->pb, c->pb.queue[it & 1], it);
+        prof_end(c);
+        prof_begin(c, TAG_SHADE);
+        launch_chain(env, c->scene->dev, c->pb, pp, it + 1, n0, max_depth);
+        prof_end(c);
+        launched += 2;
+        c->stats.max_bounce_reached = std::max(c->stats.max_bounce_reached, it + 1);
+      }
+    }
+  }
+  for (uint32_t b = 0; stable && b < max_depth; ++b) {
     if (b >= kLookBehind + 1) {
       // look-behind early exit: stop enqueueing bounces once an older bounce is
       // known to have produced no survivors; never blocks the host.
@@ -600,7 +630,7 @@ static int render_pass(pt_ctx* c, const pt_camera& cam, uint32_t first_iteration
     }
     if (c->scene->dev.n_tris != 0) {
       prof_begin(c, TAG_EXT);
-      launch_traverse(env, c->scene->dev, c->pb, b);
+      launch_traverse(env, c->scene->dev, c->pb, c->pb.tq, b);
       prof_end(c);
       launched += 1;
     }

@@ -108,9 +108,12 @@ accumulate_kernel(const PathState ps, const PassParams pp, float4* __restrict__ 
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p == 0) {
     // rays = live paths entering extend, summed over bounces (counters[0] is host-known)
-    unsigned long long r = (unsigned long long)pp.pixels * pp.samples;
-    for (uint32_t b = 1; b < max_depth; ++b) r += counters[b];
-    total_rays[0] += r;
+    // (bounce-synchronous mode only: chain_kernel counts its own rays)
+    if (pp.rng_mode == 1u) {
+      unsigned long long r = (unsigned long long)pp.pixels * pp.samples;
+      for (uint32_t b = 1; b < max_depth; ++b) r += counters[b];
+      total_rays[0] += r;
+    }
     // rays that entered the BVH traversal queue (tcounters follow counters and work cursors)
     const uint32_t* tc = counters + 2 * (max_depth + 2);
     unsigned long long tr = 0;

@@ -28,7 +28,13 @@ void launch_raygen(const LaunchEnv& env, const DevScene& sc, const PassBuffers& 
                    const PassParams& pp, uint32_t n_items);
 // BVH traversal of the traverse queue of `bounce` (length tcounters[bounce], device side).
 void launch_traverse(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb,
-                     uint32_t bounce);
+                     const uint32_t* tq, uint32_t bounce);
+// PT_RNG_PIXEL_STREAM scheduler: iter 0 = raygen + in-register chains of simple bounces for
+// the primary samples; iter >= 1 = the same for the paths traverse_kernel just served
+// (queue[(iter-1)&1], tcounters[iter-1]).  Paths whose next ray needs the BVH are parked in
+// queue[iter&1] / tcounters[iter].
+void launch_chain(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb,
+                  const PassParams& pp, uint32_t iter, uint32_t n_items_first, uint32_t max_depth);
 // shade bounce b over queue q (implicit tile order when bounce == 0): hit rebuild, material,
 // scatter, classification of the new ray; survivors -> queue q^1 / counters[b+1] (or flags for
 // the stable compaction), BVH candidates -> tq / tcounters[b+1].

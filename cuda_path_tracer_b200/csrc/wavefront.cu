@@ -676,6 +676,105 @@ shade_kernel(const DevScene sc, const PathState ps, const PassParams pp,
   }
 }
 
+// ==================================================================== chain
+// PT_RNG_PIXEL_STREAM scheduler.  Paths carry their own RNG stream and depth, so nothing forces
+// all paths to advance bounce by bounce: a thread keeps shading its path IN REGISTERS for as
+// long as the next ray is "simple" (classification proves it never enters the mesh BVH: it hits
+// a sphere or the sky) and only parks it — ray 32 B, throughput 16 B, aux 16 B, path id 4 B —
+// when a ray needs the traversal kernel.  In open scenes most rays are simple (59 % in the
+// bunny scene), so most bounces never touch HBM, and the queue that does go through
+// traverse_kernel is homogeneous.  The counted quantity is unchanged: one ray per intersection
+// resolved (== paths entering the reference's intersection_kernel, path_tracer.cu:428).
+//   FIRST: items are the tile-ordered primary samples (raygen fused);
+//   else : items are the paths whose ray traverse_kernel just finished.
+template <bool FIRST>
+__global__ void __launch_bounds__(FULL_THREADS)
+chain_kernel(const DevScene sc, const PathState ps, const PassParams pp,
+             const uint32_t* __restrict__ queue, const uint32_t* __restrict__ n_ptr,
+             uint32_t n_first, uint32_t* __restrict__ next_queue,
+             uint32_t* __restrict__ next_count, uint32_t max_depth,
+             unsigned long long* __restrict__ total_rays)
+{
+  const uint32_t n = FIRST ? n_first : *n_ptr;
+  const uint32_t n_round = (n + 31u) & ~31u;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  uint32_t rays_local = 0;
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_round; idx += stride) {
+    uint32_t pid = 0, pixel, s;
+    bool valid = idx < n;
+    if (valid) {
+      if (FIRST) {
+        valid = first_item(pp, idx, pid, pixel, s);
+      } else {
+        pid = queue[idx];
+      }
+    }
+    bool park = false; // the path leaves this kernel with a ray that needs the BVH
+    if (valid) {
+      f3 o, d, color;
+      float tmin, tbest;
+      uint32_t rng, code, depth;
+      int start = 0;
+      bool need_traversal;
+      if (FIRST) {
+        // raygen_kernel (ray_gen.cu:11-32): seed, jitter (x then y), pinhole ray
+        rng = minstd_seed(wang_hash(wang_hash(pixel) ^ (pp.first_iteration + s)));
+        const uint32_t y = pixel / pp.cam.width, x = pixel - y * pp.cam.width;
+        const float fx = (float)x + minstd_uniform(rng);
+        const float fy = (float)y + minstd_uniform(rng);
+        camera_ray(pp.cam, fx, fy, o, d);
+        tmin = 1e-4f;
+        color = mk3(1.0f, 1.0f, 1.0f);
+        depth = 0;
+        need_traversal = classify(sc, o, d, tmin, FLT_MAX, tbest, code, start);
+      } else {
+        const float4 ro = ps.ray[2 * (size_t)pid];
+        const float4 rd = ps.ray[2 * (size_t)pid + 1];
+        const float4 th = ps.thr[pid];
+        const uint4 ax = ps.aux[pid];
+        o = xyz(ro), d = xyz(rd);
+        tmin = ro.w;
+        color = xyz(th);
+        rng = __float_as_uint(th.w);
+        tbest = __uint_as_float(ax.x);
+        code = ax.y;
+        depth = ax.w;
+        need_traversal = false; // traverse_kernel has refined aux already
+      }
+      for (;;) {
+        if (need_traversal) {
+          ps.ray[2 * (size_t)pid] = mk4(o, tmin);
+          ps.ray[2 * (size_t)pid + 1] = mk4(d, FLT_MAX);
+          ps.aux[pid] = make_uint4(__float_as_uint(tbest), code, (uint32_t)start, depth);
+          park = true;
+          break;
+        }
+        ++rays_local;
+        Hit h;
+        const bool hit = resolve_hit(sc, o, d, tmin, tbest, code, h);
+        if (depth == 0u) {
+          ps.gbuf[pid] = hit ? make_float4(h.n.x, h.n.y, h.n.z, h.t)
+                             : make_float4(-d.x, -d.y, -d.z, 1e6f);
+        }
+        if (!hit) {
+          color = color * sky_color(d);
+          break;
+        }
+        const DevMaterial mat = sc.materials[h.material];
+        scatter(mat, h, o, d, tmin, color, rng);
+        if (++depth == max_depth) break; // survivors contribute their throughput (path_tracer.cu:252-265)
+        need_traversal = classify(sc, o, d, tmin, FLT_MAX, tbest, code, start);
+      }
+      ps.thr[pid] = mk4(color, __uint_as_float(rng));
+    }
+    warp_append(park, pid, next_queue, next_count, lane);
+  }
+  // one 64-bit atomic per warp for the ray counter
+  for (int off = 16; off > 0; off >>= 1) rays_local += __shfl_down_sync(0xffffffffu, rays_local, off);
+  if (lane == 0 && rays_local != 0u) atomicAdd(total_rays, (unsigned long long)rays_local);
+}
+
 // ================================================================ launchers
 static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
@@ -709,11 +808,27 @@ void launch_raygen(const LaunchEnv& env, const DevScene& sc, const PassBuffers& 
 }
 
 void launch_traverse(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb,
-                     uint32_t bounce)
+                     const uint32_t* tq, uint32_t bounce)
 {
   traverse_kernel<SRC_QUEUE><<<traverse_grid<SRC_QUEUE>(env), EXT_THREADS, 0, env.stream>>>(
-      sc, pb.ps, pb.tq, pb.tcounters + bounce, 0u, pb.work + bounce, nullptr, nullptr,
+      sc, pb.ps, tq, pb.tcounters + bounce, 0u, pb.work + bounce, nullptr, nullptr,
       tune("PT_REFILL", EXT_REFILL), tune("PT_INNER_MIN", EXT_INNER_MIN));
+}
+
+void launch_chain(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb,
+                  const PassParams& pp, uint32_t iter, uint32_t n_items_first, uint32_t max_depth)
+{
+  const uint32_t grid = (uint32_t)env.sms * 6u;
+  if (iter == 0) {
+    chain_kernel<true><<<min(grid, cdiv(n_items_first, FULL_THREADS)), FULL_THREADS, 0, env.stream>>>(
+        sc, pb.ps, pp, nullptr, nullptr, n_items_first, pb.queue[0], pb.tcounters + 0, max_depth,
+        pb.total_rays);
+  } else {
+    // consumes the traversed queue of iteration iter-1, produces the queue of iteration iter
+    chain_kernel<false><<<grid, FULL_THREADS, 0, env.stream>>>(
+        sc, pb.ps, pp, pb.queue[(iter - 1) & 1], pb.tcounters + (iter - 1), 0u, pb.queue[iter & 1],
+        pb.tcounters + iter, max_depth, pb.total_rays);
+  }
 }
 
 void launch_shade(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb,
