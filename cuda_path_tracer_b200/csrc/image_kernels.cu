@@ -254,7 +254,12 @@ denoise_prepare_kernel(const DevCamera cam, const float4* __restrict__ sum_color
 // pixel (0, v+1) while its position is still rebuilt from the ray through (W+0.5, v+0.5);
 // reads that would fall past the end of the buffer (undefined in the reference) use the last
 // row / last pixel instead.  clamp_fix selects the sane W-1/H-1 clamp.
-#define ATR_R 4
+#ifndef ATR_R
+#define ATR_R 2
+#endif
+#ifndef ATR_JUNROLL
+#define ATR_JUNROLL 6
+#endif
 
 __global__ void __launch_bounds__(128)
 atrous_kernel(const DevCamera cam, const DenoiseParams dp, const float4* __restrict__ color_in,
@@ -291,7 +296,8 @@ atrous_kernel(const DevCamera cam, const DenoiseParams dp, const float4* __restr
     cum[r] = 0.f;
   }
 
-#pragma unroll
+  constexpr int kJUnroll = ATR_JUNROLL;
+#pragma unroll kJUnroll
   for (int j = -2; j < ATR_R + 2; ++j) {
     const int v = min(max((q0 + j) * step + ph, 0), vmax);
 #pragma unroll

@@ -429,7 +429,9 @@ raygen_kernel(const DevScene sc, const PathState ps, const PassParams pp, uint32
 // EXT_REFILL lanes are still walking, so the warp stays populated although per-ray traversal
 // lengths vary by orders of magnitude.
 #define EXT_THREADS 128
+#ifndef EXT_MIN_BLOCKS
 #define EXT_MIN_BLOCKS 8
+#endif
 #define EXT_REFILL 16
 #define EXT_INNER_MIN 8
 
