@@ -40,6 +40,50 @@ class EdgeAvoidingATrousDenoiser:
     clamp_fix: bool = False
 
 
+class HostBVH:
+    """Host-only build of both trees (no CUDA call): structure checks and build timing."""
+
+    def __init__(self, desc: SceneDescription, wide: bool = True):
+        lib = load_library()
+        d, keep = desc.to_desc()
+        self._h = C.c_void_p()
+        self.info = _abi.pt_scene_info()
+        check(lib.pt_host_bvh_build(C.byref(d), 1 if wide else 0, C.byref(self._h), C.byref(self.info)))
+        del keep
+
+    def violations(self) -> int:
+        n = C.c_uint64()
+        check(load_library().pt_host_bvh_validate(self._h, C.byref(n)))
+        return int(n.value)
+
+    def arrays(self):
+        """(binary nodes [n,16] f32, wide nodes [n8,20] u32, triangles [t,12] f32) as numpy copies."""
+        a, b, t = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(load_library().pt_host_bvh_arrays(self._h, C.byref(a), C.byref(b), C.byref(t)))
+        i = self.info
+
+        def view(ptr, n, w, ct, dt):
+            if not ptr.value or n == 0:
+                return np.zeros((0, w), dtype=dt)
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(n, w)).astype(dt, copy=True)
+
+        n_tris = int(i.n_world_triangles) + (1 if int(i.n_bvh_nodes) == 1 else 0)
+        return (view(a, int(i.n_bvh_nodes), 16, C.c_float, np.float32),
+                view(b, int(i.n_bvh8_nodes), 20, C.c_uint32, np.uint32),
+                view(t, n_tris, 12, C.c_float, np.float32))
+
+    def close(self):
+        if self._h:
+            load_library().pt_host_bvh_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Scene:
     """Device-resident scene == Scene/Aggregate (scene.hpp:23-67) after build_scene()."""
 

@@ -21,7 +21,6 @@ namespace pt {
 namespace {
 
 constexpr int kBins = 16;
-constexpr int kLeafMax = 4;
 constexpr int kSahDepthLimit = 32; // beyond this depth: balanced median splits
 constexpr float kTravCost = 1.0f;
 constexpr float kIsectCost = 1.0f;
@@ -99,6 +98,7 @@ struct BuildNode {
 };
 
 struct Builder {
+  int kLeafMax = 4; // 3 when the compressed 8-wide tree is derived from this one
   std::vector<Prim> prims;
   std::vector<BuildNode> nodes;
   std::atomic<uint32_t> n_nodes{0};
@@ -292,15 +292,230 @@ inline float u2f(uint32_t u)
   return f;
 }
 
+// ------------------------------------------------------------------ 8-wide collapse
+// Compressed wide BVH in the spirit of Ylitie, Karras, Laine, "Efficient Incoherent Ray
+// Traversal on GPUs Through Compressed Wide BVHs" (HPG 2017), derived from the binary tree:
+// every wide node absorbs binary descendants (largest surface area first) until it has up to
+// eight children; children are placed in octant-ordered slots; child boxes are quantised to
+// 8 bits per plane on a per-node power-of-two grid, always outwards.
+struct WideTmp {
+  uint32_t child[8]; // binary node per slot, ~0u = empty
+  uint32_t n_inner = 0, n_tris = 0;
+};
+
+struct WideBuilder {
+  const Builder& B;
+  std::vector<uint32_t> bnode; // binary node of every wide node (breadth-first)
+  std::vector<uint32_t> new_first; // per binary leaf: position of its first triangle in the new order
+  std::vector<uint32_t> order;     // new triangle position -> index into B.prims
+  explicit WideBuilder(const Builder& b) : B(b) {}
+
+  static Box padded(const Box& b)
+  {
+    Box r;
+    for (int a = 0; a < 3; ++a) {
+      r.lo[a] = pad_lo(b.lo[a], b.hi[a]);
+      r.hi[a] = pad_hi(b.lo[a], b.hi[a]);
+    }
+    return r;
+  }
+
+  void gather(uint32_t b, WideTmp& w) const
+  {
+    uint32_t ch[8];
+    int n = 0;
+    const BuildNode& nd = B.nodes[b];
+    if (nd.count != 0) {
+      ch[n++] = b; // the whole tree is one leaf
+    } else {
+      ch[n++] = nd.left;
+      ch[n++] = nd.right;
+      while (n < 8) {
+        int pick = -1;
+        float best = -1.f;
+        for (int i = 0; i < n; ++i) {
+          const BuildNode& c = B.nodes[ch[i]];
+          if (c.count != 0) continue;
+          const float a = c.box.area();
+          if (a > best) {
+            best = a;
+            pick = i;
+          }
+        }
+        if (pick < 0) break;
+        const BuildNode& c = B.nodes[ch[pick]];
+        ch[pick] = c.left;
+        ch[n++] = c.right;
+      }
+    }
+    // octant-ordered slots: slot bit a set = the child lies towards +axis a of the node centre;
+    // greedy assignment of the (child, slot) pair with the largest projection
+    float cen[3];
+    for (int a = 0; a < 3; ++a) cen[a] = 0.5f * (nd.box.lo[a] + nd.box.hi[a]);
+    float cost[8][8];
+    for (int i = 0; i < n; ++i) {
+      const Box& cb = B.nodes[ch[i]].box;
+      float d[3];
+      for (int a = 0; a < 3; ++a) d[a] = 0.5f * (cb.lo[a] + cb.hi[a]) - cen[a];
+      for (int s = 0; s < 8; ++s)
+        cost[i][s] = ((s & 1) ? d[0] : -d[0]) + ((s & 2) ? d[1] : -d[1]) + ((s & 4) ? d[2] : -d[2]);
+    }
+    for (int s = 0; s < 8; ++s) w.child[s] = 0xffffffffu;
+    bool used_c[8] = {false, false, false, false, false, false, false, false};
+    for (int k = 0; k < n; ++k) {
+      int bi = -1, bs = -1;
+      float bc = -FLT_MAX;
+      for (int i = 0; i < n; ++i) {
+        if (used_c[i]) continue;
+        for (int s = 0; s < 8; ++s) {
+          if (w.child[s] != 0xffffffffu) continue;
+          if (cost[i][s] > bc) {
+            bc = cost[i][s];
+            bi = i;
+            bs = s;
+          }
+        }
+      }
+      used_c[bi] = true;
+      w.child[bs] = ch[bi];
+    }
+    w.n_inner = 0;
+    w.n_tris = 0;
+    for (int s = 0; s < 8; ++s) {
+      if (w.child[s] == 0xffffffffu) continue;
+      const BuildNode& c = B.nodes[w.child[s]];
+      if (c.count != 0) {
+        w.n_tris += c.count;
+      } else {
+        w.n_inner++;
+      }
+    }
+  }
+
+  // 80-byte node, 20 words:
+  //   0..2 p (grid origin)   3 = ex' | ey'<<8 | ez'<<16 | imask<<24   (e' = biased exponent - 8)
+  //   4 child base   5 triangle base   6..7 meta[8]
+  //   8..9 qlo.x[8]  10..11 qlo.y[8]  12..13 qlo.z[8]  14..15 qhi.x[8]  16..17 qhi.y[8]  18..19 qhi.z[8]
+  void emit(uint32_t b, const WideTmp& w, uint32_t child_base, uint32_t tri_base, uint32_t* o)
+  {
+    const Box nb = padded(B.nodes[b].box);
+    float p[3];
+    int eb[3];
+    double scale[3];
+    Box cbx[8];
+    for (int s = 0; s < 8; ++s)
+      if (w.child[s] != 0xffffffffu) cbx[s] = padded(B.nodes[w.child[s]].box);
+    for (int a = 0; a < 3; ++a) {
+      const float ext0 = nb.hi[a] - nb.lo[a];
+      p[a] = nb.lo[a] - (ext0 * 3e-5f + 1e-30f);
+      const double ext = (double)nb.hi[a] - (double)p[a];
+      int e = ext > 0.0 ? (int)std::ceil(std::log2(ext / 255.0)) : -110;
+      e = std::max(e, -110);
+      for (;; ++e) {
+        const double sc = std::ldexp(1.0, e);
+        bool ok = true;
+        for (int s = 0; s < 8 && ok; ++s) {
+          if (w.child[s] == 0xffffffffu) continue;
+          if (std::ceil(((double)cbx[s].hi[a] - (double)p[a]) / sc + 1.0 / 64.0) > 255.0) ok = false;
+        }
+        if (ok) break;
+      }
+      eb[a] = e + 127;
+      scale[a] = std::ldexp(1.0, e);
+    }
+    uint8_t q[6][8];
+    uint8_t meta[8];
+    uint32_t imask = 0, tri_off = 0;
+    for (int s = 0; s < 8; ++s) {
+      if (w.child[s] == 0xffffffffu) {
+        for (int a = 0; a < 3; ++a) {
+          q[a][s] = 255;
+          q[3 + a][s] = 0;
+        }
+        meta[s] = 0;
+        continue;
+      }
+      for (int a = 0; a < 3; ++a) {
+        double lo = std::floor(((double)cbx[s].lo[a] - (double)p[a]) / scale[a] - 1.0 / 64.0);
+        double hi = std::ceil(((double)cbx[s].hi[a] - (double)p[a]) / scale[a] + 1.0 / 64.0);
+        lo = std::min(std::max(lo, 0.0), 255.0);
+        hi = std::min(std::max(hi, 0.0), 255.0);
+        q[a][s] = (uint8_t)lo;
+        q[3 + a][s] = (uint8_t)hi;
+      }
+      const BuildNode& c = B.nodes[w.child[s]];
+      if (c.count != 0) {
+        meta[s] = (uint8_t)((((1u << c.count) - 1u) << 5) | tri_off); // unary count | offset
+        new_first[w.child[s]] = tri_base + tri_off;
+        for (uint32_t k = 0; k < c.count; ++k) order[tri_base + tri_off + k] = c.first + k;
+        tri_off += c.count;
+      } else {
+        meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
+        imask |= 1u << s;
+      }
+    }
+    std::memcpy(o + 0, p, 12);
+    o[3] = (uint32_t)(eb[0] - 8) | ((uint32_t)(eb[1] - 8) << 8) | ((uint32_t)(eb[2] - 8) << 16) | (imask << 24);
+    o[4] = child_base;
+    o[5] = tri_base;
+    std::memcpy(o + 6, meta, 8);
+    for (int k = 0; k < 6; ++k) std::memcpy(o + 8 + 2 * k, q[k], 8);
+  }
+
+  void run(uint32_t root, uint32_t n_prims, FlatBVH& out)
+  {
+    new_first.assign(B.n_nodes.load(), 0u);
+    order.assign(n_prims, 0u);
+    bnode.clear();
+    bnode.push_back(root);
+    std::vector<WideTmp> tmp;
+    std::vector<uint32_t> cbase, tbase;
+    uint32_t level_begin = 0, next_tri = 0, depth = 0;
+    while (level_begin < bnode.size()) {
+      const uint32_t level_end = (uint32_t)bnode.size();
+      const uint32_t nl = level_end - level_begin;
+      tmp.resize(nl);
+      cbase.resize(nl);
+      tbase.resize(nl);
+#pragma omp parallel for schedule(static) if (nl > 256)
+      for (long long i = 0; i < (long long)nl; ++i) gather(bnode[level_begin + i], tmp[i]);
+      uint32_t next_node = level_end;
+      for (uint32_t i = 0; i < nl; ++i) {
+        cbase[i] = next_node;
+        tbase[i] = next_tri;
+        next_node += tmp[i].n_inner;
+        next_tri += tmp[i].n_tris;
+      }
+      bnode.resize(next_node);
+      out.nodes8.resize((size_t)next_node * 20); // grows level by level
+#pragma omp parallel for schedule(static) if (nl > 256)
+      for (long long i = 0; i < (long long)nl; ++i) {
+        uint32_t r = 0;
+        for (int s = 0; s < 8; ++s) {
+          const uint32_t c = tmp[i].child[s];
+          if (c != 0xffffffffu && B.nodes[c].count == 0) bnode[cbase[i] + r++] = c;
+        }
+        emit(bnode[level_begin + i], tmp[i], cbase[i], tbase[i], &out.nodes8[(size_t)(level_begin + i) * 20]);
+      }
+      level_begin = level_end;
+      ++depth;
+    }
+    out.n_nodes8 = (uint32_t)bnode.size();
+    out.nodes8.resize((size_t)out.n_nodes8 * 20);
+    out.depth8 = depth;
+  }
+};
+
 } // namespace
 
-void build_bvh(const std::vector<BuildTri>& tris, FlatBVH& out)
+void build_bvh(const std::vector<BuildTri>& tris, FlatBVH& out, bool wide)
 {
   out = FlatBVH{};
   const size_t n = tris.size();
   if (n == 0) return;
 
   Builder B;
+  B.kLeafMax = wide ? 3 : 4;
   B.prims.resize(n);
   B.nodes.resize(2 * n);
   Box root_box, root_cb;
@@ -336,6 +551,10 @@ void build_bvh(const std::vector<BuildTri>& tris, FlatBVH& out)
     B.build(root, 0, (uint32_t)n, 0, root_box, root_cb);
   }
 
+  // ---- wide tree first: it decides the triangle order both trees share
+  WideBuilder W(B);
+  if (wide) W.run(root, (uint32_t)n, out);
+
   // ---- flatten: inner nodes in DFS pre-order, triangles in leaf order
   const bool root_is_leaf = B.nodes[root].count != 0;
   for (int a = 0; a < 3; ++a) {
@@ -348,7 +567,7 @@ void build_bvh(const std::vector<BuildTri>& tris, FlatBVH& out)
   out.tris.resize((size_t)out.n_tris * 12);
 #pragma omp parallel for schedule(static)
   for (long long i = 0; i < (long long)n; ++i) {
-    const BuildTri& t = tris[B.prims[i].id];
+    const BuildTri& t = tris[B.prims[wide ? W.order[i] : (uint32_t)i].id];
     float* o = &out.tris[(size_t)i * 12];
     o[0] = t.v0[0], o[1] = t.v0[1], o[2] = t.v0[2], o[3] = u2f(t.prim);
     o[4] = t.v1[0] - t.v0[0], o[5] = t.v1[1] - t.v0[1], o[6] = t.v1[2] - t.v0[2];
@@ -421,11 +640,177 @@ void build_bvh(const std::vector<BuildTri>& tris, FlatBVH& out)
     float* o = &out.nodes[(size_t)inner_index[ni] * 16];
     const BuildNode& l = B.nodes[nd.left];
     const BuildNode& r = B.nodes[nd.right];
-    write_child(o, 0, l, l.count ? leaf_code(l.first, l.count) : inner_index[nd.left]);
-    write_child(o, 1, r, r.count ? leaf_code(r.first, r.count) : inner_index[nd.right]);
+    const uint32_t lf = wide ? W.new_first[nd.left] : l.first, rf = wide ? W.new_first[nd.right] : r.first;
+    write_child(o, 0, l, l.count ? leaf_code(lf, l.count) : inner_index[nd.left]);
+    write_child(o, 1, r, r.count ? leaf_code(rf, r.count) : inner_index[nd.right]);
   }
   out.sah_cost = sah;
   out.depth = B.max_depth.load() + 1;
+}
+
+
+// ------------------------------------------------------------------- validation
+namespace {
+struct DBox {
+  double lo[3], hi[3];
+  void reset()
+  {
+    for (int a = 0; a < 3; ++a) lo[a] = 1e300, hi[a] = -1e300;
+  }
+  void grow(const DBox& b)
+  {
+    for (int a = 0; a < 3; ++a) lo[a] = std::min(lo[a], b.lo[a]), hi[a] = std::max(hi[a], b.hi[a]);
+  }
+  bool inside(const DBox& outer) const
+  {
+    for (int a = 0; a < 3; ++a)
+      if (lo[a] < outer.lo[a] || hi[a] > outer.hi[a]) return false;
+    return true;
+  }
+};
+
+struct Validator {
+  const FlatBVH& b;
+  std::vector<uint8_t> ref2, ref8;
+  uint64_t bad = 0;
+  explicit Validator(const FlatBVH& f) : b(f), ref2(f.n_tris, 0), ref8(f.n_tris, 0) {}
+
+  DBox tri_box(uint32_t t) const
+  {
+    const float* o = &b.tris[(size_t)t * 12];
+    DBox r;
+    r.reset();
+    for (int k = 0; k < 3; ++k) {
+      for (int a = 0; a < 3; ++a) {
+        // the vertices as the kernel sees them: v0, v0 + e1, v0 + e2
+        const double v = k == 0 ? (double)o[a] : (double)o[a] + (double)o[4 * k + a];
+        r.lo[a] = std::min(r.lo[a], v);
+        r.hi[a] = std::max(r.hi[a], v);
+      }
+    }
+    return r;
+  }
+
+  // binary tree: content box of a child reference, checked against the box stored in the parent
+  DBox walk2(int32_t ref, int depth)
+  {
+    DBox content;
+    content.reset();
+    if (depth > 64) {
+      ++bad;
+      return content;
+    }
+    if (ref < 0) {
+      const uint32_t code = (uint32_t)~ref;
+      const uint32_t first = code >> 3, count = (code & 7u) + 1u;
+      for (uint32_t k = 0; k < count; ++k) {
+        if (first + k >= b.n_tris) {
+          ++bad;
+          continue;
+        }
+        if (ref2[first + k]++) ++bad;
+        content.grow(tri_box(first + k));
+      }
+      return content;
+    }
+    if ((uint32_t)ref >= b.n_nodes) {
+      ++bad;
+      return content;
+    }
+    const float* nd = &b.nodes[(size_t)ref * 16];
+    for (int c = 0; c < 2; ++c) {
+      DBox stored;
+      const int o = c * 4, z = 8 + c * 2;
+      stored.lo[0] = nd[o + 0], stored.hi[0] = nd[o + 1];
+      stored.lo[1] = nd[o + 2], stored.hi[1] = nd[o + 3];
+      stored.lo[2] = nd[z + 0], stored.hi[2] = nd[z + 1];
+      int32_t child;
+      std::memcpy(&child, &nd[12 + c], 4);
+      const DBox cc = walk2(child, depth + 1);
+      if (cc.lo[0] <= cc.hi[0] && !cc.inside(stored)) ++bad;
+      content.grow(cc);
+    }
+    return content;
+  }
+
+  DBox walk8(uint32_t node, uint32_t depth)
+  {
+    DBox content;
+    content.reset();
+    if (node >= b.n_nodes8 || depth > b.depth8) {
+      ++bad;
+      return content;
+    }
+    const uint32_t* w = &b.nodes8[(size_t)node * 20];
+    float p[3];
+    std::memcpy(p, w, 12);
+    double scale[3];
+    for (int a = 0; a < 3; ++a) scale[a] = std::ldexp(1.0, (int)((w[3] >> (8 * a)) & 0xffu) + 8 - 127);
+    const uint32_t imask = w[3] >> 24;
+    const uint8_t* meta = reinterpret_cast<const uint8_t*>(w + 6);
+    const uint8_t* q = reinterpret_cast<const uint8_t*>(w + 8);
+    for (int s = 0; s < 8; ++s) {
+      const uint32_t m = meta[s];
+      if (m == 0) {
+        if (imask & (1u << s)) ++bad;
+        continue;
+      }
+      DBox stored;
+      for (int a = 0; a < 3; ++a) {
+        stored.lo[a] = (double)p[a] + q[8 * a + s] * scale[a];
+        stored.hi[a] = (double)p[a] + q[8 * (3 + a) + s] * scale[a];
+      }
+      DBox cc;
+      cc.reset();
+      if ((m & 31u) >= 24u) {
+        if ((m & 31u) != 24u + (uint32_t)s || (m >> 5) != 1u || !(imask & (1u << s))) ++bad;
+        uint32_t rel = 0;
+        for (int k = 0; k < s; ++k) rel += (imask >> k) & 1u;
+        cc = walk8(w[4] + rel, depth + 1);
+      } else {
+        if (imask & (1u << s)) ++bad;
+        const uint32_t un = m >> 5, count = un == 1 ? 1 : (un == 3 ? 2 : (un == 7 ? 3 : 0));
+        if (count == 0) ++bad;
+        for (uint32_t k = 0; k < count; ++k) {
+          const uint32_t t = w[5] + (m & 31u) + k;
+          if (t >= b.n_tris || (m & 31u) + k >= 24u) {
+            ++bad;
+            continue;
+          }
+          if (ref8[t]++) ++bad;
+          cc.grow(tri_box(t));
+        }
+      }
+      if (cc.lo[0] <= cc.hi[0] && !cc.inside(stored)) ++bad;
+      content.grow(cc);
+    }
+    return content;
+  }
+};
+} // namespace
+
+uint64_t validate_bvh(const FlatBVH& bvh)
+{
+  if (bvh.n_tris == 0) return 0;
+  Validator v(bvh);
+  const uint32_t real_tris = (uint32_t)(bvh.tris.size() / 12);
+  (void)real_tris;
+  v.walk2(0, 0);
+  // the binary root-leaf form carries one null triangle nothing else references
+  uint32_t null_tri = 0xffffffffu;
+  if (bvh.n_nodes == 1) {
+    uint32_t last;
+    std::memcpy(&last, &bvh.tris[(size_t)(bvh.n_tris - 1) * 12 + 3], 4);
+    if (last == 0xffffffffu) null_tri = bvh.n_tris - 1;
+  }
+  for (uint32_t t = 0; t < bvh.n_tris; ++t)
+    if (v.ref2[t] != 1) ++v.bad;
+  if (bvh.n_nodes8 != 0) {
+    v.walk8(0, 0);
+    for (uint32_t t = 0; t < bvh.n_tris; ++t)
+      if (v.ref8[t] != (t == null_tri ? 0 : 1)) ++v.bad;
+  }
+  return v.bad;
 }
 
 } // namespace pt

@@ -22,12 +22,26 @@ struct FlatBVH {
   uint32_t depth = 0;
   double sah_cost = 0.0;
   float root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0}; // padded bounds of everything
+  // compressed 8-wide tree over the same triangle array (layout: common.cuh), breadth-first
+  std::vector<uint32_t> nodes8; // 20 words (80 B) per node
+  uint32_t n_nodes8 = 0;
+  uint32_t depth8 = 0;
 };
 
 // Binned-SAH (16 bins x 3 axes) top-down build, <= 4 triangles per leaf,
 // OpenMP task-parallel; depth is bounded so the 64-entry traversal stack of
 // the extend kernel can never overflow (the reference's 24-entry stack is
 // unchecked, src/lib/static_stack.hpp:21-25).
-void build_bvh(const std::vector<BuildTri>& tris, FlatBVH& out);
+//
+// wide = true additionally collapses the binary tree into the compressed 8-wide tree
+// (<= 3 triangles per leaf then, the triangle array is laid out wide-node by wide-node and the
+// binary tree's leaves reference the same array).
+void build_bvh(const std::vector<BuildTri>& tris, FlatBVH& out, bool wide = true);
+
+
+// Structural check of both trees against the triangle array: returns the number of violations
+// (0 = every triangle is referenced exactly once by each tree, every child box contains its
+// content, every reference is in range).
+uint64_t validate_bvh(const FlatBVH& bvh);
 
 } // namespace pt

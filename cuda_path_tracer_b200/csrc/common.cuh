@@ -129,8 +129,21 @@ PT_HD void camera_ray(const DevCamera& c, float x, float y, f3& o, f3& d)
 //   n2 = (c0.min.z, c0.max.z, c1.min.z, c1.max.z)
 //   n3 = bits(child0, child1, -, -);  child >= 0: inner node index
 //        child < 0: leaf, ~child = (first_triangle << 3) | (count - 1)
+//
+// Compressed 8-wide node, 80 B = five uint4 (built by bvh_build.cpp, WideBuilder::emit):
+//   w0 = (bits(p.x), bits(p.y), bits(p.z), ex' | ey'<<8 | ez'<<16 | imask<<24)
+//        p = origin of the node's quantisation grid, e' = biased float exponent of (grid step / 256),
+//        imask bit s = slot s holds an inner node
+//   w1 = (first child node, first triangle, meta[0..3], meta[4..7])
+//        meta: 0 = empty slot; inner: 0x20 | (24 + slot); leaf: unary(count) << 5 | triangle offset
+//   w2 = (qlo.x[0..3], qlo.x[4..7], qlo.y[0..3], qlo.y[4..7])
+//   w3 = (qlo.z[0..3], qlo.z[4..7], qhi.x[0..3], qhi.x[4..7])
+//   w4 = (qhi.y[0..3], qhi.y[4..7], qhi.z[0..3], qhi.z[4..7])
+// Inner children of a node are consecutive nodes (in slot order); the triangles of its leaf
+// children are consecutive triangles (in slot order).
 #define PT_LEAF_MAX 4
 #define PT_STACK 64
+#define PT_STACK8 32
 #define PT_SENTINEL 0x7fffffff
 
 // Sphere object, replicating ray_object_intersection_test's sphere branch
@@ -153,12 +166,14 @@ struct DevMaterial {
 
 struct DevScene {
   const float4* nodes; // 4 float4 per node
+  const uint4* nodes8; // compressed 8-wide tree, 5 uint4 per node, breadth-first (or null)
   const float4* tris;  // 3 float4 per triangle
   const DevSphere* spheres;
   const DevMaterial* materials;
   uint32_t n_spheres;
   uint32_t n_spheres_before; // spheres[0..n_before) precede the first mesh object
   uint32_t n_nodes;
+  uint32_t n_nodes8; // 0 = traverse the binary tree
   uint32_t n_tris;
   float root_lo[3], root_hi[3]; // padded bounds of the whole mesh BVH (classification)
 };

@@ -8,6 +8,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace pt {
@@ -57,6 +58,37 @@ static void rows3x4(const float* colmajor, float* out12)
 } // namespace pt
 
 using namespace pt;
+
+// Every mesh instance baked to world space (the reference re-transforms three vertices per
+// leaf visit instead, path_tracer.cu:57-59).
+static int bake_triangles(const pt_scene_desc* desc, const std::vector<uint32_t>& mesh_objects,
+                          std::vector<BuildTri>& tris)
+{
+  const uint64_t n_tri = desc->n_indices / 3;
+  const uint64_t n_world = n_tri * mesh_objects.size();
+  if (n_world >= (1ull << 28)) return fail(PT_ERR_INVALID, "too many world-space triangles");
+  try {
+    tris.resize(n_world);
+  } catch (...) {
+    return fail(PT_ERR_NOMEM, "out of host memory baking mesh instances");
+  }
+  for (size_t k = 0; k < mesh_objects.size(); ++k) {
+    const uint32_t oi = mesh_objects[k];
+    const pt_object& ob = desc->objects[oi];
+    BuildTri* dst = tris.data() + k * n_tri;
+#pragma omp parallel for schedule(static)
+    for (long long t = 0; t < (long long)n_tri; ++t) {
+      BuildTri& bt = dst[t];
+      xform_point(ob.m, desc->positions + 3 * (size_t)desc->indices[3 * t + 0], bt.v0);
+      xform_point(ob.m, desc->positions + 3 * (size_t)desc->indices[3 * t + 1], bt.v1);
+      xform_point(ob.m, desc->positions + 3 * (size_t)desc->indices[3 * t + 2], bt.v2);
+      bt.prim = (uint32_t)t;
+      bt.object = oi;
+      bt.material = ob.material;
+    }
+  }
+  return PT_OK;
+}
 
 extern "C" {
 
@@ -137,30 +169,18 @@ int pt_scene_create(const pt_scene_desc* desc, int device, pt_scene** out)
 
   std::vector<BuildTri> tris;
   const uint64_t n_world = n_tri * mesh_objects.size();
-  if (n_world >= (1ull << 28)) return fail(PT_ERR_INVALID, "too many world-space triangles");
-  try {
-    tris.resize(n_world);
-  } catch (...) {
-    return fail(PT_ERR_NOMEM, "out of host memory baking mesh instances");
-  }
-  for (size_t k = 0; k < mesh_objects.size(); ++k) {
-    const uint32_t oi = mesh_objects[k];
-    const pt_object& ob = desc->objects[oi];
-    BuildTri* dst = tris.data() + k * n_tri;
-#pragma omp parallel for schedule(static)
-    for (long long t = 0; t < (long long)n_tri; ++t) {
-      BuildTri& bt = dst[t];
-      xform_point(ob.m, desc->positions + 3 * (size_t)desc->indices[3 * t + 0], bt.v0);
-      xform_point(ob.m, desc->positions + 3 * (size_t)desc->indices[3 * t + 1], bt.v1);
-      xform_point(ob.m, desc->positions + 3 * (size_t)desc->indices[3 * t + 2], bt.v2);
-      bt.prim = (uint32_t)t;
-      bt.object = oi;
-      bt.material = ob.material;
-    }
+  {
+    const int rc = bake_triangles(desc, mesh_objects, tris);
+    if (rc != PT_OK) return rc;
   }
 
+  // PT_BVH=8 additionally derives the compressed 8-wide tree and traverses it (opt-in: on B200
+  // it trades the binary walk's L1 wavefront bound for an ALU-pipe bound and measures 10-30 %
+  // slower, profiles/README.md); the default is the binary tree alone.
+  const char* bvh_env = getenv("PT_BVH");
+  const bool wide = bvh_env && atoi(bvh_env) == 8;
   FlatBVH bvh;
-  build_bvh(tris, bvh);
+  build_bvh(tris, bvh, wide);
   const double t1 = now_ms();
 
   std::vector<DevMaterial> mats(desc->n_materials);
@@ -190,6 +210,7 @@ int pt_scene_create(const pt_scene_desc* desc, int device, pt_scene** out)
   cudaError_t e = cudaSuccess;
   if (e == cudaSuccess) e = upload(bvh.nodes.data(), bvh.nodes.size() * 4, &sc->d_nodes);
   if (e == cudaSuccess) e = upload(bvh.tris.data(), bvh.tris.size() * 4, &sc->d_tris);
+  if (e == cudaSuccess) e = upload(bvh.nodes8.data(), bvh.nodes8.size() * 4, &sc->d_nodes8);
   if (e == cudaSuccess) e = upload(spheres.data(), spheres.size() * sizeof(DevSphere), &sc->d_spheres);
   if (e == cudaSuccess) e = upload(mats.data(), mats.size() * sizeof(DevMaterial), &sc->d_materials);
   if (e != cudaSuccess) {
@@ -205,6 +226,12 @@ int pt_scene_create(const pt_scene_desc* desc, int device, pt_scene** out)
   sc->dev.n_spheres = (uint32_t)spheres.size();
   sc->dev.n_spheres_before = (uint32_t)sph_before.size();
   sc->dev.n_nodes = bvh.n_nodes;
+  // the wide traversal keeps a PT_STACK8-entry stack: one node group per level at most
+  const bool use_wide = bvh.n_nodes8 != 0 && bvh.depth8 <= PT_STACK8;
+  sc->dev.nodes8 = use_wide ? (const uint4*)sc->d_nodes8 : nullptr;
+  sc->dev.n_nodes8 = use_wide ? bvh.n_nodes8 : 0u;
+  sc->info.n_bvh8_nodes = bvh.n_nodes8;
+  sc->info.bvh8_depth = bvh.depth8;
   sc->dev.n_tris = bvh.n_tris;
   for (int a = 0; a < 3; ++a) {
     sc->dev.root_lo[a] = bvh.root_lo[a];
@@ -223,12 +250,73 @@ int pt_scene_create(const pt_scene_desc* desc, int device, pt_scene** out)
   return PT_OK;
 }
 
+// ---- host-only builder + structural validator (CPU tests, host build benchmark): no CUDA call
+struct pt_host_bvh_impl {
+  FlatBVH bvh;
+  double build_ms = 0.0;
+};
+
+int pt_host_bvh_build(const pt_scene_desc* desc, int wide, pt_host_bvh** out, pt_scene_info* info)
+{
+  if (!desc || !out) return fail(PT_ERR_INVALID, "pt_host_bvh_build: null argument");
+  *out = nullptr;
+  if (desc->n_indices % 3 != 0) return fail(PT_ERR_INVALID, "index count is not a multiple of 3");
+  for (uint64_t i = 0; i < desc->n_indices; ++i)
+    if (desc->indices[i] >= desc->n_vertices) return fail(PT_ERR_INVALID, "vertex index out of range");
+  std::vector<uint32_t> mesh_objects;
+  for (uint32_t i = 0; i < desc->n_objects; ++i)
+    if (desc->objects[i].type == PT_OBJ_MESH) mesh_objects.push_back(i);
+  const double t0 = now_ms();
+  std::vector<BuildTri> tris;
+  const int rc = bake_triangles(desc, mesh_objects, tris);
+  if (rc != PT_OK) return rc;
+  auto* h = new pt_host_bvh_impl();
+  build_bvh(tris, h->bvh, wide != 0);
+  h->build_ms = now_ms() - t0;
+  if (info) {
+    *info = pt_scene_info{};
+    info->n_triangles = desc->n_indices / 3;
+    info->n_world_triangles = tris.size();
+    info->n_bvh_nodes = h->bvh.n_nodes;
+    info->bvh_depth = h->bvh.depth;
+    info->n_bvh8_nodes = h->bvh.n_nodes8;
+    info->bvh8_depth = h->bvh.depth8;
+    info->build_ms = h->build_ms;
+  }
+  *out = reinterpret_cast<pt_host_bvh*>(h);
+  return PT_OK;
+}
+
+int pt_host_bvh_validate(const pt_host_bvh* hb, uint64_t* violations)
+{
+  if (!hb || !violations) return fail(PT_ERR_INVALID, "pt_host_bvh_validate: null argument");
+  *violations = validate_bvh(reinterpret_cast<const pt_host_bvh_impl*>(hb)->bvh);
+  return PT_OK;
+}
+
+int pt_host_bvh_arrays(const pt_host_bvh* hb, const float** nodes, const uint32_t** nodes8, const float** tris)
+{
+  if (!hb) return fail(PT_ERR_INVALID, "pt_host_bvh_arrays: null argument");
+  const FlatBVH& b = reinterpret_cast<const pt_host_bvh_impl*>(hb)->bvh;
+  if (nodes) *nodes = b.nodes.data();
+  if (nodes8) *nodes8 = b.nodes8.data();
+  if (tris) *tris = b.tris.data();
+  return PT_OK;
+}
+
+int pt_host_bvh_free(pt_host_bvh* hb)
+{
+  delete reinterpret_cast<pt_host_bvh_impl*>(hb);
+  return PT_OK;
+}
+
 int pt_scene_destroy(pt_scene* sc)
 {
   if (!sc) return PT_OK;
   cudaSetDevice(sc->device);
   cudaFree(sc->d_nodes);
   cudaFree(sc->d_tris);
+  cudaFree(sc->d_nodes8);
   cudaFree(sc->d_spheres);
   cudaFree(sc->d_materials);
   delete sc;

@@ -56,6 +56,7 @@ struct pt_scene {
   pt::DevScene dev{};
   void* d_nodes = nullptr;
   void* d_tris = nullptr;
+  void* d_nodes8 = nullptr;
   void* d_spheres = nullptr;
   void* d_materials = nullptr;
   pt_scene_info info{};

@@ -24,6 +24,7 @@
 #include "kernels.h"
 
 #include <float.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 namespace pt {
@@ -538,6 +539,295 @@ traverse_kernel(const DevScene sc, const PathState ps, const uint32_t* __restric
   }
 }
 
+
+// ================================================================ traverse8
+// Traversal of the compressed 8-wide tree (node layout: common.cuh).  Per node visit a lane
+// fetches 80 bytes and tests eight quantised child boxes, instead of 64 bytes and two boxes:
+// about a third of the dependent fetch -> test -> fetch steps of the binary walk, and half its
+// L1 wavefronts (ncu: the binary traverse_kernel keeps l1tex__data_pipe_lsu_wavefronts at 83 %
+// of peak).  The top of the tree (breadth-first prefix) is staged into shared memory once per
+// CTA with one TMA bulk copy; deeper nodes and the triangles come through L1/L2.
+//
+// Per-lane state follows Ylitie et al. 2017: a node group (first child, hit bits of the inner
+// children in octant order | imask) and a triangle group (first triangle, hit bits); the stack
+// holds node groups only.  Scheduling is the while-while form of traverse_kernel: lanes take
+// node steps together, then triangle steps together, and a persistent warp refills lanes that
+// ran out of work.
+PT_D void tri_test(const DevScene& sc, Trav& T, uint32_t slot)
+{
+  const float4* tp = sc.tris + (size_t)slot * 3;
+  const float4 t0 = ldg4(tp + 0);
+  const float4 t1 = ldg4(tp + 1);
+  const float4 t2 = ldg4(tp + 2);
+  const f3 e1 = xyz(t1), e2 = xyz(t2);
+  const f3 hh = cross3(T.d, e2);
+  const float a = dot3(e1, hh);
+  const float f = 1.0f / a;
+  const f3 s = T.o - xyz(t0);
+  const float u = f * dot3(s, hh);
+  const f3 q = cross3(s, e1);
+  const float v = f * dot3(T.d, q);
+  const float t = f * dot3(e2, q);
+  const bool ok = !(a > -0.0000001f && a < 0.0000001f) && !(u < 0.0f || u > 1.0f) &&
+                  !(v < 0.0f || u + v > 1.0f) && (t >= T.tmin && t <= T.tbest);
+  if (ok) {
+    T.tbest = t;
+    T.best = (int)slot;
+  }
+}
+
+// One quantised plane: byte k of `w` dropped into the mantissa of 2^23 (bits 8..15) by a single
+// PRMT, so that t = m * A + B needs no integer->float conversion.  A already carries the
+// 1/256 of the byte position, B the -2^23 * A of the magic offset.  `magic` (0x4B000000) is kept
+// in a register on purpose: PRMT takes one immediate, and it has to be the selector.
+template <int K> PT_D float qplane(uint32_t w, uint32_t magic, float A, float B)
+{
+  return fmaf(__uint_as_float(__byte_perm(w, magic, 0x7404u | (K << 4))), A, B);
+}
+
+// bit4/cnt4: per-byte hit-bit position and unary triangle count (1 for an inner child) of four slots
+template <int K>
+PT_D void child8_test(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t fx, uint32_t fy, uint32_t fz,
+                      uint32_t bit4, uint32_t cnt4, uint32_t magic, float Ax, float Ay, float Az,
+                      float Bx, float By, float Bz, float tmin, float tbest, uint32_t& hitmask)
+{
+  const float tnx = qplane<K>(nx, magic, Ax, Bx), tny = qplane<K>(ny, magic, Ay, By),
+              tnz = qplane<K>(nz, magic, Az, Bz);
+  const float tfx = qplane<K>(fx, magic, Ax, Bx), tfy = qplane<K>(fy, magic, Ay, By),
+              tfz = qplane<K>(fz, magic, Az, Bz);
+  const float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
+  const float cmax = fminf(fminf(tfx, tfy), fminf(tfz, tbest));
+  const uint32_t bits = __byte_perm(cnt4, 0u, 0x4440u | K) << __byte_perm(bit4, 0u, 0x4440u | K);
+  // robust slab comparison (Ize 2013): widen the far side by 2 ulp
+  if (cmax * 1.0000004f >= cmin) hitmask |= bits;
+}
+
+PT_D void node8_test(const uint4* __restrict__ np, const Trav& T, uint32_t octm, uint32_t magic,
+                     uint2& ng, uint2& tg)
+{
+  const uint4 w0 = np[0], w1 = np[1], w2 = np[2], w3 = np[3], w4 = np[4];
+  const float Ax = __uint_as_float((w0.w & 0xffu) << 23) * T.idx;
+  const float Ay = __uint_as_float((w0.w & 0xff00u) << 15) * T.idy;
+  const float Az = __uint_as_float((w0.w & 0xff0000u) << 7) * T.idz;
+  const float Bx = fmaf(-8388608.0f, Ax, (__uint_as_float(w0.x) - T.o.x) * T.idx);
+  const float By = fmaf(-8388608.0f, Ay, (__uint_as_float(w0.y) - T.o.y) * T.idy);
+  const float Bz = fmaf(-8388608.0f, Az, (__uint_as_float(w0.z) - T.o.z) * T.idz);
+  // entry planes are the low planes for a positive direction, the high planes otherwise
+  const bool sx = T.idx < 0.0f, sy = T.idy < 0.0f, sz = T.idz < 0.0f;
+  const uint32_t nx0 = sx ? w3.z : w2.x, nx1 = sx ? w3.w : w2.y;
+  const uint32_t fx0 = sx ? w2.x : w3.z, fx1 = sx ? w2.y : w3.w;
+  const uint32_t ny0 = sy ? w4.x : w2.z, ny1 = sy ? w4.y : w2.w;
+  const uint32_t fy0 = sy ? w2.z : w4.x, fy1 = sy ? w2.w : w4.y;
+  const uint32_t nz0 = sz ? w4.z : w3.x, nz1 = sz ? w4.w : w3.y;
+  const uint32_t fz0 = sz ? w3.x : w4.z, fz1 = sz ? w3.y : w4.w;
+  // hit-bit positions, four slots at a time: low five bits of meta, inner slots (>= 24) XORed
+  // with the ray's octant so that the nearest inner child owns the highest bit
+  const uint32_t oct4 = octm * 0x01010101u;
+  const uint32_t i0 = w1.z & 0x1f1f1f1fu, i1 = w1.w & 0x1f1f1f1fu;
+  const uint32_t in0 = ((i0 + 0x08080808u) >> 5) & 0x01010101u, in1 = ((i1 + 0x08080808u) >> 5) & 0x01010101u;
+  const uint32_t bit0 = i0 ^ (oct4 & (in0 * 7u)), bit1 = i1 ^ (oct4 & (in1 * 7u));
+  const uint32_t cnt0 = (w1.z >> 5) & 0x07070707u, cnt1 = (w1.w >> 5) & 0x07070707u;
+  uint32_t hm = 0u;
+  child8_test<0>(nx0, ny0, nz0, fx0, fy0, fz0, bit0, cnt0, magic, Ax, Ay, Az, Bx, By, Bz, T.tmin, T.tbest, hm);
+  child8_test<1>(nx0, ny0, nz0, fx0, fy0, fz0, bit0, cnt0, magic, Ax, Ay, Az, Bx, By, Bz, T.tmin, T.tbest, hm);
+  child8_test<2>(nx0, ny0, nz0, fx0, fy0, fz0, bit0, cnt0, magic, Ax, Ay, Az, Bx, By, Bz, T.tmin, T.tbest, hm);
+  child8_test<3>(nx0, ny0, nz0, fx0, fy0, fz0, bit0, cnt0, magic, Ax, Ay, Az, Bx, By, Bz, T.tmin, T.tbest, hm);
+  child8_test<0>(nx1, ny1, nz1, fx1, fy1, fz1, bit1, cnt1, magic, Ax, Ay, Az, Bx, By, Bz, T.tmin, T.tbest, hm);
+  child8_test<1>(nx1, ny1, nz1, fx1, fy1, fz1, bit1, cnt1, magic, Ax, Ay, Az, Bx, By, Bz, T.tmin, T.tbest, hm);
+  child8_test<2>(nx1, ny1, nz1, fx1, fy1, fz1, bit1, cnt1, magic, Ax, Ay, Az, Bx, By, Bz, T.tmin, T.tbest, hm);
+  child8_test<3>(nx1, ny1, nz1, fx1, fy1, fz1, bit1, cnt1, magic, Ax, Ay, Az, Bx, By, Bz, T.tmin, T.tbest, hm);
+  ng = make_uint2(w1.x, (hm & 0xff000000u) | (w0.w >> 24));
+  tg = make_uint2(w1.y, hm & 0x00ffffffu);
+}
+
+PT_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int SRC, int THREADS, int BLOCKS>
+__global__ void __launch_bounds__(THREADS, BLOCKS)
+traverse8_kernel(const DevScene sc, const PathState ps, const uint32_t* __restrict__ tq,
+                 const uint32_t* __restrict__ n_ptr, uint32_t n_host, uint32_t* __restrict__ work,
+                 const float4* __restrict__ batch_rays, HitRecord* __restrict__ batch_out,
+                 int refill_min, int node_min, int tri_min, uint32_t n_staged,
+                 uint32_t magic /* 0x4B000000, a parameter so that ptxas keeps it in a register */)
+{
+  extern __shared__ __align__(128) uint4 s_nodes[];
+  __shared__ __align__(8) unsigned long long s_bar;
+  const uint32_t n = SRC == SRC_QUEUE ? *n_ptr : n_host;
+  if (n == 0u) return;
+  // ---- stage the breadth-first prefix of the tree: one TMA bulk copy, completion on an mbarrier
+  if (n_staged != 0u) {
+    const uint32_t bar = smem_u32(&s_bar);
+    const uint32_t bytes = n_staged * 80u;
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+              smem_u32(s_nodes)),
+          "l"(sc.nodes8), "r"(bytes), "r"(bar)
+          : "memory");
+    }
+    uint32_t ready = 0;
+    while (!ready) {
+      asm volatile(
+          "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+          : "=r"(ready)
+          : "r"(bar)
+          : "memory");
+    }
+  }
+
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  uint2 stack[PT_STACK8];
+  Trav T;
+  T.best = -1;
+  uint2 ng = make_uint2(0u, 0u), tg = make_uint2(0u, 0u);
+  int sp = 0;
+  uint32_t octm = 0;
+  bool has = false, done = false;
+  bool exhausted = false; // warp-uniform
+  uint32_t pid = 0, code = 0;
+
+  for (;;) {
+    // ---- refill idle lanes: one atomic per warp
+    const uint32_t need = __ballot_sync(0xffffffffu, !has);
+    if (need != 0u && !exhausted) {
+      const uint32_t cnt = (uint32_t)__popc(need);
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(work, cnt);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (base + cnt >= n) exhausted = true;
+      if (!has) {
+        const uint32_t idx = base + (uint32_t)__popc(need & lt_mask);
+        if (idx < n) {
+          float4 ro, rd;
+          float tbest;
+          bool complex_ray = true;
+          if (SRC == SRC_QUEUE) {
+            pid = tq[idx];
+            ro = ps.ray[2 * (size_t)pid];
+            rd = ps.ray[2 * (size_t)pid + 1];
+            tbest = __uint_as_float(ps.aux[pid].x);
+          } else {
+            pid = idx;
+            ro = batch_rays[2 * (size_t)idx], rd = batch_rays[2 * (size_t)idx + 1];
+            int start;
+            complex_ray = classify(sc, xyz(ro), xyz(rd), ro.w, rd.w, tbest, code, start);
+          }
+          T.o = xyz(ro);
+          T.d = xyz(rd);
+          T.tmin = ro.w;
+          T.tbest = tbest;
+          T.best = -1;
+          T.idx = safe_inv(rd.x);
+          T.idy = safe_inv(rd.y);
+          T.idz = safe_inv(rd.z);
+          octm = (T.idx < 0.0f ? 0u : 1u) | (T.idy < 0.0f ? 0u : 2u) | (T.idz < 0.0f ? 0u : 4u);
+          ng = make_uint2(0u, 0x80000000u); // "child 0 of nothing" = the root
+          tg = make_uint2(0u, 0u);
+          sp = 0;
+          done = !complex_ray;
+          has = true;
+        }
+      }
+    }
+    if (__ballot_sync(0xffffffffu, has) == 0u) {
+      if (exhausted) break;
+      continue;
+    }
+    const int threshold = exhausted ? 1 : refill_min;
+    for (;;) {
+      if (__popc(__ballot_sync(0xffffffffu, has && !done)) < threshold) break;
+      // ---- node steps
+      for (;;) {
+        const bool act = has && !done;
+        const bool nw = act && tg.y == 0u;
+        const uint32_t m_node = __ballot_sync(0xffffffffu, nw);
+        const uint32_t m_tri = __ballot_sync(0xffffffffu, act && tg.y != 0u);
+        if (m_node == 0u) break;
+        if (__popc(m_node) < node_min && m_tri != 0u) break;
+        if (nw) {
+          const uint32_t hits = ng.y;
+          const int bit = 31 - __clz((int)hits);
+          const uint32_t rest = hits & ~(1u << bit);
+          const uint32_t slot = (uint32_t)(bit - 24) ^ octm;
+          const uint32_t node = ng.x + (uint32_t)__popc(hits & 0xffu & ((1u << slot) - 1u));
+          const uint4* np = node < n_staged ? s_nodes + (size_t)node * 5 : sc.nodes8 + (size_t)node * 5;
+          const uint2 rest_g = make_uint2(ng.x, rest);
+          uint2 ng2;
+          node8_test(np, T, octm, magic, ng2, tg);
+          if (ng2.y & 0xff000000u) {
+            if (rest & 0xff000000u) stack[sp++] = rest_g;
+            ng = ng2;
+          } else {
+            ng = rest_g;
+          }
+          if (tg.y == 0u && (ng.y & 0xff000000u) == 0u) {
+            if (sp == 0) {
+              done = true;
+            } else {
+              ng = stack[--sp];
+            }
+          }
+        }
+      }
+      // ---- triangle steps (the first one is unconditional: with few lanes on either side the
+      // two phases must not keep deferring to each other)
+      for (bool first_step = true;; first_step = false) {
+        const bool act = has && !done;
+        const bool tw = act && tg.y != 0u;
+        const uint32_t m_tri = __ballot_sync(0xffffffffu, tw);
+        const uint32_t m_node = __ballot_sync(0xffffffffu, act && tg.y == 0u);
+        if (m_tri == 0u) break;
+        if (!first_step && __popc(m_tri) < tri_min && m_node != 0u) break;
+        if (tw) {
+          const uint32_t b = (uint32_t)__ffs((int)tg.y) - 1u;
+          tg.y &= tg.y - 1u;
+          tri_test(sc, T, tg.x + b);
+          if (tg.y == 0u && (ng.y & 0xff000000u) == 0u) {
+            if (sp == 0) {
+              done = true;
+            } else {
+              ng = stack[--sp];
+            }
+          }
+        }
+      }
+    }
+    // ---- retire finished lanes
+    if (has && done) {
+      if (SRC == SRC_QUEUE) {
+        if (T.best >= 0)
+          *reinterpret_cast<uint2*>(ps.aux + pid) =
+              make_uint2(__float_as_uint(T.tbest), AUX_TRI | (uint32_t)T.best);
+      } else {
+        if (T.best >= 0) code = AUX_TRI | (uint32_t)T.best;
+        Hit h;
+        HitRecord r;
+        if (resolve_hit(sc, T.o, T.d, T.tmin, T.tbest, code, h)) {
+          r.t = h.t;
+          r.px = h.p.x, r.py = h.p.y, r.pz = h.p.z;
+          r.nx = h.n.x, r.ny = h.n.y, r.nz = h.n.z;
+          r.material = h.material, r.side = h.side;
+          r.object = h.object, r.prim = h.prim;
+        } else {
+          r.t = -1.0f;
+          r.px = r.py = r.pz = r.nx = r.ny = r.nz = 0.f;
+          r.material = 0, r.side = 0, r.object = -1, r.prim = -1;
+        }
+        r.pad = 0;
+        batch_out[pid] = r;
+      }
+      has = false;
+    }
+  }
+}
+
 // ==================================================================== shade
 // random_in_unit_sphere (distributions.cuh:6-19): uniform ON the sphere.
 PT_D f3 random_on_sphere(uint32_t& rng)
@@ -689,6 +979,10 @@ shade_kernel(const DevScene sc, const PathState ps, const PassParams pp,
 // resolved (== paths entering the reference's intersection_kernel, path_tracer.cu:428).
 //   FIRST: items are the tile-ordered primary samples (raygen fused);
 //   else : items are the paths whose ray traverse_kernel just finished.
+// (A persistent variant in which a lane that parks or terminates its path immediately takes the
+// next item — lane refill as in traverse_kernel — was measured and rejected: lane occupancy
+// rose but chain<true> went 4.65 -> 7.0 ms and chain<false> 6.05 -> 6.6 ms on the bunny frame;
+// these kernels are bound by the latency of their path-state loads/stores, not by issue slots.)
 template <bool FIRST>
 __global__ void __launch_bounds__(FULL_THREADS)
 chain_kernel(const DevScene sc, const PathState ps, const PassParams pp,
@@ -809,9 +1103,77 @@ void launch_raygen(const LaunchEnv& env, const DevScene& sc, const PassBuffers& 
                                                        pb.tcounters + 0);
 }
 
+// ---- compressed-wide traversal: CTA shape and staging budget are run-time choices
+// (PT_T8="threads,blocks_per_sm,smem_kb"); every shape is a separate instantiation.
+struct T8Shape {
+  int threads, blocks, smem_kb;
+};
+static T8Shape t8_shape()
+{
+  static T8Shape sh = [] {
+    T8Shape d{256, 2, 64};
+    if (const char* v = getenv("PT_T8")) sscanf(v, "%d,%d,%d", &d.threads, &d.blocks, &d.smem_kb);
+    return d;
+  }();
+  return sh;
+}
+
+template <int SRC, int THREADS, int BLOCKS>
+static void launch_t8(const LaunchEnv& env, const DevScene& sc, const PathState& ps, const uint32_t* tq,
+                      const uint32_t* n_ptr, uint32_t n_host, uint32_t* work, const float4* rays,
+                      HitRecord* out, int smem_kb, uint32_t max_grid)
+{
+  auto kern = traverse8_kernel<SRC, THREADS, BLOCKS>;
+  const int kMaxDyn = 226 * 1024; // 227 KB per CTA minus the static barrier and alignment
+  const uint32_t n_staged = min(sc.n_nodes8, (uint32_t)(min(smem_kb * 1024, kMaxDyn) / 80));
+  const size_t smem = (size_t)n_staged * 80;
+  // per device: opt in to the big dynamic shared memory window and size the persistent grid
+  static int grid_per_sm[64] = {0};
+  static size_t smem_for[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (grid_per_sm[dev] == 0 || smem_for[dev] != smem) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, THREADS, smem) != cudaSuccess || nb <= 0) nb = 1;
+    grid_per_sm[dev] = nb;
+    smem_for[dev] = smem;
+  }
+  const uint32_t grid = min((uint32_t)(env.sms * grid_per_sm[dev]), max_grid);
+  kern<<<grid, THREADS, smem, env.stream>>>(sc, ps, tq, n_ptr, n_host, work, rays, out,
+                                            tune("PT_REFILL", EXT_REFILL), tune("PT_NODE_MIN", 8),
+                                            tune("PT_TRI_MIN", 8), n_staged, 0x4B000000u);
+}
+
+template <int SRC>
+static void launch_t8_shape(const LaunchEnv& env, const DevScene& sc, const PathState& ps,
+                            const uint32_t* tq, const uint32_t* n_ptr, uint32_t n_host, uint32_t* work,
+                            const float4* rays, HitRecord* out, uint32_t max_grid)
+{
+  const T8Shape sh = t8_shape();
+#define PT_T8_CASE(T, B)                                                                          \
+  if (sh.threads == T && sh.blocks == B)                                                          \
+    return launch_t8<SRC, T, B>(env, sc, ps, tq, n_ptr, n_host, work, rays, out, sh.smem_kb, max_grid);
+  PT_T8_CASE(128, 8)
+  PT_T8_CASE(128, 4)
+  PT_T8_CASE(256, 4)
+  PT_T8_CASE(256, 2)
+  PT_T8_CASE(512, 2)
+  PT_T8_CASE(512, 1)
+  PT_T8_CASE(1024, 1)
+#undef PT_T8_CASE
+  launch_t8<SRC, 256, 2>(env, sc, ps, tq, n_ptr, n_host, work, rays, out, sh.smem_kb, max_grid);
+}
+
 void launch_traverse(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb,
                      const uint32_t* tq, uint32_t bounce)
 {
+  if (sc.n_nodes8 != 0u) {
+    launch_t8_shape<SRC_QUEUE>(env, sc, pb.ps, tq, pb.tcounters + bounce, 0u, pb.work + bounce, nullptr,
+                               nullptr, 0xffffffffu);
+    return;
+  }
   traverse_kernel<SRC_QUEUE><<<traverse_grid<SRC_QUEUE>(env), EXT_THREADS, 0, env.stream>>>(
       sc, pb.ps, tq, pb.tcounters + bounce, 0u, pb.work + bounce, nullptr, nullptr,
       tune("PT_REFILL", EXT_REFILL), tune("PT_INNER_MIN", EXT_INNER_MIN));
@@ -854,6 +1216,12 @@ void launch_trace_batch(const LaunchEnv& env, const DevScene& sc, const float4* 
                         uint32_t n, HitRecord* out)
 {
   // the parity hook runs the SAME classification + persistent traversal code as the renderer
+  if (sc.n_nodes8 != 0u) {
+    const T8Shape sh = t8_shape();
+    launch_t8_shape<SRC_BATCH>(env, sc, PathState{}, nullptr, nullptr, n, work, rays, out,
+                               cdiv(n, (uint32_t)sh.threads));
+    return;
+  }
   const uint32_t grid = min(traverse_grid<SRC_BATCH>(env), cdiv(n, EXT_THREADS));
   traverse_kernel<SRC_BATCH><<<grid, EXT_THREADS, 0, env.stream>>>(sc, PathState{}, nullptr, nullptr,
                                                                    n, work, rays, out, EXT_REFILL,

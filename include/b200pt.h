@@ -181,6 +181,9 @@ typedef struct pt_scene_info {
   double build_ms;  /* host BVH build */
   double upload_ms; /* H2D */
   uint64_t device_bytes;
+  uint64_t n_bvh8_nodes; /* compressed 8-wide tree (0 = not built) */
+  uint32_t bvh8_depth;
+  uint32_t reserved;
 } pt_scene_info;
 
 /* Result of loading a reference scene file (assets/json_parser.cpp:174-224). */
@@ -202,6 +205,18 @@ PT_API int pt_version(void);
 PT_API int pt_scene_create(const pt_scene_desc* desc, int device, pt_scene** out);
 PT_API int pt_scene_destroy(pt_scene* scene);
 PT_API int pt_scene_get_info(const pt_scene* scene, pt_scene_info* info);
+
+/* Host-only half of pt_scene_create (no CUDA call): bake the mesh instances and build both
+ * trees; pt_host_bvh_validate walks them and counts structural violations (a triangle that is
+ * not referenced exactly once, content outside the stored/decoded child box, a child index out
+ * of range).  Used by the CPU tests and the host build benchmark; == bvh_from_mesh
+ * (accelerators/bvh.cpp:211-253) + our flattening. */
+typedef struct pt_host_bvh pt_host_bvh;
+PT_API int pt_host_bvh_build(const pt_scene_desc* desc, int wide, pt_host_bvh** out, pt_scene_info* info);
+PT_API int pt_host_bvh_validate(const pt_host_bvh* bvh, uint64_t* violations);
+PT_API int pt_host_bvh_arrays(const pt_host_bvh* bvh, const float** nodes, const uint32_t** nodes8,
+                              const float** tris);
+PT_API int pt_host_bvh_free(pt_host_bvh* bvh);
 
 /* replaces read_scene/scene_from_json/load_obj (assets/scene_parser.cpp:6-22,
  * assets/json_parser.cpp:174-224, assets/model_loader.cpp:11-44). */

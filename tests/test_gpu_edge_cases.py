@@ -163,3 +163,53 @@ def test_denoiser_on_ragged_frame(oracle):
         assert np.isfinite(ours).all()
         if fix:
             assert not taint.any()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scene_name", ["bunny", "terrain", "single"])
+def test_wide_tree_traversal_matches_binary_and_oracle(oracle, scene_name, monkeypatch):
+    """PT_BVH=8 (compressed 8-wide tree, shared-memory staged top levels, traverse8_kernel): the
+    same closest hits and the same image as the default binary tree."""
+    if scene_name == "bunny":
+        sd = pt.bunny_scene(pt.bunny_like(4), 96, 54)
+    elif scene_name == "terrain":
+        sd = pt.terrain_scene(40, 64, 36)
+    else:
+        sd = pt.SceneDescription()
+        sd.add_material("m", pt.Material.lambertian((0.5, 0.5, 0.5)))
+        sd.add_mesh("tri", pt.Mesh(np.array([[-1, -1, -3], [1, -1, -3], [0, 1, -3]], np.float32),
+                                   np.array([0, 1, 2], np.uint32)))
+        sd.add_mesh_object("tri", pt.translate((0, 0, 0)), "m")
+        sd.resolution = (48, 32)
+    w, h = sd.resolution
+    rays, _ = _rays_for(oracle, sd, w, h, n_random=3000, seed=5)   # jittered: no edge-on alignments
+    binary = pt.Scene.from_description(sd)
+    assert int(binary.info.n_bvh8_nodes) == 0
+    hb = binary.trace_batch(rays)
+    monkeypatch.setenv("PT_BVH", "8")
+    monkeypatch.setenv("PT_T8", "256,2,32")
+    wide = pt.Scene.from_description(sd)
+    assert int(wide.info.n_bvh8_nodes) >= 1
+    hw = wide.trace_batch(rays)
+    ref = oracle.scene(sd).trace_batch(rays, 0)
+    for got in (hb, hw):
+        _check_hits(got, ref, allow_frac=2e-3)
+    # the two trees index one triangle array in different orders: compare what the hit means
+    same = (hb["t"] > 0) & (hw["t"] > 0)
+    assert np.array_equal(hb["t"] > 0, hw["t"] > 0)
+    assert np.array_equal(hb["t"][same], hw["t"][same])          # bit-equal t: same triangle arithmetic
+    assert (hb["prim"][same] != hw["prim"][same]).sum() <= max(1, same.sum() // 2000)   # exact ties only
+
+    def image(scene):
+        tr = pt.PathTracer(max_depth=5)
+        tr.max_iterations = 2
+        tr.create_buffers((w, h), scene)
+        tr.render(sd.camera, 2)
+        tr.synchronize()
+        return tr.download(DB.color), int(tr.stats().rays)
+
+    ib, rb = image(binary)
+    iw, rw = image(wide)
+    assert abs(rb - rw) <= max(2, rb // 2000)
+    d = np.abs(ib - iw).max(axis=2)
+    assert (d > 1e-5).mean() < 2e-3, (d > 1e-5).mean()

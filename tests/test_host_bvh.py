@@ -1,0 +1,189 @@
+"""CPU checks of the host builder (csrc/bvh_build.cpp): both trees are structurally valid, and the
+compressed 8-wide tree — decoded with the DEVICE's arithmetic (byte dropped into the mantissa of
+2^23, one FMA per plane; csrc/wavefront.cu node8_test), restated here in float32 — finds the
+closest hits the oracle's brute-force reference traversal finds (intersection semantics:
+reference path_tracer.cu:36-76, intersections.cuh:49-85)."""
+import numpy as np
+import pytest
+
+import cuda_path_tracer_b200 as pt
+from cuda_path_tracer_b200.api import HostBVH
+from tests.oracle_lib import load_oracle
+
+f32 = np.float32
+
+
+def _mesh_scene(mesh, xf=None):
+    sd = pt.SceneDescription()
+    sd.add_material("m", pt.Material.lambertian((0.5, 0.5, 0.5)))
+    sd.add_mesh("mesh", mesh)
+    sd.add_mesh_object("mesh", xf if xf is not None else pt.translate((0, 0, 0)), "m")
+    return sd
+
+
+def _flat_quads(n):
+    """n x n axis-aligned quads in the plane y = 0: every box has zero thickness."""
+    xs = np.linspace(-1, 1, n + 1, dtype=np.float32)
+    gx, gz = np.meshgrid(xs, xs, indexing="ij")
+    pos = np.stack([gx.ravel(), np.zeros(gx.size, np.float32), gz.ravel()], axis=1)
+    idx = []
+    for i in range(n):
+        for j in range(n):
+            a, b, c, d = i * (n + 1) + j, (i + 1) * (n + 1) + j, (i + 1) * (n + 1) + j + 1, i * (n + 1) + j + 1
+            idx += [a, b, c, a, c, d]
+    return pt.Mesh(pos, np.array(idx, dtype=np.uint32))
+
+
+MESHES = {
+    "one_triangle": lambda: pt.Mesh(np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32),
+                                    np.array([0, 1, 2], np.uint32)),
+    "three_coincident": lambda: pt.Mesh(np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32),
+                                        np.array([0, 1, 2] * 5, np.uint32)),
+    "bunny_320": lambda: pt.bunny_like(2),
+    "bunny_5k": lambda: pt.bunny_like(4),
+    "bunny_20k": lambda: pt.bunny_like(5),
+    "terrain_5k": lambda: pt.heightfield(50),
+    "flat_quads": lambda: _flat_quads(24),
+}
+
+
+@pytest.mark.parametrize("name", sorted(MESHES))
+@pytest.mark.parametrize("wide", [False, True])
+def test_trees_are_structurally_valid(name, wide):
+    hb = HostBVH(_mesh_scene(MESHES[name]()), wide=wide)
+    i = hb.info
+    assert hb.violations() == 0
+    assert int(i.n_bvh_nodes) >= 1
+    if wide:
+        assert int(i.n_bvh8_nodes) >= 1 and 1 <= int(i.bvh8_depth) <= 32
+        assert int(i.n_bvh8_nodes) <= max(1, int(i.n_bvh_nodes))
+    else:
+        assert int(i.n_bvh8_nodes) == 0
+
+
+def test_instances_are_baked_into_one_tree():
+    sd = pt.bunny_scene(pt.bunny_like(3), 64, 36)          # two instances of one mesh + a sphere
+    hb = HostBVH(sd)
+    assert int(hb.info.n_world_triangles) == 2 * int(hb.info.n_triangles)
+    assert hb.violations() == 0
+
+
+# ---------------------------------------------------------------- device arithmetic, restated
+def _fma(a, b, c):
+    return f32(np.float64(a) * np.float64(b) + np.float64(c))
+
+
+def _safe_inv(x):
+    e = f32(8.271806125530277e-25)
+    x = f32(x)
+    return f32(1.0) / (x if abs(x) > e else f32(np.copysign(e, x)))
+
+
+def _tri_test(tris, slot, o, d, tmin, tbest):
+    t0, t1, t2 = tris[slot, 0:3], tris[slot, 4:7], tris[slot, 8:11]
+
+    def cross(a, b):
+        return np.array([a[1] * b[2] - b[1] * a[2], a[2] * b[0] - b[2] * a[0], a[0] * b[1] - b[0] * a[1]], f32)
+
+    def dot(a, b):
+        return f32(f32(f32(a[0] * b[0]) + f32(a[1] * b[1])) + f32(a[2] * b[2]))
+
+    h = cross(d, t2)
+    a = dot(t1, h)
+    if -1e-7 < a < 1e-7:
+        return None
+    f = f32(1.0) / a
+    s = (o - t0).astype(f32)
+    u = f32(f * dot(s, h))
+    if u < 0 or u > 1:
+        return None
+    q = cross(s, t1)
+    v = f32(f * dot(d, q))
+    if v < 0 or f32(u + v) > 1:
+        return None
+    t = f32(f * dot(t2, q))
+    return t if tmin <= t <= tbest else None
+
+
+def _trace_wide(nodes8, tris, o, d, tmin, tmax):
+    """Closest hit through the wide tree: slab arithmetic as node8_test, unordered stack walk."""
+    o, d = o.astype(f32), d.astype(f32)
+    idir = np.array([_safe_inv(x) for x in d], f32)
+    tbest, best = f32(tmax), -1
+    stack = [0]
+    visited = 0
+    while stack:
+        w = nodes8[stack.pop()]
+        visited += 1
+        p = w[0:3].view(f32)
+        eb = [(int(w[3]) >> (8 * a)) & 0xFF for a in range(3)]
+        imask = int(w[3]) >> 24
+        A = [f32(np.array([e << 23], np.uint32).view(f32)[0] * idir[a]) for a, e in enumerate(eb)]
+        B = [_fma(f32(-8388608.0), A[a], f32(f32(p[a] - o[a]) * idir[a])) for a in range(3)]
+        meta = w[6:8].view(np.uint8)
+        q = w[8:20].view(np.uint8).reshape(6, 8)
+        rel = 0
+        for s in range(8):
+            m = int(meta[s])
+            inner = (imask >> s) & 1
+            if m:
+                cmin, cmax = f32(tmin), tbest
+                for a in range(3):
+                    lo = np.array([0x4B000000 | (int(q[a, s]) << 8)], np.uint32).view(f32)[0]
+                    hi = np.array([0x4B000000 | (int(q[3 + a, s]) << 8)], np.uint32).view(f32)[0]
+                    tlo, thi = _fma(lo, A[a], B[a]), _fma(hi, A[a], B[a])
+                    near, far = (thi, tlo) if idir[a] < 0 else (tlo, thi)
+                    cmin, cmax = max(cmin, near), min(cmax, far)
+                if f32(cmax * f32(1.0000004)) >= cmin:
+                    if inner:
+                        stack.append(int(w[4]) + rel)
+                    else:
+                        count = {1: 1, 3: 2, 7: 3}[m >> 5]
+                        for k in range(count):
+                            slot = int(w[5]) + (m & 31) + k
+                            t = _tri_test(tris, slot, o, d, f32(tmin), tbest)
+                            if t is not None:
+                                tbest, best = t, slot
+            rel += inner
+    return tbest, best, visited
+
+
+@pytest.mark.parametrize("name", ["bunny_5k", "terrain_5k", "flat_quads"])
+def test_wide_tree_with_device_arithmetic_matches_oracle(name):
+    mesh = MESHES[name]()
+    xf = pt.compose(pt.translate((0.3, -0.2, -3.0)), pt.rotate(0.7, (0.2, 1.0, 0.1)), pt.scale((1.3, 0.9, 1.1)))
+    sd = _mesh_scene(mesh, xf)
+    hb = HostBVH(sd)
+    _, nodes8, tris = hb.arrays()
+    rng = np.random.default_rng(7)
+    n = 160
+    # rays from a shell around the object towards jittered points near it (most hit), a few
+    # axis-parallel ones and a few that start inside the bounds
+    lo = tris[:, 0:3].min(axis=0) - 0.5
+    hi = tris[:, 0:3].max(axis=0) + 0.5
+    cen, rad = 0.5 * (lo + hi), 0.5 * np.linalg.norm(hi - lo)
+    dirs = rng.normal(size=(n, 3))
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    org = cen + dirs * rad * rng.uniform(0.05, 2.0, size=(n, 1))
+    tgt = cen + rng.uniform(-0.5, 0.5, size=(n, 3)) * (hi - lo)
+    d = tgt - org
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d[:12] = np.eye(3)[rng.integers(0, 3, 12)] * rng.choice([-1.0, 1.0], size=(12, 1))
+    rays = np.concatenate([org, np.full((n, 1), 1e-4), d, np.full((n, 1), 3.4e38)], axis=1).astype(np.float32)
+    ref = load_oracle().scene(sd).trace_batch(rays)
+    hits = 0
+    coord = float(np.abs(tris[:, 0:3]).max())
+    for i in range(n):
+        t, slot, visited = _trace_wide(nodes8, tris, rays[i, 0:3], rays[i, 4:7], rays[i, 3], rays[i, 7])
+        if ref["t"][i] < 0:
+            assert slot < 0, (i, t, slot)
+            continue
+        hits += 1
+        assert slot >= 0, (i, ref["t"][i])
+        # 1e-5 relative (north star); hits a few millimetres from the origin only reach the
+        # absolute rounding of world-space coordinates (the reference intersects in object space)
+        assert abs(t - ref["t"][i]) <= max(1e-5 * abs(ref["t"][i]), 4e-7 * coord), (i, t, ref["t"][i])
+        prim = int(tris[slot, 3:4].view(np.uint32)[0])
+        if prim != ref["prim"][i]:      # ties between coincident/adjacent triangles only
+            assert abs(t - ref["t"][i]) <= 1e-6 * abs(ref["t"][i])
+    assert hits > n // 4
