@@ -34,7 +34,8 @@ class pt_scene_desc(C.Structure):
                 ("indices", C.POINTER(C.c_uint32)), ("n_indices", C.c_uint64),
                 ("objects", C.POINTER(pt_object)), ("n_objects", C.c_uint32),
                 ("spheres", C.POINTER(pt_sphere)), ("n_spheres", C.c_uint32),
-                ("materials", C.POINTER(pt_material)), ("n_materials", C.c_uint32)]
+                ("materials", C.POINTER(pt_material)), ("n_materials", C.c_uint32),
+                ("n_meshes", C.c_uint32), ("mesh_first_index", C.POINTER(C.c_uint64))]
 
 
 class pt_camera(C.Structure):
@@ -119,6 +120,8 @@ SYMBOLS = {
     "pt_ctx_set_sample_count": (C.c_int, [VP, C.c_int]),
     "pt_ctx_bind_sums": (C.c_int, [VP, VP]),
     "pt_ctx_upload_frame": (C.c_int, [VP, VP, VP, VP, C.POINTER(pt_camera)]),
+    "pt_ctx_save_state": (C.c_int, [VP, C.c_char_p]),
+    "pt_ctx_load_state": (C.c_int, [VP, C.c_char_p]),
     "pt_get_stats": (C.c_int, [VP, C.POINTER(pt_stats)]),
     "pt_reset_stats": (C.c_int, [VP]),
     "pt_trace_batch": (C.c_int, [VP, VP, C.c_uint64, VP]),

@@ -253,6 +253,14 @@ class PathTracer:
     def bind_sums(self, device_ptr: int | None):
         check(load_library().pt_ctx_bind_sums(self._ctx, C.c_void_p(device_ptr or 0)))
 
+    def save_state(self, path: str):
+        """Progressive state (running sums + iteration) to disk."""
+        check(load_library().pt_ctx_save_state(self._ctx, str(path).encode()))
+
+    def load_state(self, path: str):
+        """Resume from a saved progressive state of the same resolution."""
+        check(load_library().pt_ctx_load_state(self._ctx, str(path).encode()))
+
     def set_sample_count(self, n: int):
         check(load_library().pt_ctx_set_sample_count(self._ctx, int(n)))
 

@@ -86,7 +86,11 @@ void print_help()
               "      --filter-size arg  Run the A-Trous denoiser with this filter size\n"
               "      --rng-mode arg     0 = per-pixel stream (megakernel order), 1 = streaming re-seed\n"
               "      --device arg       CUDA device (default 0)\n"
-              "      --stats-json arg   Write run statistics to this file\n\n");
+              "      --stats-json arg   Write run statistics to this file\n"
+              "      --checkpoint arg   Save the progressive state (sums + iteration) to this file\n"
+              "      --resume arg       Continue from a saved progressive state up to --spp\n"
+              "      --all-meshes       Load every mesh a scene names (the reference loads the first)\n"
+              "      --mesh-cache       Keep a binary copy (<obj>.b200mesh) of every parsed OBJ\n\n");
 }
 
 } // namespace
@@ -128,7 +132,7 @@ extern "C" int pt_write_png_rgba8(const char* path, const void* rgba, uint32_t w
 
 extern "C" int pt_cli_main(int argc, char** argv)
 {
-  std::optional<std::string> filename, output, stats_json;
+  std::optional<std::string> filename, output, stats_json, checkpoint, resume;
   std::optional<int> spp;
   int max_depth = 50, filter_size = 0, device = 0, rng_mode = 0;
   for (int i = 1; i < argc; ++i) {
@@ -180,6 +184,16 @@ extern "C" int pt_cli_main(int argc, char** argv)
     } else if (a == "--stats-json" || eq("--stats-json", v)) {
       if (v.empty()) { const char* s = value("stats-json"); if (!s) return 1; v = s; }
       stats_json = v;
+    } else if (a == "--checkpoint" || eq("--checkpoint", v)) {
+      if (v.empty()) { const char* s = value("checkpoint"); if (!s) return 1; v = s; }
+      checkpoint = v;
+    } else if (a == "--resume" || eq("--resume", v)) {
+      if (v.empty()) { const char* s = value("resume"); if (!s) return 1; v = s; }
+      resume = v;
+    } else if (a == "--all-meshes") {
+      setenv("PT_ALL_MESHES", "1", 1);
+    } else if (a == "--mesh-cache") {
+      setenv("PT_MESH_CACHE", "1", 1);
     } else if (a == "--filename" || eq("--filename", v)) {
       if (v.empty()) { const char* s = value("filename"); if (!s) return 1; v = s; }
       filename = v;
@@ -242,9 +256,12 @@ extern "C" int pt_cli_main(int argc, char** argv)
   sw.end_stage("Initialization");
 
   int rc = 0;
+  if (resume && pt_ctx_load_state(ctx, resume->c_str()) != PT_OK) rc = 1;
   pt_ctx_set_max_iterations(ctx, n_spp);
-  if (pt_render(ctx, &finfo.camera, n_spp) != PT_OK || pt_sync(ctx) != PT_OK) rc = 1;
+  // pt_render clips at max_iterations: a resumed context only renders what is missing
+  if (!rc && (pt_render(ctx, &finfo.camera, n_spp) != PT_OK || pt_sync(ctx) != PT_OK)) rc = 1;
   sw.end_stage("Path Tracing");
+  if (!rc && checkpoint && pt_ctx_save_state(ctx, checkpoint->c_str()) != PT_OK) rc = 1;
   if (!rc && filter_size > 0) {
     pt_denoise_params dp;
     pt_denoise_params_default(&dp);

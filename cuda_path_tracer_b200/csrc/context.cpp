@@ -61,11 +61,35 @@ using namespace pt;
 
 // Every mesh instance baked to world space (the reference re-transforms three vertices per
 // leaf visit instead, path_tracer.cu:57-59).
+// Index range [first, first + 3 * count) of the mesh a mesh object instances.
+static bool mesh_range(const pt_scene_desc* desc, const pt_object& ob, uint64_t& first_tri, uint64_t& n_tri)
+{
+  if (desc->n_meshes == 0) {
+    first_tri = 0;
+    n_tri = desc->n_indices / 3;
+    return true;
+  }
+  if (ob.prim_index >= desc->n_meshes || !desc->mesh_first_index) return false;
+  const uint64_t a = desc->mesh_first_index[ob.prim_index], b = desc->mesh_first_index[ob.prim_index + 1];
+  if (a > b || b > desc->n_indices || a % 3 != 0 || b % 3 != 0) return false;
+  first_tri = a / 3;
+  n_tri = (b - a) / 3;
+  return true;
+}
+
+// Every mesh instance baked to world space (the reference re-transforms three vertices per
+// leaf visit instead, path_tracer.cu:57-59).
 static int bake_triangles(const pt_scene_desc* desc, const std::vector<uint32_t>& mesh_objects,
                           std::vector<BuildTri>& tris)
 {
-  const uint64_t n_tri = desc->n_indices / 3;
-  const uint64_t n_world = n_tri * mesh_objects.size();
+  std::vector<uint64_t> first(mesh_objects.size()), count(mesh_objects.size()), out_at(mesh_objects.size());
+  uint64_t n_world = 0;
+  for (size_t k = 0; k < mesh_objects.size(); ++k) {
+    if (!mesh_range(desc, desc->objects[mesh_objects[k]], first[k], count[k]))
+      return fail(PT_ERR_INVALID, "mesh object refers to a mesh that does not exist");
+    out_at[k] = n_world;
+    n_world += count[k];
+  }
   if (n_world >= (1ull << 28)) return fail(PT_ERR_INVALID, "too many world-space triangles");
   try {
     tris.resize(n_world);
@@ -75,14 +99,16 @@ static int bake_triangles(const pt_scene_desc* desc, const std::vector<uint32_t>
   for (size_t k = 0; k < mesh_objects.size(); ++k) {
     const uint32_t oi = mesh_objects[k];
     const pt_object& ob = desc->objects[oi];
-    BuildTri* dst = tris.data() + k * n_tri;
+    BuildTri* dst = tris.data() + out_at[k];
+    const uint64_t t0 = first[k];
 #pragma omp parallel for schedule(static)
-    for (long long t = 0; t < (long long)n_tri; ++t) {
+    for (long long t = 0; t < (long long)count[k]; ++t) {
       BuildTri& bt = dst[t];
-      xform_point(ob.m, desc->positions + 3 * (size_t)desc->indices[3 * t + 0], bt.v0);
-      xform_point(ob.m, desc->positions + 3 * (size_t)desc->indices[3 * t + 1], bt.v1);
-      xform_point(ob.m, desc->positions + 3 * (size_t)desc->indices[3 * t + 2], bt.v2);
-      bt.prim = (uint32_t)t;
+      const uint64_t g = t0 + (uint64_t)t;
+      xform_point(ob.m, desc->positions + 3 * (size_t)desc->indices[3 * g + 0], bt.v0);
+      xform_point(ob.m, desc->positions + 3 * (size_t)desc->indices[3 * g + 1], bt.v1);
+      xform_point(ob.m, desc->positions + 3 * (size_t)desc->indices[3 * g + 2], bt.v2);
+      bt.prim = (uint32_t)g;
       bt.object = oi;
       bt.material = ob.material;
     }
@@ -168,11 +194,11 @@ int pt_scene_create(const pt_scene_desc* desc, int device, pt_scene** out)
   }
 
   std::vector<BuildTri> tris;
-  const uint64_t n_world = n_tri * mesh_objects.size();
   {
     const int rc = bake_triangles(desc, mesh_objects, tris);
     if (rc != PT_OK) return rc;
   }
+  const uint64_t n_world = tris.size();
 
   // PT_BVH=8 additionally derives the compressed 8-wide tree and traverses it (opt-in: on B200
   // it trades the binary walk's L1 wavefront bound for an ALU-pipe bound and measures 10-30 %
@@ -343,6 +369,10 @@ static void desc_from_file(const SceneFile& sf, pt_scene_desc& d)
   d.n_spheres = (uint32_t)sf.spheres.size();
   d.materials = sf.materials.data();
   d.n_materials = (uint32_t)sf.materials.size();
+  if (!sf.mesh_first_index.empty()) {
+    d.n_meshes = (uint32_t)sf.mesh_first_index.size() - 1;
+    d.mesh_first_index = sf.mesh_first_index.data();
+  }
 }
 
 int pt_scene_file_read(const char* json_path, pt_scene_file** out, pt_scene_desc* desc,
@@ -894,6 +924,69 @@ int pt_ctx_set_sample_count(pt_ctx* c, int n)
 {
   if (!c) return fail(PT_ERR_INVALID, "null context");
   c->iteration = n;
+  return PT_OK;
+}
+
+// ---- progressive state on disk: the running sums are associative, so a 1024-spp render can be
+// stopped and resumed (or merged from shards) without changing the result.
+namespace {
+struct StateHeader {
+  char magic[8]; // "B200PTST"
+  uint32_t version, width, height, iteration;
+  uint64_t n_floats;
+  uint32_t reserved[8];
+};
+static_assert(sizeof(StateHeader) == 64, "state header is 64 bytes");
+} // namespace
+
+int pt_ctx_save_state(pt_ctx* c, const char* path)
+{
+  if (!c || !path) return fail(PT_ERR_INVALID, "pt_ctx_save_state: null argument");
+  PT_CUDA(cudaSetDevice(c->scene->device));
+  PT_CUDA(cudaStreamSynchronize(c->stream));
+  const size_t n = (size_t)c->pixels * 8;
+  std::vector<float> host(n);
+  PT_CUDA(cudaMemcpy(host.data(), c->d_sums, n * sizeof(float), cudaMemcpyDeviceToHost));
+  StateHeader h{};
+  std::memcpy(h.magic, "B200PTST", 8);
+  h.version = 1;
+  h.width = c->width;
+  h.height = c->height;
+  h.iteration = (uint32_t)c->iteration;
+  h.n_floats = n;
+  FILE* f = std::fopen(path, "wb");
+  if (!f) return fail(PT_ERR_IO, std::string("cannot write ") + path);
+  const bool ok = std::fwrite(&h, sizeof(h), 1, f) == 1 && std::fwrite(host.data(), sizeof(float), n, f) == n;
+  std::fclose(f);
+  if (!ok) return fail(PT_ERR_IO, std::string("short write to ") + path);
+  return PT_OK;
+}
+
+int pt_ctx_load_state(pt_ctx* c, const char* path)
+{
+  if (!c || !path) return fail(PT_ERR_INVALID, "pt_ctx_load_state: null argument");
+  FILE* f = std::fopen(path, "rb");
+  if (!f) return fail(PT_ERR_IO, std::string("cannot open ") + path);
+  StateHeader h{};
+  const size_t n = (size_t)c->pixels * 8;
+  std::vector<float> host(n);
+  bool ok = std::fread(&h, sizeof(h), 1, f) == 1;
+  if (ok && (std::memcmp(h.magic, "B200PTST", 8) != 0 || h.version != 1)) {
+    std::fclose(f);
+    return fail(PT_ERR_PARSE, std::string(path) + " is not a progressive-state file");
+  }
+  if (ok && (h.width != c->width || h.height != c->height || h.n_floats != n)) {
+    std::fclose(f);
+    return fail(PT_ERR_INVALID, "progressive state has a different resolution");
+  }
+  ok = ok && std::fread(host.data(), sizeof(float), n, f) == n;
+  std::fclose(f);
+  if (!ok) return fail(PT_ERR_IO, std::string("short read from ") + path);
+  PT_CUDA(cudaSetDevice(c->scene->device));
+  PT_CUDA(cudaStreamSynchronize(c->stream));
+  PT_CUDA(cudaMemcpy(c->d_sums, host.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+  c->iteration = (int)h.iteration;
+  c->final_rgb = nullptr;
   return PT_OK;
 }
 

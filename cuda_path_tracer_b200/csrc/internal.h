@@ -36,6 +36,7 @@ DevCamera make_dev_camera(const pt_camera& cam, uint32_t w, uint32_t h);
 struct SceneFile {
   std::vector<float> positions;
   std::vector<uint32_t> indices;
+  std::vector<uint64_t> mesh_first_index; // empty = one mesh (reference behaviour)
   std::vector<pt_object> objects;
   std::vector<pt_sphere> spheres;
   std::vector<pt_material> materials;

@@ -293,7 +293,94 @@ Mat4 read_transform(const JValue* j)
 // Assimp semantics kept: first mesh only (faces up to the first o/g/usemtl
 // statement that follows a face), polygons fan-triangulated, one vertex per
 // face corner (positions has 3T entries, indices = 0,1,2,...).
+// Binary side-car of a parsed OBJ (opt-in, PT_MESH_CACHE=1 / cuda_pt --mesh-cache): the
+// 10-M-triangle OBJ of the stress config is ~1 GB of text; the cache is the two arrays verbatim,
+// keyed by the source's size and modification time.
+namespace {
+struct MeshCacheHeader {
+  char magic[8]; // "B200MESH"
+  uint32_t version, reserved;
+  uint64_t source_bytes;
+  int64_t source_mtime;
+  uint64_t n_floats, n_indices;
+};
+
+bool mesh_cache_enabled()
+{
+  const char* v = std::getenv("PT_MESH_CACHE");
+  return v && std::atoi(v) != 0;
+}
+
+bool source_key(const char* path, uint64_t& bytes, int64_t& mtime)
+{
+  std::error_code ec;
+  const auto sz = std::filesystem::file_size(path, ec);
+  if (ec) return false;
+  const auto tm = std::filesystem::last_write_time(path, ec);
+  if (ec) return false;
+  bytes = (uint64_t)sz;
+  mtime = (int64_t)tm.time_since_epoch().count();
+  return true;
+}
+
+bool read_mesh_cache(const char* path, std::vector<float>& positions, std::vector<uint32_t>& indices)
+{
+  uint64_t bytes;
+  int64_t mtime;
+  if (!source_key(path, bytes, mtime)) return false;
+  FILE* f = std::fopen((std::string(path) + ".b200mesh").c_str(), "rb");
+  if (!f) return false;
+  MeshCacheHeader h{};
+  bool ok = std::fread(&h, sizeof(h), 1, f) == 1 && !std::memcmp(h.magic, "B200MESH", 8) && h.version == 1 &&
+            h.source_bytes == bytes && h.source_mtime == mtime && h.n_indices % 3 == 0 &&
+            h.n_floats % 3 == 0 && h.n_floats < (1ull << 34) && h.n_indices < (1ull << 34);
+  if (ok) {
+    positions.resize(h.n_floats);
+    indices.resize(h.n_indices);
+    ok = std::fread(positions.data(), 4, h.n_floats, f) == h.n_floats &&
+         std::fread(indices.data(), 4, h.n_indices, f) == h.n_indices;
+    const uint64_t nv = h.n_floats / 3;
+    for (size_t i = 0; ok && i < indices.size(); ++i) ok = indices[i] < nv;
+  }
+  std::fclose(f);
+  if (!ok) {
+    positions.clear();
+    indices.clear();
+  }
+  return ok;
+}
+
+void write_mesh_cache(const char* path, const std::vector<float>& positions, const std::vector<uint32_t>& indices)
+{
+  MeshCacheHeader h{};
+  std::memcpy(h.magic, "B200MESH", 8);
+  h.version = 1;
+  if (!source_key(path, h.source_bytes, h.source_mtime)) return;
+  h.n_floats = positions.size();
+  h.n_indices = indices.size();
+  const std::string out = std::string(path) + ".b200mesh";
+  FILE* f = std::fopen(out.c_str(), "wb");
+  if (!f) return; // read-only asset directory: the cache is best effort
+  const bool ok = std::fwrite(&h, sizeof(h), 1, f) == 1 &&
+                  std::fwrite(positions.data(), 4, positions.size(), f) == positions.size() &&
+                  std::fwrite(indices.data(), 4, indices.size(), f) == indices.size();
+  std::fclose(f);
+  if (!ok) std::remove(out.c_str());
+}
+} // namespace
+
+static int parse_obj_file(const char* path, std::vector<float>& positions, std::vector<uint32_t>& indices);
+
 int load_obj_file(const char* path, std::vector<float>& positions, std::vector<uint32_t>& indices)
+{
+  const bool cache = mesh_cache_enabled();
+  if (cache && read_mesh_cache(path, positions, indices)) return PT_OK;
+  const int rc = parse_obj_file(path, positions, indices);
+  if (rc == PT_OK && cache) write_mesh_cache(path, positions, indices);
+  return rc;
+}
+
+static int parse_obj_file(const char* path, std::vector<float>& positions, std::vector<uint32_t>& indices)
 {
   std::string text;
   if (!read_file(path, text)) return fail(PT_ERR_IO, std::string("Unable to load ") + path);
@@ -413,6 +500,7 @@ int load_scene_file(const char* json_path, SceneFile& out)
     const JValue* surfaces = root->find("surfaces");
     if (!surfaces || surfaces->kind != JValue::Arr) throw ParseError{"Json Parser: surfaces is not array"};
     std::map<std::string, int> mesh_paths; // canonical path -> seen
+    std::vector<std::pair<size_t, std::string>> mesh_object_paths; // object index -> its mesh
     for (auto& sj : surfaces->arr) {
       const std::string type = str(sj->find("type"), "surface type");
       const std::string material = str(sj->find("material"), "surface material");
@@ -437,20 +525,41 @@ int load_scene_file(const char* json_path, SceneFile& out)
         const fs::path canon = fs::canonical(file_dir / filename, ec);
         if (ec) throw ParseError{"Unable to load " + (file_dir / filename).string()};
         mesh_paths[canon.string()] = 1;
+        mesh_object_paths.emplace_back(out.objects.size(), canon.string());
       } else {
         throw ParseError{"Json Parser: Not supported surface type " + type};
       }
       out.objects.push_back(ob);
     }
-    if (!mesh_paths.empty()) {
+    const char* all_env = std::getenv("PT_ALL_MESHES");
+    const bool all_meshes = all_env && std::atoi(all_env) != 0;
+    if (!mesh_paths.empty() && !all_meshes) {
       // Only the alphabetically-first mesh is uploaded and every mesh object
       // instances it (scene_description.cpp:95, scene.hpp:33-39).
       if (mesh_paths.size() > 1)
         std::fprintf(stderr,
-                     "warning: %zu meshes referenced; like the reference only the first (%s) is used\n",
+                     "warning: %zu meshes referenced; like the reference only the first (%s) is used "
+                     "(PT_ALL_MESHES=1 / --all-meshes honours every mesh)\n",
                      mesh_paths.size(), mesh_paths.begin()->first.c_str());
       int rc = load_obj_file(mesh_paths.begin()->first.c_str(), out.positions, out.indices);
       if (rc != PT_OK) return rc;
+    } else if (!mesh_paths.empty()) {
+      // extension: every referenced mesh is loaded (alphabetical order, one shared vertex and
+      // index buffer) and each mesh object instances its own
+      std::map<std::string, uint32_t> mesh_rank;
+      out.mesh_first_index.push_back(0);
+      for (auto& kv : mesh_paths) {
+        std::vector<float> pos;
+        std::vector<uint32_t> idx;
+        int rc = load_obj_file(kv.first.c_str(), pos, idx);
+        if (rc != PT_OK) return rc;
+        const uint32_t base = (uint32_t)(out.positions.size() / 3);
+        out.positions.insert(out.positions.end(), pos.begin(), pos.end());
+        for (uint32_t i : idx) out.indices.push_back(base + i);
+        mesh_rank[kv.first] = (uint32_t)out.mesh_first_index.size() - 1;
+        out.mesh_first_index.push_back(out.indices.size());
+      }
+      for (auto& op : mesh_object_paths) out.objects[op.first].prim_index = mesh_rank[op.second];
     }
 
     // camera (json_parser.cpp:187-209)

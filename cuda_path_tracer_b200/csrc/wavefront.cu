@@ -423,6 +423,36 @@ raygen_kernel(const DevScene sc, const PathState ps, const PassParams pp, uint32
   }
 }
 
+PT_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Stages `bytes` (a multiple of 16) from global to shared memory with ONE TMA bulk copy issued by
+// thread 0; every thread of the CTA waits on the mbarrier the copy completes on.
+PT_D void stage_prefix(void* smem_dst, const void* gsrc, uint32_t bytes, unsigned long long* s_bar)
+{
+  const uint32_t bar = smem_u32(s_bar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"(bar)
+        : "memory");
+  }
+  uint32_t ready = 0;
+  while (!ready) {
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+        : "=r"(ready)
+        : "r"(bar)
+        : "memory");
+  }
+}
+
 // ================================================================= traverse
 // Persistent warps (grid = SMs x resident CTAs).  Each lane owns one ray at a time.  Work is
 // fetched from a device-side cursor with ONE atomic per refill for all idle lanes of the warp;
@@ -438,6 +468,9 @@ raygen_kernel(const DevScene sc, const PathState ps, const PassParams pp, uint32
 
 enum { SRC_QUEUE = 1, SRC_BATCH = 2 };
 
+// (Staging the hottest nodes of the binary tree in shared memory — area-ordered prefix, 80-byte
+// stride against bank conflicts, up to 200 KB per SM — was measured and rejected: 15.6-17.1 ms
+// against 15.7 ms for plain L1-cached loads on the bunny frame, profiles/README.md.)
 template <int SRC>
 __global__ void __launch_bounds__(EXT_THREADS, EXT_MIN_BLOCKS)
 traverse_kernel(const DevScene sc, const PathState ps, const uint32_t* __restrict__ tq,
@@ -640,8 +673,6 @@ PT_D void node8_test(const uint4* __restrict__ np, const Trav& T, uint32_t octm,
   tg = make_uint2(w1.y, hm & 0x00ffffffu);
 }
 
-PT_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
 template <int SRC, int THREADS, int BLOCKS>
 __global__ void __launch_bounds__(THREADS, BLOCKS)
 traverse8_kernel(const DevScene sc, const PathState ps, const uint32_t* __restrict__ tq,
@@ -655,31 +686,7 @@ traverse8_kernel(const DevScene sc, const PathState ps, const uint32_t* __restri
   const uint32_t n = SRC == SRC_QUEUE ? *n_ptr : n_host;
   if (n == 0u) return;
   // ---- stage the breadth-first prefix of the tree: one TMA bulk copy, completion on an mbarrier
-  if (n_staged != 0u) {
-    const uint32_t bar = smem_u32(&s_bar);
-    const uint32_t bytes = n_staged * 80u;
-    if (threadIdx.x == 0) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-      asm volatile(
-          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-              smem_u32(s_nodes)),
-          "l"(sc.nodes8), "r"(bytes), "r"(bar)
-          : "memory");
-    }
-    uint32_t ready = 0;
-    while (!ready) {
-      asm volatile(
-          "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
-          : "=r"(ready)
-          : "r"(bar)
-          : "memory");
-    }
-  }
+  if (n_staged != 0u) stage_prefix(s_nodes, sc.nodes8, n_staged * 80u, &s_bar);
 
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t lt_mask = (1u << lane) - 1u;
@@ -1080,21 +1087,6 @@ static int tune(const char* name, int dflt)
   return v ? atoi(v) : dflt;
 }
 
-// persistent grid: SMs x the number of CTAs the kernel can keep resident per SM
-template <int SRC> static uint32_t traverse_grid(const LaunchEnv& env)
-{
-  static int per_sm = 0;
-  if (per_sm == 0) {
-    int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, traverse_kernel<SRC>, EXT_THREADS, 0) !=
-            cudaSuccess ||
-        nb <= 0)
-      nb = EXT_MIN_BLOCKS;
-    per_sm = nb;
-  }
-  return (uint32_t)(env.sms * per_sm);
-}
-
 void launch_raygen(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb,
                    const PassParams& pp, uint32_t n_items)
 {
@@ -1103,19 +1095,55 @@ void launch_raygen(const LaunchEnv& env, const DevScene& sc, const PassBuffers& 
                                                        pb.tcounters + 0);
 }
 
-// ---- compressed-wide traversal: CTA shape and staging budget are run-time choices
-// (PT_T8="threads,blocks_per_sm,smem_kb"); every shape is a separate instantiation.
-struct T8Shape {
+// ---- traversal launch shape: CTA size, CTAs per SM and the shared-memory staging budget per CTA
+// are run-time choices for the wide kernel (PT_T8 = "threads,blocks_per_sm,smem_kb"); every shape
+// is a separate instantiation.  Grids are persistent: SMs x resident CTAs.
+struct TShape {
   int threads, blocks, smem_kb;
 };
-static T8Shape t8_shape()
+static TShape shape_from_env(const char* name, TShape d)
 {
-  static T8Shape sh = [] {
-    T8Shape d{256, 2, 64};
-    if (const char* v = getenv("PT_T8")) sscanf(v, "%d,%d,%d", &d.threads, &d.blocks, &d.smem_kb);
-    return d;
-  }();
+  if (const char* v = getenv(name)) sscanf(v, "%d,%d,%d", &d.threads, &d.blocks, &d.smem_kb);
+  return d;
+}
+static TShape t8_shape()
+{
+  static TShape sh = shape_from_env("PT_T8", TShape{128, 8, 0});
   return sh;
+}
+
+static const int kMaxDynSmem = 226 * 1024; // 227 KB per CTA minus the static barrier and alignment
+
+// per device and kernel: opt in to the big dynamic shared-memory window, size the persistent grid
+template <typename K>
+static uint32_t persistent_grid(K kern, const LaunchEnv& env, int threads, size_t smem, int* cache_nb,
+                                size_t* cache_smem)
+{
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (cache_nb[dev] == 0 || cache_smem[dev] != smem) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem) != cudaSuccess || nb <= 0) nb = 1;
+    cache_nb[dev] = nb;
+    cache_smem[dev] = smem;
+  }
+  return (uint32_t)(env.sms * cache_nb[dev]);
+}
+
+template <int SRC>
+static void launch_t2(const LaunchEnv& env, const DevScene& sc, const PathState& ps, const uint32_t* tq,
+                      const uint32_t* n_ptr, uint32_t n_host, uint32_t* work, const float4* rays,
+                      HitRecord* out, uint32_t max_grid)
+{
+  auto kern = traverse_kernel<SRC>;
+  static int nb[64] = {0};
+  static size_t sm[64] = {0};
+  const uint32_t grid = min(persistent_grid(kern, env, EXT_THREADS, 0, nb, sm), max_grid);
+  kern<<<grid, EXT_THREADS, 0, env.stream>>>(sc, ps, tq, n_ptr, n_host, work, rays, out,
+                                             tune("PT_REFILL", EXT_REFILL),
+                                             tune("PT_INNER_MIN", EXT_INNER_MIN));
 }
 
 template <int SRC, int THREADS, int BLOCKS>
@@ -1124,59 +1152,46 @@ static void launch_t8(const LaunchEnv& env, const DevScene& sc, const PathState&
                       HitRecord* out, int smem_kb, uint32_t max_grid)
 {
   auto kern = traverse8_kernel<SRC, THREADS, BLOCKS>;
-  const int kMaxDyn = 226 * 1024; // 227 KB per CTA minus the static barrier and alignment
-  const uint32_t n_staged = min(sc.n_nodes8, (uint32_t)(min(smem_kb * 1024, kMaxDyn) / 80));
+  const uint32_t n_staged = min(sc.n_nodes8, (uint32_t)(min(smem_kb * 1024, kMaxDynSmem) / 80));
   const size_t smem = (size_t)n_staged * 80;
-  // per device: opt in to the big dynamic shared memory window and size the persistent grid
-  static int grid_per_sm[64] = {0};
-  static size_t smem_for[64] = {0};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  dev &= 63;
-  if (grid_per_sm[dev] == 0 || smem_for[dev] != smem) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
-    int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, THREADS, smem) != cudaSuccess || nb <= 0) nb = 1;
-    grid_per_sm[dev] = nb;
-    smem_for[dev] = smem;
-  }
-  const uint32_t grid = min((uint32_t)(env.sms * grid_per_sm[dev]), max_grid);
+  static int nb[64] = {0};
+  static size_t sm[64] = {0};
+  const uint32_t grid = min(persistent_grid(kern, env, THREADS, smem, nb, sm), max_grid);
   kern<<<grid, THREADS, smem, env.stream>>>(sc, ps, tq, n_ptr, n_host, work, rays, out,
-                                            tune("PT_REFILL", EXT_REFILL), tune("PT_NODE_MIN", 8),
-                                            tune("PT_TRI_MIN", 8), n_staged, 0x4B000000u);
+                                            tune("PT_REFILL", EXT_REFILL), tune("PT_NODE_MIN", 12),
+                                            tune("PT_TRI_MIN", 4), n_staged, 0x4B000000u);
 }
 
 template <int SRC>
-static void launch_t8_shape(const LaunchEnv& env, const DevScene& sc, const PathState& ps,
-                            const uint32_t* tq, const uint32_t* n_ptr, uint32_t n_host, uint32_t* work,
-                            const float4* rays, HitRecord* out, uint32_t max_grid)
+static void launch_traverse_shape(const LaunchEnv& env, const DevScene& sc, const PathState& ps,
+                                  const uint32_t* tq, const uint32_t* n_ptr, uint32_t n_host,
+                                  uint32_t* work, const float4* rays, HitRecord* out, bool batch)
 {
-  const T8Shape sh = t8_shape();
-#define PT_T8_CASE(T, B)                                                                          \
-  if (sh.threads == T && sh.blocks == B)                                                          \
+  if (sc.n_nodes8 == 0u) {
+    launch_t2<SRC>(env, sc, ps, tq, n_ptr, n_host, work, rays, out,
+                   batch ? cdiv(n_host, (uint32_t)EXT_THREADS) : 0xffffffffu);
+    return;
+  }
+  const TShape sh = t8_shape();
+  const uint32_t max_grid = batch ? cdiv(n_host, (uint32_t)sh.threads) : 0xffffffffu;
+#define PT_SHAPE_CASE(T, B)                                                                        \
+  if (sh.threads == T && sh.blocks == B)                                                           \
     return launch_t8<SRC, T, B>(env, sc, ps, tq, n_ptr, n_host, work, rays, out, sh.smem_kb, max_grid);
-  PT_T8_CASE(128, 8)
-  PT_T8_CASE(128, 4)
-  PT_T8_CASE(256, 4)
-  PT_T8_CASE(256, 2)
-  PT_T8_CASE(512, 2)
-  PT_T8_CASE(512, 1)
-  PT_T8_CASE(1024, 1)
-#undef PT_T8_CASE
-  launch_t8<SRC, 256, 2>(env, sc, ps, tq, n_ptr, n_host, work, rays, out, sh.smem_kb, max_grid);
+  PT_SHAPE_CASE(128, 8)
+  PT_SHAPE_CASE(256, 4)
+  PT_SHAPE_CASE(256, 2)
+  PT_SHAPE_CASE(512, 2)
+  PT_SHAPE_CASE(512, 1)
+  PT_SHAPE_CASE(1024, 1)
+#undef PT_SHAPE_CASE
+  launch_t8<SRC, 128, 8>(env, sc, ps, tq, n_ptr, n_host, work, rays, out, sh.smem_kb, max_grid);
 }
 
 void launch_traverse(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb,
                      const uint32_t* tq, uint32_t bounce)
 {
-  if (sc.n_nodes8 != 0u) {
-    launch_t8_shape<SRC_QUEUE>(env, sc, pb.ps, tq, pb.tcounters + bounce, 0u, pb.work + bounce, nullptr,
-                               nullptr, 0xffffffffu);
-    return;
-  }
-  traverse_kernel<SRC_QUEUE><<<traverse_grid<SRC_QUEUE>(env), EXT_THREADS, 0, env.stream>>>(
-      sc, pb.ps, tq, pb.tcounters + bounce, 0u, pb.work + bounce, nullptr, nullptr,
-      tune("PT_REFILL", EXT_REFILL), tune("PT_INNER_MIN", EXT_INNER_MIN));
+  launch_traverse_shape<SRC_QUEUE>(env, sc, pb.ps, tq, pb.tcounters + bounce, 0u, pb.work + bounce,
+                                   nullptr, nullptr, false);
 }
 
 void launch_chain(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb,
@@ -1216,16 +1231,7 @@ void launch_trace_batch(const LaunchEnv& env, const DevScene& sc, const float4* 
                         uint32_t n, HitRecord* out)
 {
   // the parity hook runs the SAME classification + persistent traversal code as the renderer
-  if (sc.n_nodes8 != 0u) {
-    const T8Shape sh = t8_shape();
-    launch_t8_shape<SRC_BATCH>(env, sc, PathState{}, nullptr, nullptr, n, work, rays, out,
-                               cdiv(n, (uint32_t)sh.threads));
-    return;
-  }
-  const uint32_t grid = min(traverse_grid<SRC_BATCH>(env), cdiv(n, EXT_THREADS));
-  traverse_kernel<SRC_BATCH><<<grid, EXT_THREADS, 0, env.stream>>>(sc, PathState{}, nullptr, nullptr,
-                                                                   n, work, rays, out, EXT_REFILL,
-                                                                   EXT_INNER_MIN);
+  launch_traverse_shape<SRC_BATCH>(env, sc, PathState{}, nullptr, nullptr, n, work, rays, out, true);
 }
 
 } // namespace pt

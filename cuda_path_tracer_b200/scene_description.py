@@ -139,6 +139,7 @@ class _Object:
     prim_index: int
     material: str
     m: np.ndarray
+    mesh_name: str = ""
 
 
 class SceneDescription:
@@ -156,6 +157,9 @@ class SceneDescription:
         self.resolution = (0, 0)
         self.spp = 1
         self.filename = ""
+        # extension: True = every mesh is uploaded and each mesh object instances its own
+        # (the reference, and the default here, uploads only the alphabetically-first mesh)
+        self.all_meshes = False
 
     def add_material(self, name: str, material: Material):
         self.materials.setdefault(name, material)
@@ -178,7 +182,9 @@ class SceneDescription:
             raise KeyError(f"Cannot find material {material}")
         if mesh_name not in self.meshes:
             raise KeyError(f"Cannot find mesh {mesh_name}")
-        self.objects.append(_Object(_abi.OBJ_MESH, 0, material, np.asarray(transform, dtype=np.float32)))
+        o = _Object(_abi.OBJ_MESH, 0, material, np.asarray(transform, dtype=np.float32))
+        o.mesh_name = mesh_name
+        self.objects.append(o)
 
     # ---- flat arrays for the C ABI -------------------------------------------------
     def to_desc(self):
@@ -207,7 +213,24 @@ class SceneDescription:
         for i, (c, r) in enumerate(self.spheres):
             sph[i].center[:] = [float(x) for x in c]
             sph[i].radius = r
-        if self.meshes:
+        first = None
+        if self.meshes and self.all_meshes:
+            names_m = sorted(self.meshes)
+            rank = {n: i for i, n in enumerate(names_m)}
+            ps, ix, first, base = [], [], [0], 0
+            for n in names_m:
+                mp = np.ascontiguousarray(self.meshes[n].positions, dtype=np.float32).reshape(-1, 3)
+                mi = np.ascontiguousarray(self.meshes[n].indices, dtype=np.uint32).reshape(-1)
+                ps.append(mp)
+                ix.append(mi + np.uint32(base))
+                base += mp.shape[0]
+                first.append(first[-1] + mi.size)
+            pos, idx = np.concatenate(ps), np.concatenate(ix).astype(np.uint32)
+            first = np.array(first, dtype=np.uint64)
+            for i, o in enumerate(self.objects):
+                if o.type == _abi.OBJ_MESH:
+                    objs[i].prim_index = rank[o.mesh_name]
+        elif self.meshes:
             mesh = self.meshes[sorted(self.meshes)[0]]
             pos = np.ascontiguousarray(mesh.positions, dtype=np.float32).reshape(-1, 3)
             idx = np.ascontiguousarray(mesh.indices, dtype=np.uint32).reshape(-1)
@@ -225,7 +248,10 @@ class SceneDescription:
         d.n_spheres = len(self.spheres)
         d.materials = mats
         d.n_materials = len(names)
-        return d, (pos, idx, objs, sph, mats)
+        if first is not None:
+            d.n_meshes = len(first) - 1
+            d.mesh_first_index = first.ctypes.data_as(C.POINTER(C.c_uint64))
+        return d, (pos, idx, objs, sph, mats, first)
 
 
 # ----------------------------------------------------------------------------- procedural meshes

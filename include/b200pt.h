@@ -89,7 +89,8 @@ typedef struct pt_sphere {
  * material-table index the reference keeps in object_material_indices. */
 typedef struct pt_object {
   int32_t type;        /* pt_object_type */
-  uint32_t prim_index; /* sphere: index into spheres[]; mesh: ignored (one mesh) */
+  uint32_t prim_index; /* sphere: index into spheres[]; mesh: index of the mesh when
+                          pt_scene_desc.n_meshes > 0, else ignored (one mesh) */
   uint32_t material;   /* index into materials[] */
   float m[16];         /* object -> world */
   float inv[16];       /* world -> object */
@@ -109,6 +110,13 @@ typedef struct pt_scene_desc {
   uint32_t n_spheres;
   const pt_material* materials;
   uint32_t n_materials;
+  /* Extension (the reference uploads only its alphabetically-first mesh and every mesh object
+   * instances it, scene_description.cpp:95): several meshes in the one index buffer.
+   * n_meshes == 0: one mesh covering all indices (reference behaviour, prim_index ignored).
+   * Otherwise mesh k is indices[mesh_first_index[k] .. mesh_first_index[k+1]) — n_meshes + 1
+   * entries, multiples of 3 — and a mesh object's prim_index selects its mesh. */
+  uint32_t n_meshes;
+  const uint64_t* mesh_first_index;
 } pt_scene_desc;
 
 /* Camera (src/lib/camera.hpp:17-23). vfov in radians. */
@@ -287,6 +295,12 @@ PT_API int pt_ctx_bind_sums(pt_ctx* ctx, void* device_ptr);
  * (denoiser parity tests feed identical inputs to both implementations). */
 PT_API int pt_ctx_upload_frame(pt_ctx* ctx, const float* color3, const float* normal3,
                                const float* depth1, const pt_camera* camera);
+
+/* Progressive state on disk (checkpoint + resume of long progressive renders): the
+ * running sums and the iteration counter.  load requires a context of the same resolution and
+ * continues where the saved render stopped (same seeds, same result as an uninterrupted run). */
+PT_API int pt_ctx_save_state(pt_ctx* ctx, const char* path);
+PT_API int pt_ctx_load_state(pt_ctx* ctx, const char* path);
 
 PT_API int pt_get_stats(pt_ctx* ctx, pt_stats* stats);
 PT_API int pt_reset_stats(pt_ctx* ctx);

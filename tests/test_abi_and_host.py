@@ -182,3 +182,84 @@ def test_python_scene_description_mirror():
     assert s.materials["ground"].albedo == (0.8, 0.8, 0.0)
     with pytest.raises(KeyError):
         s.add_sphere(1.0, pt.translate((0, 0, 0)), "missing")
+
+
+def test_scene_json_first_mesh_only_by_default_and_all_meshes_extension(tmp_path, monkeypatch):
+    """Two different OBJs named by one scene: the reference uploads only the alphabetically-first
+    mesh and every mesh object instances it (scene_description.cpp:95) — kept as the default;
+    PT_ALL_MESHES=1 (cuda_pt --all-meshes) gives every mesh object its own mesh."""
+    a, b = pt.bunny_like(0), pt.bunny_like(1)
+    (tmp_path / "models").mkdir(exist_ok=True)
+    pt.write_obj(str(tmp_path / "models" / "a.obj"), a)
+    pt.write_obj(str(tmp_path / "models" / "b.obj"), b)
+    js = json.loads(json.dumps(BUNNY_JSON))
+    js["surfaces"][1]["filename"] = "../models/b.obj"
+    js["surfaces"][2]["filename"] = "../models/a.obj"
+    path = _write_scene(tmp_path, js)
+    monkeypatch.delenv("PT_ALL_MESHES", raising=False)
+    rc, h, d, info = _read(path)
+    assert rc == 0 and d.n_meshes == 0 and d.n_indices == a.indices.size       # a.obj sorts first
+    pt.load_library().pt_scene_file_free(h)
+    monkeypatch.setenv("PT_ALL_MESHES", "1")
+    rc, h, d, info = _read(path)
+    assert rc == 0 and d.n_meshes == 2
+    assert [d.mesh_first_index[i] for i in range(3)] == [0, a.indices.size, a.indices.size + b.indices.size]
+    assert d.n_indices == a.indices.size + b.indices.size
+    assert [d.objects[i].prim_index for i in (1, 2)] == [1, 0]                 # b.obj, a.obj
+    idx = np.ctypeslib.as_array(d.indices, shape=(d.n_indices,))
+    assert idx[:a.indices.size].max() < a.positions.shape[0] <= idx[a.indices.size:].min()
+    pt.load_library().pt_scene_file_free(h)
+
+
+def test_multi_mesh_description_bakes_every_mesh():
+    from cuda_path_tracer_b200.api import HostBVH
+    sd = pt.SceneDescription()
+    sd.add_material("m", pt.Material.lambertian((0.5, 0.5, 0.5)))
+    sd.add_mesh("a", pt.bunny_like(1))
+    sd.add_mesh("b", pt.heightfield(6))
+    sd.add_mesh_object("b", pt.translate((0, -1, -3)), "m")
+    sd.add_mesh_object("a", pt.translate((0, 0, -3)), "m")
+    sd.add_mesh_object("a", pt.translate((2, 0, -3)), "m")
+    first_only = HostBVH(sd)                      # reference behaviour: three instances of "a"
+    assert int(first_only.info.n_world_triangles) == 3 * pt.bunny_like(1).triangle_count
+    sd.all_meshes = True
+    hb = HostBVH(sd)
+    assert int(hb.info.n_world_triangles) == 2 * pt.bunny_like(1).triangle_count + pt.heightfield(6).triangle_count
+    assert hb.violations() == 0
+    # a mesh object naming a mesh that does not exist is an error, not a crash
+    d, keep = sd.to_desc()
+    d.objects[0].prim_index = 7
+    h = C.c_void_p()
+    assert pt.load_library().pt_host_bvh_build(C.byref(d), 1, C.byref(h), None) != 0
+    assert b"mesh" in pt.load_library().pt_last_error()
+
+
+def test_binary_mesh_cache_round_trip(tmp_path, monkeypatch):
+    """PT_MESH_CACHE=1: the parsed OBJ is kept as <obj>.b200mesh and reused while the source is
+    unchanged; a modified source invalidates it; without the switch nothing is written."""
+    mesh = pt.bunny_like(2)
+    path = _write_scene(tmp_path, BUNNY_JSON, mesh)
+    obj = tmp_path / "models" / "bunny.obj"
+    side = tmp_path / "models" / "bunny.obj.b200mesh"
+    monkeypatch.delenv("PT_MESH_CACHE", raising=False)
+    rc, h, d, _ = _read(path)
+    assert rc == 0 and not side.exists()
+    first = np.ctypeslib.as_array(d.positions, shape=(d.n_vertices * 3,)).copy()
+    pt.load_library().pt_scene_file_free(h)
+    monkeypatch.setenv("PT_MESH_CACHE", "1")
+    rc, h, d, _ = _read(path)
+    assert rc == 0 and side.exists()
+    pt.load_library().pt_scene_file_free(h)
+    rc, h, d, _ = _read(path)                                  # served from the cache
+    assert rc == 0
+    assert np.array_equal(np.ctypeslib.as_array(d.positions, shape=(d.n_vertices * 3,)), first)
+    assert d.n_indices == mesh.indices.size
+    pt.load_library().pt_scene_file_free(h)
+    pt.write_obj(str(obj), pt.bunny_like(1))                   # the source changes: cache is stale
+    rc, h, d, _ = _read(path)
+    assert rc == 0 and d.n_indices == pt.bunny_like(1).indices.size
+    pt.load_library().pt_scene_file_free(h)
+    side.write_bytes(b"garbage")                               # a corrupt side-car is ignored
+    rc, h, d, _ = _read(path)
+    assert rc == 0 and d.n_indices == pt.bunny_like(1).indices.size
+    pt.load_library().pt_scene_file_free(h)

@@ -213,3 +213,76 @@ def test_wide_tree_traversal_matches_binary_and_oracle(oracle, scene_name, monke
     assert abs(rb - rw) <= max(2, rb // 2000)
     d = np.abs(ib - iw).max(axis=2)
     assert (d > 1e-5).mean() < 2e-3, (d > 1e-5).mean()
+
+
+def test_multi_mesh_scene_matches_oracle_on_the_merged_mesh(oracle):
+    """Several meshes (extension beyond the reference, which uploads one): the hits equal the
+    oracle's on the equivalent single-mesh scene whose mesh is the union of the transformed parts."""
+    a, b = pt.bunny_like(3), pt.heightfield(12)
+    xa, xb = pt.compose(pt.scale(1.6), pt.translate((0.4, 0.1, -2.5))), pt.compose(pt.scale(2.0), pt.translate((0.0, -0.9, -2.5)))
+    sd = pt.SceneDescription()
+    sd.add_material("m", pt.Material.lambertian((0.5, 0.5, 0.5)))
+    sd.add_mesh("a", a)
+    sd.add_mesh("b", b)
+    sd.add_mesh_object("a", xa, "m")
+    sd.add_mesh_object("b", xb, "m")
+    sd.resolution = (80, 60)
+    sd.all_meshes = True
+
+    def world(mesh, xf):
+        p = np.concatenate([mesh.positions.astype(np.float32), np.ones((mesh.positions.shape[0], 1), np.float32)], 1)
+        return (p @ np.asarray(xf, np.float32).T)[:, :3].astype(np.float32)
+
+    merged = pt.Mesh(np.concatenate([world(a, xa), world(b, xb)]),
+                     np.concatenate([a.indices, b.indices + np.uint32(a.positions.shape[0])]).astype(np.uint32))
+    one = pt.SceneDescription()
+    one.add_material("m", pt.Material.lambertian((0.5, 0.5, 0.5)))
+    one.add_mesh("merged", merged)
+    one.add_mesh_object("merged", pt.translate((0, 0, 0)), "m")
+    one.resolution, one.camera = sd.resolution, sd.camera
+    rays, rng = _rays_for(oracle, sd, 80, 60, n_random=3000, seed=3)
+    ours = pt.Scene.from_description(sd).trace_batch(rays)
+    ref = oracle.scene(one).trace_batch(rays, 0)
+    assert (ref["t"] > 0).mean() > 0.1
+    m = (ours["t"] > 0) & (ref["t"] > 0)
+    assert ((ours["t"] > 0) != (ref["t"] > 0)).sum() <= 2
+    rel = np.abs(ours["t"][m] - ref["t"][m]) / np.maximum(ref["t"][m], 1e-6)
+    assert (rel > 1e-5).sum() <= 2
+    # primitive ids are positions in the shared index buffer: identical to the merged mesh's
+    agree = m & (rel.max(initial=0) <= 1e-5)
+    assert (ours["prim"][agree] != ref["prim"][agree]).sum() <= max(2, agree.sum() // 500)
+    # the two objects are told apart
+    assert set(np.unique(ours["object"][m])) == {0, 1}
+
+
+def test_checkpoint_and_resume_continue_the_same_render(tmp_path):
+    sd = pt.bunny_scene(pt.bunny_like(3), 96, 54)
+    w, h = sd.resolution
+    scene = pt.Scene.from_description(sd)
+
+    def tracer():
+        tr = pt.PathTracer(max_depth=6)
+        tr.max_iterations = 8
+        tr.create_buffers((w, h), scene)
+        return tr
+
+    full = tracer()
+    full.render(sd.camera, 8)
+    ref = full.download(DB.color)
+    part = tracer()
+    part.render(sd.camera, 3)
+    state = str(tmp_path / "state.b200pt")
+    part.save_state(state)
+    cont = tracer()
+    cont.load_state(state)
+    assert cont.iteration() == 3
+    cont.render(sd.camera, 8)                     # clipped at max_iterations: renders 5 more
+    assert cont.iteration() == 8
+    got = cont.download(DB.color)
+    assert np.allclose(got, ref, rtol=2e-6, atol=1e-6), np.abs(got - ref).max()
+    other = pt.PathTracer(max_depth=6)
+    other.create_buffers((w // 2, h), scene)
+    with pytest.raises(pt.PTError):
+        other.load_state(state)                   # resolution mismatch is an error
+    with pytest.raises(pt.PTError):
+        other.load_state(str(tmp_path / "missing"))
