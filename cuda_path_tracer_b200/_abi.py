@@ -105,6 +105,8 @@ SYMBOLS = {
     "pt_ctx_create": (C.c_int, [VP, C.c_uint32, C.c_uint32, C.POINTER(pt_params), VP, C.POINTER(VP)]),
     "pt_ctx_destroy": (C.c_int, [VP]),
     "pt_ctx_resize": (C.c_int, [VP, C.c_uint32, C.c_uint32]),
+    "pt_ctx_set_rows": (C.c_int, [VP, C.c_uint32, C.c_uint32]),
+    "pt_denoise_halo_rows": (C.c_int, [C.POINTER(pt_denoise_params), C.POINTER(C.c_uint32)]),
     "pt_ctx_restart": (C.c_int, [VP]),
     "pt_ctx_iteration": (C.c_int, [VP]),
     "pt_ctx_set_max_iterations": (C.c_int, [VP, C.c_int]),

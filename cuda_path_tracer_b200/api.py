@@ -217,6 +217,20 @@ class PathTracer:
         p.clamp_fix = 1 if d.clamp_fix else 0
         check(load_library().pt_denoise(self._ctx, C.byref(p)))
 
+    # -- row-band sharding of one frame (multi-GPU interactive path)
+    def set_rows(self, row_begin: int, row_end: int):
+        """Render / accumulate / denoise rows [row_begin, row_end) only (multiples of 4)."""
+        check(load_library().pt_ctx_set_rows(self._ctx, int(row_begin), int(row_end)))
+
+    def halo_rows(self) -> int:
+        """Rows of valid neighbour data the denoiser needs beyond either end of a band."""
+        p = _abi.pt_denoise_params()
+        load_library().pt_denoise_params_default(C.byref(p))
+        p.filter_size = int(self.atrous_denoiser.filter_size)
+        n = C.c_uint32()
+        check(load_library().pt_denoise_halo_rows(C.byref(p), C.byref(n)))
+        return int(n.value)
+
     # -- PathTracer::send_to_preview (path_tracer.cu:487-520)
     def send_to_preview(self, dev_pbo=None, resolution=None, type: int = DisplayBufferType.final):
         """Tonemap into an RGBA8 image.  dev_pbo: device pointer (int) or None -> numpy [H,W,4]."""

@@ -200,7 +200,9 @@ struct PathState {
 struct PassParams {
   DevCamera cam;
   uint32_t pixels;
-  uint32_t tiles_x, tiles_y; // 8x4-pixel warp tiles
+  uint32_t tiles_x, tiles_y; // 8x4-pixel warp tiles (tiles_y = tile rows of the rendered band)
+  uint32_t tile_y0;          // first tile row of the band (row-band sharding), else 0
+  uint32_t pixel_begin, pixel_end; // pixel range of the band (accumulate)
   uint32_t samples;
   uint32_t first_iteration;
   uint32_t rng_mode;

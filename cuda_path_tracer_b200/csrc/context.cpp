@@ -470,6 +470,8 @@ static int alloc_image_buffers(pt_ctx* c, uint32_t width, uint32_t height)
     return fail(PT_ERR_INVALID, "unsupported resolution");
   c->width = width;
   c->height = height;
+  c->row_begin = 0;
+  c->row_end = height;
   c->pixels = width * height;
   uint32_t spp_pass = 1;
   if (c->params.rng_mode == PT_RNG_SLOT_RESEED) {
@@ -605,6 +607,31 @@ int pt_ctx_resize(pt_ctx* c, uint32_t width, uint32_t height)
   return alloc_image_buffers(c, width, height);
 }
 
+int pt_ctx_set_rows(pt_ctx* c, uint32_t row_begin, uint32_t row_end)
+{
+  if (!c) return fail(PT_ERR_INVALID, "pt_ctx_set_rows: null context");
+  if (row_begin >= row_end || row_end > c->height) return fail(PT_ERR_INVALID, "row band outside the frame");
+  if (row_begin % 4 != 0 || (row_end % 4 != 0 && row_end != c->height))
+    return fail(PT_ERR_INVALID, "row bands start and end on multiples of 4 rows (8x4 primary-ray tiles)");
+  c->row_begin = row_begin;
+  c->row_end = row_end;
+  return PT_OK;
+}
+
+int pt_denoise_halo_rows(const pt_denoise_params* dp, uint32_t* rows)
+{
+  if (!rows) return fail(PT_ERR_INVALID, "pt_denoise_halo_rows: null argument");
+  pt_denoise_params d;
+  if (dp)
+    d = *dp;
+  else
+    pt_denoise_params_default(&d);
+  uint32_t halo = 0;
+  for (int step = 1; step <= d.filter_size; step *= 2) halo += 2u * (uint32_t)step;
+  *rows = halo;
+  return PT_OK;
+}
+
 int pt_ctx_restart(pt_ctx* c)
 {
   if (!c) return fail(PT_ERR_INVALID, "pt_ctx_restart: null context");
@@ -690,13 +717,18 @@ static int render_pass(pt_ctx* c, const pt_camera& cam, uint32_t first_iteration
   pp.cam = make_dev_camera(cam, c->width, c->height);
   pp.pixels = c->pixels;
   pp.tiles_x = (c->width + 7) / 8;
-  pp.tiles_y = (c->height + 3) / 4;
+  pp.tiles_y = (c->row_end - c->row_begin + 3) / 4;
+  pp.tile_y0 = c->row_begin / 4;
+  pp.pixel_begin = c->row_begin * c->width;
+  pp.pixel_end = c->row_end * c->width;
   pp.samples = samples;
   pp.first_iteration = first_iteration;
   pp.rng_mode = (uint32_t)c->params.rng_mode;
   const uint32_t n0 = samples * pp.tiles_x * pp.tiles_y * 32u;
   const uint32_t max_depth = (uint32_t)c->params.max_depth;
   const bool stable = c->params.rng_mode == PT_RNG_SLOT_RESEED;
+  if (stable && (c->row_begin != 0 || c->row_end != c->height))
+    return fail(PT_ERR_INVALID, "row bands need PT_RNG_PIXEL_STREAM (slot re-seeding numbers the whole frame)");
   const uint32_t kLookBehind = 2;
 
   PT_CUDA(cudaMemsetAsync(c->d_counters, 0, c->counters_bytes, c->stream));
@@ -777,7 +809,7 @@ static int render_pass(pt_ctx* c, const pt_camera& cam, uint32_t first_iteration
   PT_CUDA(cudaGetLastError());
   c->stats.kernel_launches += launched;
   c->stats.passes += 1;
-  c->stats.samples += (uint64_t)samples * c->pixels;
+  c->stats.samples += (uint64_t)samples * (pp.pixel_end - pp.pixel_begin);
   return PT_OK;
 }
 
@@ -832,8 +864,18 @@ int pt_denoise(pt_ctx* c, const pt_denoise_params* dp_in)
     if (!p) PT_CUDA(cudaMalloc((void**)&p, (size_t)c->pixels * sizeof(float4)));
   const LaunchEnv env{c->stream, c->sms};
   const DevCamera cam = make_dev_camera(c->last_camera, c->width, c->height);
+  // Row-band sharding: this context owns rows [row_begin, row_end) and holds valid sums for
+  // `halo` more rows on either side (pt_denoise_halo_rows, exchanged by the caller).  Every
+  // iteration runs over the widened window; whatever the missing rows beyond it spoil moves
+  // inwards by 2*step per iteration and stops exactly at the band.
+  uint32_t halo = 0;
+  for (int step = 1; step <= dp.filter_size; step *= 2) halo += 2u * (uint32_t)step;
+  const bool whole = c->row_begin == 0 && c->row_end == c->height;
+  const uint32_t row_lo = whole ? 0u : (c->row_begin > halo ? c->row_begin - halo : 0u);
+  const uint32_t row_hi = whole ? c->height : std::min(c->height, c->row_end + halo);
   prof_begin(c, TAG_DENOISE);
-  launch_denoise_prepare(env, cam, c->d_sums, c->d_sums + c->pixels, c->d_dn[0], c->d_dn[1], c->d_dn[2]);
+  launch_denoise_prepare(env, cam, c->d_sums, c->d_sums + c->pixels, c->d_dn[0], c->d_dn[1], c->d_dn[2],
+                         row_lo, row_hi);
   DenoiseParams kp{dp.color_weight, dp.normal_weight, dp.position_weight, dp.clamp_fix};
   const float4* in = c->d_dn[0];
   float4* bufs[2] = {c->d_dn[3], c->d_dn[4]};
@@ -841,7 +883,7 @@ int pt_denoise(pt_ctx* c, const pt_denoise_params* dp_in)
   float4* last = nullptr;
   uint32_t launches = 1;
   for (int step = 1; step <= dp.filter_size; step *= 2) {
-    launch_atrous(env, cam, kp, in, c->d_dn[1], c->d_dn[2], bufs[which], step);
+    launch_atrous(env, cam, kp, in, c->d_dn[1], c->d_dn[2], bufs[which], step, row_lo, row_hi);
     last = bufs[which];
     in = last;
     which ^= 1;

@@ -105,12 +105,12 @@ accumulate_kernel(const PathState ps, const PassParams pp, float4* __restrict__ 
                   uint32_t n_first, uint32_t max_depth,
                   unsigned long long* __restrict__ total_rays)
 {
-  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p == 0) {
+  const uint32_t p = pp.pixel_begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
     // rays = live paths entering extend, summed over bounces (counters[0] is host-known)
     // (bounce-synchronous mode only: chain_kernel counts its own rays)
     if (pp.rng_mode == 1u) {
-      unsigned long long r = (unsigned long long)pp.pixels * pp.samples;
+      unsigned long long r = (unsigned long long)(pp.pixel_end - pp.pixel_begin) * pp.samples;
       for (uint32_t b = 1; b < max_depth; ++b) r += counters[b];
       total_rays[0] += r;
     }
@@ -120,7 +120,7 @@ accumulate_kernel(const PathState ps, const PassParams pp, float4* __restrict__ 
     for (uint32_t b = 0; b < max_depth; ++b) tr += tc[b];
     total_rays[1] += tr;
   }
-  if (p >= pp.pixels) return;
+  if (p >= pp.pixel_end) return;
   float4 c = sum_color[p];
   float4 g = sum_gbuf[p];
   for (uint32_t s = 0; s < pp.samples; ++s) {
@@ -223,10 +223,11 @@ import_kernel(const float* __restrict__ color3, const float* __restrict__ normal
 __global__ void __launch_bounds__(256)
 denoise_prepare_kernel(const DevCamera cam, const float4* __restrict__ sum_color,
                        const float4* __restrict__ sum_gbuf, float4* __restrict__ color0,
-                       float4* __restrict__ normal_depth, float4* __restrict__ position)
+                       float4* __restrict__ normal_depth, float4* __restrict__ position,
+                       uint32_t row_lo)
 {
   const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t y = blockIdx.y;
+  const uint32_t y = row_lo + blockIdx.y;
   if (x >= cam.width) return;
   const uint32_t p = y * cam.width + x;
   const float4 c = sum_color[p];
@@ -264,14 +265,16 @@ denoise_prepare_kernel(const DevCamera cam, const float4* __restrict__ sum_color
 __global__ void __launch_bounds__(128)
 atrous_kernel(const DevCamera cam, const DenoiseParams dp, const float4* __restrict__ color_in,
               const float4* __restrict__ normal_depth, const float4* __restrict__ position,
-              float4* __restrict__ color_out, int step, int n_groups)
+              float4* __restrict__ color_out, int step, int n_groups, int row_lo, int row_hi)
 {
+  // rows [row_lo, row_hi) are written (the whole frame, or one GPU's band plus its halo); taps
+  // are clamped at the FRAME edges either way, so a band computes what the full frame would
   const int W = (int)cam.width, H = (int)cam.height;
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
   const int g = blockIdx.y * 4 + (threadIdx.x >> 5); // (phase, group of ATR_R dilated rows)
   const int ph = g % step, k = g / step;
   if (x >= W || k >= n_groups) return;
-  const int q0 = k * ATR_R;
+  const int q0 = row_lo / step + k * ATR_R;
 
   const float log2e = 1.4426950408889634f;
   const float kc = log2e / dp.c_phi;
@@ -286,7 +289,7 @@ atrous_kernel(const DevCamera cam, const DenoiseParams dp, const float4* __restr
 #pragma unroll
   for (int r = 0; r < ATR_R; ++r) {
     const int y = (q0 + r) * step + ph;
-    valid[r] = y < H;
+    valid[r] = y < row_hi && y >= row_lo;
     const int p = min(y, H - 1) * W + x;
     const float4 c = ldg4(color_in + p), n = ldg4(normal_depth + p), q = ldg4(position + p);
     cv[r] = mk3(c.x, c.y, c.z);
@@ -361,7 +364,7 @@ void launch_stable_compact(const LaunchEnv& env, const PassBuffers& pb, const Pa
 void launch_accumulate(const LaunchEnv& env, const PassBuffers& pb, const PassParams& pp,
                        float4* sum_color, float4* sum_gbuf, uint32_t max_depth)
 {
-  accumulate_kernel<<<cdiv(pp.pixels, 256), 256, 0, env.stream>>>(
+  accumulate_kernel<<<cdiv(pp.pixel_end - pp.pixel_begin, 256), 256, 0, env.stream>>>(
       pb.ps, pp, sum_color, sum_gbuf, pb.counters, 0u, max_depth, pb.total_rays);
 }
 
@@ -391,23 +394,26 @@ void launch_import_frame(const LaunchEnv& env, const float* color3, const float*
 
 void launch_denoise_prepare(const LaunchEnv& env, const DevCamera& cam, const float4* sum_color,
                             const float4* sum_gbuf, float4* color0, float4* normal_depth,
-                            float4* position)
+                            float4* position, uint32_t row_lo, uint32_t row_hi)
 {
-  dim3 grid(cdiv(cam.width, 256), cam.height);
+  dim3 grid(cdiv(cam.width, 256), row_hi - row_lo);
   denoise_prepare_kernel<<<grid, 256, 0, env.stream>>>(cam, sum_color, sum_gbuf, color0,
-                                                       normal_depth, position);
+                                                       normal_depth, position, row_lo);
 }
 
 void launch_atrous(const LaunchEnv& env, const DevCamera& cam, const DenoiseParams& dp,
                    const float4* color_in, const float4* normal_depth, const float4* position,
-                   float4* color_out, int step_width)
+                   float4* color_out, int step_width, uint32_t row_lo, uint32_t row_hi)
 {
-  // rows are grouped per phase (y mod step): ATR_R outputs of one thread are `step` apart
-  const uint32_t nq = cdiv(cam.height, (uint32_t)step_width);
+  // rows are grouped per phase (y mod step): ATR_R outputs of one thread are `step` apart;
+  // dilated row index q = y / step runs over the window [row_lo, row_hi)
+  const uint32_t q_lo = row_lo / (uint32_t)step_width;
+  const uint32_t nq = cdiv(row_hi, (uint32_t)step_width) - q_lo;
   const uint32_t n_groups = cdiv(nq, ATR_R);
   dim3 grid(cdiv(cam.width, 32), cdiv(n_groups * (uint32_t)step_width, 4));
   atrous_kernel<<<grid, 128, 0, env.stream>>>(cam, dp, color_in, normal_depth, position,
-                                              color_out, step_width, (int)n_groups);
+                                              color_out, step_width, (int)n_groups, (int)row_lo,
+                                              (int)row_hi);
 }
 
 } // namespace pt

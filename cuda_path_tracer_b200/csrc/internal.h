@@ -72,6 +72,7 @@ struct pt_ctx {
   int sms = 148;
   int iteration = 0;
   uint32_t samples_per_pass = 1;
+  uint32_t row_begin = 0, row_end = 0; // rendered / denoised band (row-band sharding); whole frame by default
 
   pt::PassBuffers pb{};
   void* d_state = nullptr;    // one slab for the six PathState planes

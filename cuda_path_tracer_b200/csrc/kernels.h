@@ -66,10 +66,10 @@ struct DenoiseParams {
 // mean colour / normal / world position planes from the running sums
 void launch_denoise_prepare(const LaunchEnv& env, const DevCamera& cam, const float4* sum_color,
                             const float4* sum_gbuf, float4* color0, float4* normal_depth,
-                            float4* position);
+                            float4* position, uint32_t row_lo, uint32_t row_hi);
 void launch_atrous(const LaunchEnv& env, const DevCamera& cam, const DenoiseParams& dp,
                    const float4* color_in, const float4* normal_depth, const float4* position,
-                   float4* color_out, int step_width);
+                   float4* color_out, int step_width, uint32_t row_lo, uint32_t row_hi);
 
 // closest-hit parity hook
 struct HitRecord {

@@ -369,7 +369,7 @@ PT_D bool first_item(const PassParams& pp, uint32_t idx, uint32_t& pid, uint32_t
   const uint32_t tile = r >> 5, lane = r & 31u;
   const uint32_t ty = tile / pp.tiles_x, tx = tile - ty * pp.tiles_x;
   const uint32_t x = tx * 8u + (lane & 7u);
-  const uint32_t y = ty * 4u + (lane >> 3);
+  const uint32_t y = (ty + pp.tile_y0) * 4u + (lane >> 3);
   pixel = y * pp.cam.width + x;
   pid = s * pp.pixels + pixel;
   return x < pp.cam.width && y < pp.cam.height && s < pp.samples;

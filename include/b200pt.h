@@ -250,6 +250,14 @@ PT_API int pt_ctx_create(const pt_scene* scene, uint32_t width, uint32_t height,
 PT_API int pt_ctx_destroy(pt_ctx* ctx);
 /* PathTracer::resize_image (path_tracer.cu:527-545): reallocates and restarts. */
 PT_API int pt_ctx_resize(pt_ctx* ctx, uint32_t width, uint32_t height);
+/* Row-band sharding of ONE frame over several GPUs (the 1-spp interactive path has no sample
+ * range to split): the context renders, accumulates and denoises rows [row_begin, row_end) only.
+ * row_begin and row_end are multiples of 4 (row_end may also be the frame height).  The sums
+ * buffer stays frame-sized, so neighbours' halo rows are received straight into place;
+ * pt_denoise then needs pt_denoise_halo_rows() valid rows beyond either end of the band
+ * (2 * (1 + 2 + ... + last step): 62 for filter_size 16), clipped at the frame edge. */
+PT_API int pt_ctx_set_rows(pt_ctx* ctx, uint32_t row_begin, uint32_t row_end);
+PT_API int pt_denoise_halo_rows(const pt_denoise_params* params, uint32_t* rows);
 /* PathTracer::restart (path_tracer.cu:522-525). */
 PT_API int pt_ctx_restart(pt_ctx* ctx);
 /* PathTracer::iteration(). */
