@@ -322,7 +322,7 @@ def main():
 
 def tracer_state_mb(W, H, tracer):
     spp_pass = int(os.environ.get("PT_SPP_PASS", "0")) or max(1, min(64, (1 << 27) // (W * H)))
-    return int(W * H * spp_pass * 92 / 1e6)
+    return int(W * H * spp_pass * 168 / 1e6)
 
 
 if __name__ == "__main__":

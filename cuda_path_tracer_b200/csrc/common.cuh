@@ -196,6 +196,16 @@ struct PathState {
   uint4* aux;
 };
 
+// Compacted state of the paths parked for one traversal (PT_RNG_PIXEL_STREAM scheduler), indexed
+// by slot = position in that iteration's list: ray[2*slot], ray[2*slot+1], thr[slot], aux[slot]
+// as in PathState, pid[slot] = the path id the final contribution is written under.
+struct ParkBuf {
+  float4* ray;
+  float4* thr;
+  uint4* aux;
+  uint32_t* pid;
+};
+
 // One wavefront pass = `samples` consecutive iterations of every pixel.
 struct PassParams {
   DevCamera cam;

@@ -480,13 +480,13 @@ static int alloc_image_buffers(pt_ctx* c, uint32_t width, uint32_t height)
     spp_pass = (uint32_t)c->params.samples_per_pass;
   } else {
     // Paths in flight per wavefront.  Big passes amortise the latency-bound tail bounces
-    // (measured: 1080p, 64 spp: 4 -> 64 iterations per pass = +30 % Mrays/s); at ~100 B per
-    // path 2^27 paths are 13 GB of B200's 180 GB.  Never take more than a quarter of what is
+    // (measured: 1080p, 64 spp: 4 -> 64 iterations per pass = +30 % Mrays/s); at 168 B per
+    // path 2^27 paths are 22.5 GB of B200's 180 GB.  Never take more than a quarter of what is
     // free on the device.
     uint64_t target = 1ull << 27;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-      const uint64_t by_mem = (uint64_t)(free_b / 4) / 100;
+      const uint64_t by_mem = (uint64_t)(free_b / 4) / 168;
       target = std::max<uint64_t>(1ull << 21, std::min<uint64_t>(target, by_mem));
     }
     spp_pass = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(64, target / c->pixels));
@@ -495,18 +495,38 @@ static int alloc_image_buffers(pt_ctx* c, uint32_t width, uint32_t height)
   const size_t cap = (size_t)c->pixels * spp_pass;
   if (cap > (1ull << 30)) return fail(PT_ERR_INVALID, "wavefront too large");
   c->pb.capacity = (uint32_t)cap;
-  PT_CUDA(cudaMalloc(&c->d_state, cap * (sizeof(float4) * 4 + sizeof(uint4))));
-  float4* base = (float4*)c->d_state;
-  c->pb.ps.ray = base + 0 * cap; // 2 float4 per path, interleaved
-  c->pb.ps.thr = base + 2 * cap;
-  c->pb.ps.gbuf = base + 3 * cap;
-  c->pb.ps.aux = (uint4*)(base + 4 * cap);
-  PT_CUDA(cudaMalloc((void**)&c->pb.queue[0], cap * 4));
-  PT_CUDA(cudaMalloc((void**)&c->pb.queue[1], cap * 4));
-  PT_CUDA(cudaMalloc((void**)&c->pb.tq, cap * 4));
   if (c->params.rng_mode == PT_RNG_SLOT_RESEED) {
+    // bounce-synchronous kernels: path-id indexed planes + id queues
+    PT_CUDA(cudaMalloc(&c->d_state, cap * (sizeof(float4) * 4 + sizeof(uint4))));
+    float4* base = (float4*)c->d_state;
+    c->pb.ps.ray = base + 0 * cap; // 2 float4 per path, interleaved
+    c->pb.ps.thr = base + 2 * cap;
+    c->pb.ps.gbuf = base + 3 * cap;
+    c->pb.ps.aux = (uint4*)(base + 4 * cap);
+    PT_CUDA(cudaMalloc((void**)&c->pb.queue[0], cap * 4));
+    PT_CUDA(cudaMalloc((void**)&c->pb.queue[1], cap * 4));
+    PT_CUDA(cudaMalloc((void**)&c->pb.tq, cap * 4));
     PT_CUDA(cudaMalloc((void**)&c->pb.flags, cap));
     PT_CUDA(cudaMalloc((void**)&c->pb.block_sums, ((cap + 2047) / 2048 + 1) * 4));
+  } else {
+    // chain scheduler: per-path result planes (contribution + first-hit G-buffer, 32 B) and two
+    // compacted park buffers (68 B per slot each)
+    PT_CUDA(cudaMalloc(&c->d_state, cap * (sizeof(float4) * 2 + 2 * (sizeof(float4) * 4 + sizeof(uint32_t)))));
+    float4* base = (float4*)c->d_state;
+    c->pb.ps.ray = nullptr;
+    c->pb.ps.aux = nullptr;
+    c->pb.ps.thr = base + 0 * cap;
+    c->pb.ps.gbuf = base + 1 * cap;
+    float4* p = base + 2 * cap;
+    for (int k = 0; k < 2; ++k) {
+      c->pb.park[k].ray = p;
+      c->pb.park[k].thr = p + 2 * cap;
+      c->pb.park[k].aux = (uint4*)(p + 3 * cap);
+      p += 4 * cap;
+    }
+    uint32_t* ids = (uint32_t*)p;
+    c->pb.park[0].pid = ids;
+    c->pb.park[1].pid = ids + cap;
   }
   PT_CUDA(cudaMalloc((void**)&c->d_sums, (size_t)c->pixels * sizeof(float4) * 2));
   PT_CUDA(cudaMemsetAsync(c->d_sums, 0, (size_t)c->pixels * sizeof(float4) * 2, c->stream));
@@ -754,7 +774,7 @@ static int render_pass(pt_ctx* c, const pt_camera& cam, uint32_t first_iteration
           if (cudaEventQuery(c->bounce_events[probe]) == cudaSuccess && c->h_counts[probe] == 0) break;
         }
         prof_begin(c, TAG_EXT);
-        launch_traverse(env, c->scene->dev, c->pb, c->pb.queue[it & 1], it);
+        launch_traverse_parked(env, c->scene->dev, c->pb, it);
         prof_end(c);
         prof_begin(c, TAG_SHADE);
         launch_chain(env, c->scene->dev, c->pb, pp, it + 1, n0, max_depth);

@@ -12,6 +12,7 @@ struct LaunchEnv {
 // Per-pass device scratch owned by the context.
 struct PassBuffers {
   PathState ps;
+  ParkBuf park[2];     // compacted parked-path state, alternating between iterations (chain scheduler)
   uint32_t* queue[2];  // ping-pong path-id queues (all live paths of a bounce)
   uint32_t* tq;        // traverse queue: paths whose ray enters the mesh BVH this bounce
   uint32_t* counters;  // [0 .. max_depth]   live paths entering bounce b
@@ -29,6 +30,8 @@ void launch_raygen(const LaunchEnv& env, const DevScene& sc, const PassBuffers& 
 // BVH traversal of the traverse queue of `bounce` (length tcounters[bounce], device side).
 void launch_traverse(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb,
                      const uint32_t* tq, uint32_t bounce);
+// traversal of the compacted parked state of chain iteration `iter` (length tcounters[iter]).
+void launch_traverse_parked(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb, uint32_t iter);
 // PT_RNG_PIXEL_STREAM scheduler: iter 0 = raygen + in-register chains of simple bounces for
 // the primary samples; iter >= 1 = the same for the paths traverse_kernel just served
 // (queue[(iter-1)&1], tcounters[iter-1]).  Paths whose next ray needs the BVH are parked in

@@ -501,7 +501,7 @@ traverse_kernel(const DevScene sc, const PathState ps, const uint32_t* __restric
         const uint32_t idx = base + (uint32_t)__popc(need & lt_mask);
         if (idx < n) {
           if (SRC == SRC_QUEUE) {
-            pid = tq[idx];
+            pid = tq ? tq[idx] : idx; // no list: the state is compacted, slot == index
             const float4 ro = ps.ray[2 * (size_t)pid];
             const float4 rd = ps.ray[2 * (size_t)pid + 1];
             const uint4 ax = ps.aux[pid];
@@ -716,7 +716,7 @@ traverse8_kernel(const DevScene sc, const PathState ps, const uint32_t* __restri
           float tbest;
           bool complex_ray = true;
           if (SRC == SRC_QUEUE) {
-            pid = tq[idx];
+            pid = tq ? tq[idx] : idx; // no list: the state is compacted, slot == index
             ro = ps.ray[2 * (size_t)pid];
             rd = ps.ray[2 * (size_t)pid + 1];
             tbest = __uint_as_float(ps.aux[pid].x);
@@ -990,12 +990,29 @@ shade_kernel(const DevScene sc, const PathState ps, const PassParams pp,
 // next item — lane refill as in traverse_kernel — was measured and rejected: lane occupancy
 // rose but chain<true> went 4.65 -> 7.0 ms and chain<false> 6.05 -> 6.6 ms on the bunny frame;
 // these kernels are bound by the latency of their path-state loads/stores, not by issue slots.)
+//
+// Parked paths are COMPACTED: the state a parked path needs to continue (ray 32 B, throughput +
+// RNG 16 B, aux 16 B, path id 4 B) is written to slot = its position in the next iteration's
+// list, so the append, the traversal's ray fetch / result store and the next chain launch's
+// reload are contiguous streams — no path-id gather anywhere between the two ends of a path.
+// (Measured: regrouping the list by direction octant, which scatters these accesses, slowed the
+// next chain launch by 30-100 %.)  Two park buffers alternate between iterations.
+PT_D uint32_t warp_slot(bool push, uint32_t* __restrict__ count, uint32_t lane)
+{
+  const uint32_t mask = __ballot_sync(0xffffffffu, push);
+  if (mask == 0u) return 0u;
+  const int leader = __ffs(mask) - 1;
+  uint32_t base = 0;
+  if ((int)lane == leader) base = atomicAdd(count, (uint32_t)__popc(mask));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+}
+
 template <bool FIRST>
 __global__ void __launch_bounds__(FULL_THREADS)
-chain_kernel(const DevScene sc, const PathState ps, const PassParams pp,
-             const uint32_t* __restrict__ queue, const uint32_t* __restrict__ n_ptr,
-             uint32_t n_first, uint32_t* __restrict__ next_queue,
-             uint32_t* __restrict__ next_count, uint32_t max_depth,
+chain_kernel(const DevScene sc, const PathState ps, const PassParams pp, const ParkBuf in,
+             const uint32_t* __restrict__ n_ptr, uint32_t n_first, const ParkBuf out,
+             uint32_t* __restrict__ out_count, uint32_t max_depth,
              unsigned long long* __restrict__ total_rays)
 {
   const uint32_t n = FIRST ? n_first : *n_ptr;
@@ -1006,19 +1023,13 @@ chain_kernel(const DevScene sc, const PathState ps, const PassParams pp,
   for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_round; idx += stride) {
     uint32_t pid = 0, pixel, s;
     bool valid = idx < n;
-    if (valid) {
-      if (FIRST) {
-        valid = first_item(pp, idx, pid, pixel, s);
-      } else {
-        pid = queue[idx];
-      }
-    }
+    if (FIRST && valid) valid = first_item(pp, idx, pid, pixel, s);
     bool park = false; // the path leaves this kernel with a ray that needs the BVH
+    f3 o = mk3(0.f, 0.f, 0.f), d = o, color = o;
+    float tmin = 0.f, tbest = 0.f;
+    uint32_t rng = 0u, code = 0u, depth = 0u;
+    int start = 0;
     if (valid) {
-      f3 o, d, color;
-      float tmin, tbest;
-      uint32_t rng, code, depth;
-      int start = 0;
       bool need_traversal;
       if (FIRST) {
         // raygen_kernel (ray_gen.cu:11-32): seed, jitter (x then y), pinhole ray
@@ -1032,10 +1043,11 @@ chain_kernel(const DevScene sc, const PathState ps, const PassParams pp,
         depth = 0;
         need_traversal = classify(sc, o, d, tmin, FLT_MAX, tbest, code, start);
       } else {
-        const float4 ro = ps.ray[2 * (size_t)pid];
-        const float4 rd = ps.ray[2 * (size_t)pid + 1];
-        const float4 th = ps.thr[pid];
-        const uint4 ax = ps.aux[pid];
+        const float4 ro = in.ray[2 * (size_t)idx];
+        const float4 rd = in.ray[2 * (size_t)idx + 1];
+        const float4 th = in.thr[idx];
+        const uint4 ax = in.aux[idx];
+        pid = in.pid[idx];
         o = xyz(ro), d = xyz(rd);
         tmin = ro.w;
         color = xyz(th);
@@ -1047,9 +1059,6 @@ chain_kernel(const DevScene sc, const PathState ps, const PassParams pp,
       }
       for (;;) {
         if (need_traversal) {
-          ps.ray[2 * (size_t)pid] = mk4(o, tmin);
-          ps.ray[2 * (size_t)pid + 1] = mk4(d, FLT_MAX);
-          ps.aux[pid] = make_uint4(__float_as_uint(tbest), code, (uint32_t)start, depth);
           park = true;
           break;
         }
@@ -1069,9 +1078,16 @@ chain_kernel(const DevScene sc, const PathState ps, const PassParams pp,
         if (++depth == max_depth) break; // survivors contribute their throughput (path_tracer.cu:252-265)
         need_traversal = classify(sc, o, d, tmin, FLT_MAX, tbest, code, start);
       }
-      ps.thr[pid] = mk4(color, __uint_as_float(rng));
+      if (!park) ps.thr[pid] = mk4(color, __uint_as_float(rng)); // the path's contribution
     }
-    warp_append(park, pid, next_queue, next_count, lane);
+    const uint32_t slot = warp_slot(park, out_count, lane);
+    if (park) {
+      out.ray[2 * (size_t)slot] = mk4(o, tmin);
+      out.ray[2 * (size_t)slot + 1] = mk4(d, FLT_MAX);
+      out.thr[slot] = mk4(color, __uint_as_float(rng));
+      out.aux[slot] = make_uint4(__float_as_uint(tbest), code, (uint32_t)start, depth);
+      out.pid[slot] = pid;
+    }
   }
   // one 64-bit atomic per warp for the ray counter
   for (int off = 16; off > 0; off >>= 1) rays_local += __shfl_down_sync(0xffffffffu, rays_local, off);
@@ -1194,18 +1210,28 @@ void launch_traverse(const LaunchEnv& env, const DevScene& sc, const PassBuffers
                                    nullptr, nullptr, false);
 }
 
+void launch_traverse_parked(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb, uint32_t iter)
+{
+  // the compacted state of iteration `iter` is its own work list
+  PathState view{};
+  view.ray = pb.park[iter & 1].ray;
+  view.aux = pb.park[iter & 1].aux;
+  launch_traverse_shape<SRC_QUEUE>(env, sc, view, nullptr, pb.tcounters + iter, 0u, pb.work + iter,
+                                   nullptr, nullptr, false);
+}
+
 void launch_chain(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb,
                   const PassParams& pp, uint32_t iter, uint32_t n_items_first, uint32_t max_depth)
 {
   const uint32_t grid = (uint32_t)env.sms * 6u;
   if (iter == 0) {
     chain_kernel<true><<<min(grid, cdiv(n_items_first, FULL_THREADS)), FULL_THREADS, 0, env.stream>>>(
-        sc, pb.ps, pp, nullptr, nullptr, n_items_first, pb.queue[0], pb.tcounters + 0, max_depth,
+        sc, pb.ps, pp, ParkBuf{}, nullptr, n_items_first, pb.park[0], pb.tcounters + 0, max_depth,
         pb.total_rays);
   } else {
-    // consumes the traversed queue of iteration iter-1, produces the queue of iteration iter
+    // consumes the traversed state of iteration iter-1, parks into the buffer of iteration iter
     chain_kernel<false><<<grid, FULL_THREADS, 0, env.stream>>>(
-        sc, pb.ps, pp, pb.queue[(iter - 1) & 1], pb.tcounters + (iter - 1), 0u, pb.queue[iter & 1],
+        sc, pb.ps, pp, pb.park[(iter - 1) & 1], pb.tcounters + (iter - 1), 0u, pb.park[iter & 1],
         pb.tcounters + iter, max_depth, pb.total_rays);
   }
 }
