@@ -168,17 +168,18 @@ PT_D void node_test(const DevScene& sc, int node, f3 id, f3 od, float tmin, floa
 }
 
 #define PREFIX_MAX 6
+// `hs` receives the full Intersection of the sphere named by `code` (valid when the ray is simple
+// and code != 0): a caller that shades the ray at once (chain_kernel) need not rebuild it.
 PT_D bool classify(const DevScene& sc, f3 o, f3 d, float tmin, float tmax, float& tbest,
-                   uint32_t& code, int& start)
+                   uint32_t& code, int& start, Hit& hs)
 {
   tbest = tmax;
   code = 0u;
   start = 0;
   for (uint32_t i = 0; i < sc.n_spheres_before; ++i) {
-    float t;
-    if (sphere_t(sc.spheres + i, o, d, tmin, tbest, t)) {
+    if (sphere_test(sc.spheres + i, o, d, tmin, tbest, hs)) {
       code = i + 1u;
-      tbest = t;
+      tbest = hs.t;
     }
   }
   bool complex_ray = false;
@@ -210,14 +211,19 @@ PT_D bool classify(const DevScene& sc, f3 o, f3 d, float tmin, float tmax, float
     code |= AUX_PENDING;
   } else {
     for (uint32_t i = sc.n_spheres_before; i < sc.n_spheres; ++i) {
-      float t;
-      if (sphere_t(sc.spheres + i, o, d, tmin, tbest, t)) {
+      if (sphere_test(sc.spheres + i, o, d, tmin, tbest, hs)) {
         code = i + 1u;
-        tbest = t;
+        tbest = hs.t;
       }
     }
   }
   return complex_ray;
+}
+PT_D bool classify(const DevScene& sc, f3 o, f3 d, float tmin, float tmax, float& tbest,
+                   uint32_t& code, int& start)
+{
+  Hit hs;
+  return classify(sc, o, d, tmin, tmax, tbest, code, start, hs);
 }
 
 // Rebuilds the Intersection (intersection.hpp:8-14) from the 8-byte aux word.
@@ -842,7 +848,9 @@ PT_D f3 random_on_sphere(uint32_t& rng)
   const float phi = (2.0f * 3.14159265358979323846264338327950288f) * minstd_uniform(rng);
   const float cos_theta = 2.0f * minstd_uniform(rng) - 1.0f;
   const float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
-  return mk3(cosf(phi) * sin_theta, sinf(phi) * sin_theta, cos_theta);
+  float sp, cp; // one shared range reduction; same values as sinf(phi), cosf(phi)
+  sincosf(phi, &sp, &cp);
+  return mk3(cp * sin_theta, sp * sin_theta, cos_theta);
 }
 
 PT_D float sign1(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
@@ -1031,6 +1039,8 @@ chain_kernel(const DevScene sc, const PathState ps, const PassParams pp, const P
     int start = 0;
     if (valid) {
       bool need_traversal;
+      Hit h;
+      bool have_hit = false; // h already holds the Intersection of `code` (a sphere found by classify)
       if (FIRST) {
         // raygen_kernel (ray_gen.cu:11-32): seed, jitter (x then y), pinhole ray
         rng = minstd_seed(wang_hash(wang_hash(pixel) ^ (pp.first_iteration + s)));
@@ -1041,7 +1051,8 @@ chain_kernel(const DevScene sc, const PathState ps, const PassParams pp, const P
         tmin = 1e-4f;
         color = mk3(1.0f, 1.0f, 1.0f);
         depth = 0;
-        need_traversal = classify(sc, o, d, tmin, FLT_MAX, tbest, code, start);
+        need_traversal = classify(sc, o, d, tmin, FLT_MAX, tbest, code, start, h);
+        have_hit = true;
       } else {
         const float4 ro = in.ray[2 * (size_t)idx];
         const float4 rd = in.ray[2 * (size_t)idx + 1];
@@ -1063,8 +1074,9 @@ chain_kernel(const DevScene sc, const PathState ps, const PassParams pp, const P
           break;
         }
         ++rays_local;
-        Hit h;
-        const bool hit = resolve_hit(sc, o, d, tmin, tbest, code, h);
+        // a simple ray's sphere hit comes straight from classification (same arithmetic, same
+        // root as resolve_hit would pick); traversed rays rebuild theirs from the aux word
+        const bool hit = have_hit ? code != 0u : resolve_hit(sc, o, d, tmin, tbest, code, h);
         if (depth == 0u) {
           ps.gbuf[pid] = hit ? make_float4(h.n.x, h.n.y, h.n.z, h.t)
                              : make_float4(-d.x, -d.y, -d.z, 1e6f);
@@ -1076,7 +1088,8 @@ chain_kernel(const DevScene sc, const PathState ps, const PassParams pp, const P
         const DevMaterial mat = sc.materials[h.material];
         scatter(mat, h, o, d, tmin, color, rng);
         if (++depth == max_depth) break; // survivors contribute their throughput (path_tracer.cu:252-265)
-        need_traversal = classify(sc, o, d, tmin, FLT_MAX, tbest, code, start);
+        need_traversal = classify(sc, o, d, tmin, FLT_MAX, tbest, code, start, h);
+        have_hit = true;
       }
       if (!park) ps.thr[pid] = mk4(color, __uint_as_float(rng)); // the path's contribution
     }
