@@ -15,6 +15,9 @@
 #include <atomic>
 #include <cfloat>
 #include <cmath>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace pt {
@@ -514,6 +517,16 @@ void build_bvh(const std::vector<BuildTri>& tris, FlatBVH& out, bool wide)
   const size_t n = tris.size();
   if (n == 0) return;
 
+  // PT_BUILD_TIMING=1 prints the phases to stderr
+  const bool timing = std::getenv("PT_BUILD_TIMING") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "build_bvh: %-22s %8.1f ms\n", what,
+                 std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
   Builder B;
   B.kLeafMax = wide ? 3 : 4;
   B.prims.resize(n);
@@ -544,16 +557,19 @@ void build_bvh(const std::vector<BuildTri>& tris, FlatBVH& out, bool wide)
       root_cb.grow(lc);
     }
   }
+  lap("primitive boxes");
   const uint32_t root = B.alloc_node();
 #pragma omp parallel
   {
 #pragma omp single
     B.build(root, 0, (uint32_t)n, 0, root_box, root_cb);
   }
+  lap("binned SAH recursion");
 
   // ---- wide tree first: it decides the triangle order both trees share
   WideBuilder W(B);
   if (wide) W.run(root, (uint32_t)n, out);
+  lap("wide collapse");
 
   // ---- flatten: inner nodes in DFS pre-order, triangles in leaf order
   const bool root_is_leaf = B.nodes[root].count != 0;
@@ -646,6 +662,7 @@ void build_bvh(const std::vector<BuildTri>& tris, FlatBVH& out, bool wide)
   }
   out.sah_cost = sah;
   out.depth = B.max_depth.load() + 1;
+  lap("flatten");
 }
 
 
