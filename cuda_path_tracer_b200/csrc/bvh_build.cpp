@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <new>
 
 namespace pt {
 namespace {
@@ -94,16 +95,40 @@ struct BinSet {
   }
 };
 
+// trivially constructible on purpose: the node and primitive arrays are allocated without being
+// cleared (a single-threaded clear of ~0.5 GB cost more than the parallel passes that fill them)
 struct BuildNode {
   Box box;
-  uint32_t left = 0, right = 0;  // children (inner) ...
-  uint32_t first = 0, count = 0; // ... or primitive range (leaf, count > 0)
+  uint32_t left, right;  // children (inner) ...
+  uint32_t first, count; // ... or primitive range (leaf, count > 0)
+  uint32_t inner;        // inner nodes in this subtree, itself included (0 for a leaf)
+};
+
+template <typename T> struct RawArray {
+  T* p = nullptr;
+  size_t n = 0;
+  RawArray() = default;
+  RawArray(const RawArray&) = delete;
+  RawArray& operator=(const RawArray&) = delete;
+  ~RawArray() { std::free(p); }
+  void resize(size_t count)
+  {
+    std::free(p);
+    p = static_cast<T*>(std::malloc(std::max<size_t>(1, count) * sizeof(T)));
+    if (!p) throw std::bad_alloc();
+    n = count;
+  }
+  T* data() { return p; }
+  const T* data() const { return p; }
+  T* begin() { return p; }
+  T& operator[](size_t i) { return p[i]; }
+  const T& operator[](size_t i) const { return p[i]; }
 };
 
 struct Builder {
   int kLeafMax = 4; // 3 when the compressed 8-wide tree is derived from this one
-  std::vector<Prim> prims;
-  std::vector<BuildNode> nodes;
+  RawArray<Prim> prims;
+  RawArray<BuildNode> nodes;
   std::atomic<uint32_t> n_nodes{0};
   std::atomic<uint32_t> max_depth{0};
 
@@ -113,6 +138,8 @@ struct Builder {
   {
     nodes[ni].first = first;
     nodes[ni].count = count;
+    nodes[ni].left = nodes[ni].right = 0;
+    nodes[ni].inner = 0;
     uint32_t d = (uint32_t)depth, cur = max_depth.load(std::memory_order_relaxed);
     while (d > cur && !max_depth.compare_exchange_weak(cur, d)) {}
   }
@@ -263,6 +290,7 @@ struct Builder {
     nodes[ni].left = l;
     nodes[ni].right = r;
     nodes[ni].count = 0;
+    nodes[ni].first = first;
     const uint32_t lc = mid - first, rc = first + count - mid;
     if (count >= kTaskMin) {
 #pragma omp task default(shared) firstprivate(l, first, lc, depth, lbox, lcb)
@@ -274,6 +302,7 @@ struct Builder {
       build(l, first, lc, depth + 1, lbox, lcb);
       build(r, mid, rc, depth + 1, rbox, rcb);
     }
+    nodes[ni].inner = 1u + nodes[l].inner + nodes[r].inner;
   }
 };
 
@@ -580,7 +609,7 @@ void build_bvh(const std::vector<BuildTri>& tris, FlatBVH& out, bool wide)
   }
   const bool need_null = root_is_leaf;
   out.n_tris = (uint32_t)n + (need_null ? 1u : 0u);
-  out.tris.resize((size_t)out.n_tris * 12);
+  out.tris.resize((size_t)out.n_tris * 12); // not cleared: every element is written below
 #pragma omp parallel for schedule(static)
   for (long long i = 0; i < (long long)n; ++i) {
     const BuildTri& t = tris[B.prims[wide ? W.order[i] : (uint32_t)i].id];
@@ -624,41 +653,77 @@ void build_bvh(const std::vector<BuildTri>& tris, FlatBVH& out, bool wide)
     return;
   }
 
-  // count inner nodes and assign pre-order indices iteratively
+  // DFS pre-order index of an inner node = its parent's + 1 (left child) or + 1 + the left
+  // subtree's inner-node count (right child): known without a sequential walk, so the nodes are
+  // emitted by parallel tasks
   const uint32_t total = B.n_nodes.load();
-  std::vector<uint32_t> inner_index(total, 0xffffffffu);
-  std::vector<uint32_t> stack;
-  stack.reserve(128);
-  uint32_t n_inner = 0;
-  stack.push_back(root);
-  while (!stack.empty()) {
-    const uint32_t ni = stack.back();
-    stack.pop_back();
-    const BuildNode& nd = B.nodes[ni];
-    if (nd.count != 0) continue;
-    inner_index[ni] = n_inner++;
-    stack.push_back(nd.right);
-    stack.push_back(nd.left);
-  }
+  const uint32_t n_inner = B.nodes[root].inner;
   out.n_nodes = n_inner;
-  out.nodes.assign((size_t)n_inner * 16, 0.f);
+  out.nodes.resize((size_t)n_inner * 16);
+  struct Emit {
+    const Builder& B;
+    const WideBuilder& W;
+    FlatBVH& out;
+    bool wide;
+    void run(uint32_t ni, uint32_t index) const
+    {
+      for (;;) {
+        const BuildNode& nd = B.nodes[ni];
+        const BuildNode& l = B.nodes[nd.left];
+        const BuildNode& r = B.nodes[nd.right];
+        const uint32_t li = index + 1u, ri = index + 1u + l.inner;
+        const uint32_t lf = wide ? W.new_first[nd.left] : l.first, rf = wide ? W.new_first[nd.right] : r.first;
+        float* o = &out.nodes[(size_t)index * 16];
+        o[14] = o[15] = 0.f;
+        write_child(o, 0, l, l.count ? leaf_code(lf, l.count) : li);
+        write_child(o, 1, r, r.count ? leaf_code(rf, r.count) : ri);
+        const bool go_l = l.count == 0, go_r = r.count == 0;
+        if (go_l && go_r) {
+          if (r.inner >= 2048u) {
+            const uint32_t rn = nd.right;
+#pragma omp task default(shared) firstprivate(rn, ri)
+            run(rn, ri);
+          } else {
+            run(nd.right, ri);
+          }
+          ni = nd.left;
+          index = li;
+        } else if (go_l) {
+          ni = nd.left;
+          index = li;
+        } else if (go_r) {
+          ni = nd.right;
+          index = ri;
+        } else {
+          return;
+        }
+      }
+    }
+    static uint32_t leaf_code(uint32_t first, uint32_t count) { return ~((first << 3) | (count - 1u)); }
+    static void write_child(float* nd, int c, const BuildNode& ch, uint32_t code)
+    {
+      const Box& b = ch.box;
+      const int o = c == 0 ? 0 : 4, z = c == 0 ? 8 : 10;
+      nd[o + 0] = pad_lo(b.lo[0], b.hi[0]), nd[o + 1] = pad_hi(b.lo[0], b.hi[0]);
+      nd[o + 2] = pad_lo(b.lo[1], b.hi[1]), nd[o + 3] = pad_hi(b.lo[1], b.hi[1]);
+      nd[z + 0] = pad_lo(b.lo[2], b.hi[2]), nd[z + 1] = pad_hi(b.lo[2], b.hi[2]);
+      nd[12 + c] = u2f(code);
+    }
+  };
+  const Emit emit{B, W, out, wide};
+#pragma omp parallel
+  {
+#pragma omp single
+    emit.run(root, 0u);
+  }
   double sah = 0.0;
   const double root_area = B.nodes[root].box.area();
+  if (root_area > 0) {
 #pragma omp parallel for schedule(static) reduction(+ : sah)
-  for (long long ni = 0; ni < (long long)total; ++ni) {
-    const BuildNode& nd = B.nodes[ni];
-    if (nd.count != 0) {
-      if (root_area > 0) sah += (double)nd.box.area() / root_area * nd.count * kIsectCost;
-      continue;
+    for (long long ni = 0; ni < (long long)total; ++ni) {
+      const BuildNode& nd = B.nodes[ni];
+      sah += (double)nd.box.area() / root_area * (nd.count != 0 ? nd.count * kIsectCost : kTravCost);
     }
-    if (inner_index[ni] == 0xffffffffu) continue;
-    if (root_area > 0) sah += (double)nd.box.area() / root_area * kTravCost;
-    float* o = &out.nodes[(size_t)inner_index[ni] * 16];
-    const BuildNode& l = B.nodes[nd.left];
-    const BuildNode& r = B.nodes[nd.right];
-    const uint32_t lf = wide ? W.new_first[nd.left] : l.first, rf = wide ? W.new_first[nd.right] : r.first;
-    write_child(o, 0, l, l.count ? leaf_code(lf, l.count) : inner_index[nd.left]);
-    write_child(o, 1, r, r.count ? leaf_code(rf, r.count) : inner_index[nd.right]);
   }
   out.sah_cost = sah;
   out.depth = B.max_depth.load() + 1;

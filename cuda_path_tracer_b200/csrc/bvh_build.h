@@ -2,6 +2,9 @@
 // bvh_from_mesh, src/lib/accelerators/bvh.cpp:211-253).
 #pragma once
 #include <cstdint>
+#include <memory>
+#include <new>
+#include <utility>
 #include <vector>
 
 namespace pt {
@@ -14,16 +17,30 @@ struct BuildTri {
   uint32_t material; // material-table index of that object
 };
 
+// std::vector whose resize() leaves new elements uninitialised: the big output arrays are filled
+// by parallel loops, a serial zero fill first would cost as much as filling them.
+template <typename T> struct DefaultInitAlloc : std::allocator<T> {
+  template <typename U> struct rebind {
+    using other = DefaultInitAlloc<U>;
+  };
+  template <typename U> void construct(U* p) noexcept { ::new (static_cast<void*>(p)) U; }
+  template <typename U, typename... A> void construct(U* p, A&&... a)
+  {
+    ::new (static_cast<void*>(p)) U(std::forward<A>(a)...);
+  }
+};
+template <typename T> using RawVector = std::vector<T, DefaultInitAlloc<T>>;
+
 struct FlatBVH {
-  std::vector<float> nodes; // 16 floats per node  (layout: common.cuh)
-  std::vector<float> tris;  // 12 floats per triangle, leaf order
+  RawVector<float> nodes; // 16 floats per node  (layout: common.cuh)
+  RawVector<float> tris;  // 12 floats per triangle, leaf order
   uint32_t n_nodes = 0;
   uint32_t n_tris = 0; // including the trailing null triangle, if any
   uint32_t depth = 0;
   double sah_cost = 0.0;
   float root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0}; // padded bounds of everything
   // compressed 8-wide tree over the same triangle array (layout: common.cuh), breadth-first
-  std::vector<uint32_t> nodes8; // 20 words (80 B) per node
+  RawVector<uint32_t> nodes8; // 20 words (80 B) per node
   uint32_t n_nodes8 = 0;
   uint32_t depth8 = 0;
 };

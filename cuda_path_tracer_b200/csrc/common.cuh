@@ -206,6 +206,30 @@ struct ParkBuf {
   uint32_t* pid;
 };
 
+// Exact unsigned division by a run-time constant (Granlund & Montgomery 1994, round-up method):
+// the bounce-0 index map divides three times per primary sample, ~20 instructions each as a
+// plain `/`.  q = (t + ((n - t) >> sh1)) >> sh2 with t = umulhi(m, n).
+struct FastDiv {
+  uint32_t m, sh1, sh2;
+};
+inline FastDiv make_fastdiv(uint32_t d)
+{
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l; // ceil(log2 d)
+  FastDiv f;
+  f.m = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+  f.sh1 = l < 1u ? l : 1u;
+  f.sh2 = l > 1u ? l - 1u : 0u;
+  return f;
+}
+#ifdef __CUDACC__
+PT_D uint32_t fd_div(uint32_t n, const FastDiv& f)
+{
+  const uint32_t t = __umulhi(f.m, n);
+  return (t + ((n - t) >> f.sh1)) >> f.sh2;
+}
+#endif
+
 // One wavefront pass = `samples` consecutive iterations of every pixel.
 struct PassParams {
   DevCamera cam;
@@ -213,6 +237,7 @@ struct PassParams {
   uint32_t tiles_x, tiles_y; // 8x4-pixel warp tiles (tiles_y = tile rows of the rendered band)
   uint32_t tile_y0;          // first tile row of the band (row-band sharding), else 0
   uint32_t pixel_begin, pixel_end; // pixel range of the band (accumulate)
+  FastDiv fd_per_sample, fd_tiles_x, fd_width; // divisors of the bounce-0 index map
   uint32_t samples;
   uint32_t first_iteration;
   uint32_t rng_mode;

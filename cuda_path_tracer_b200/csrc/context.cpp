@@ -741,6 +741,9 @@ static int render_pass(pt_ctx* c, const pt_camera& cam, uint32_t first_iteration
   pp.tile_y0 = c->row_begin / 4;
   pp.pixel_begin = c->row_begin * c->width;
   pp.pixel_end = c->row_end * c->width;
+  pp.fd_per_sample = make_fastdiv(pp.tiles_x * pp.tiles_y * 32u);
+  pp.fd_tiles_x = make_fastdiv(pp.tiles_x);
+  pp.fd_width = make_fastdiv(c->width);
   pp.samples = samples;
   pp.first_iteration = first_iteration;
   pp.rng_mode = (uint32_t)c->params.rng_mode;

@@ -367,18 +367,23 @@ PT_D void trav_leaf(const DevScene& sc, Trav& T, int* stack)
 // Work item -> (sample, pixel): one warp covers an 8x4 pixel tile so primary
 // rays of a warp are coherent.  Returns false for padding lanes.
 PT_D bool first_item(const PassParams& pp, uint32_t idx, uint32_t& pid, uint32_t& pixel,
-                     uint32_t& s)
+                     uint32_t& s, uint32_t& x, uint32_t& y)
 {
   const uint32_t per_sample = pp.tiles_x * pp.tiles_y * 32u;
-  s = idx / per_sample;
+  s = fd_div(idx, pp.fd_per_sample);
   const uint32_t r = idx - s * per_sample;
   const uint32_t tile = r >> 5, lane = r & 31u;
-  const uint32_t ty = tile / pp.tiles_x, tx = tile - ty * pp.tiles_x;
-  const uint32_t x = tx * 8u + (lane & 7u);
-  const uint32_t y = (ty + pp.tile_y0) * 4u + (lane >> 3);
+  const uint32_t ty = fd_div(tile, pp.fd_tiles_x), tx = tile - ty * pp.tiles_x;
+  x = tx * 8u + (lane & 7u);
+  y = (ty + pp.tile_y0) * 4u + (lane >> 3);
   pixel = y * pp.cam.width + x;
   pid = s * pp.pixels + pixel;
   return x < pp.cam.width && y < pp.cam.height && s < pp.samples;
+}
+PT_D bool first_item(const PassParams& pp, uint32_t idx, uint32_t& pid, uint32_t& pixel, uint32_t& s)
+{
+  uint32_t x, y;
+  return first_item(pp, idx, pid, pixel, s, x, y);
 }
 
 // Appends `pid` of every lane with `push` set: one atomic per warp (ballot + popc prefix).
@@ -1029,9 +1034,9 @@ chain_kernel(const DevScene sc, const PathState ps, const PassParams pp, const P
   const uint32_t stride = gridDim.x * blockDim.x;
   uint32_t rays_local = 0;
   for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_round; idx += stride) {
-    uint32_t pid = 0, pixel, s;
+    uint32_t pid = 0, pixel, s, px, py;
     bool valid = idx < n;
-    if (FIRST && valid) valid = first_item(pp, idx, pid, pixel, s);
+    if (FIRST && valid) valid = first_item(pp, idx, pid, pixel, s, px, py);
     bool park = false; // the path leaves this kernel with a ray that needs the BVH
     f3 o = mk3(0.f, 0.f, 0.f), d = o, color = o;
     float tmin = 0.f, tbest = 0.f;
@@ -1044,9 +1049,8 @@ chain_kernel(const DevScene sc, const PathState ps, const PassParams pp, const P
       if (FIRST) {
         // raygen_kernel (ray_gen.cu:11-32): seed, jitter (x then y), pinhole ray
         rng = minstd_seed(wang_hash(wang_hash(pixel) ^ (pp.first_iteration + s)));
-        const uint32_t y = pixel / pp.cam.width, x = pixel - y * pp.cam.width;
-        const float fx = (float)x + minstd_uniform(rng);
-        const float fy = (float)y + minstd_uniform(rng);
+        const float fx = (float)px + minstd_uniform(rng);
+        const float fy = (float)py + minstd_uniform(rng);
         camera_ray(pp.cam, fx, fy, o, d);
         tmin = 1e-4f;
         color = mk3(1.0f, 1.0f, 1.0f);
