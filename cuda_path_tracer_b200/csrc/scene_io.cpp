@@ -14,7 +14,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fcntl.h>
 #include <filesystem>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <map>
 #include <memory>
 
@@ -370,6 +374,14 @@ void write_mesh_cache(const char* path, const std::vector<float>& positions, con
 } // namespace
 
 static int parse_obj_file(const char* path, std::vector<float>& positions, std::vector<uint32_t>& indices);
+struct TextView {
+  const char* p;
+  size_t n;
+  const char* data() const { return p; }
+  size_t size() const { return n; }
+};
+static int parse_obj_serial(const char* path, const TextView& text, std::vector<float>& positions,
+                            std::vector<uint32_t>& indices);
 
 int load_obj_file(const char* path, std::vector<float>& positions, std::vector<uint32_t>& indices)
 {
@@ -380,10 +392,9 @@ int load_obj_file(const char* path, std::vector<float>& positions, std::vector<u
   return rc;
 }
 
-static int parse_obj_file(const char* path, std::vector<float>& positions, std::vector<uint32_t>& indices)
+static int parse_obj_serial(const char* path, const TextView& text, std::vector<float>& positions,
+                            std::vector<uint32_t>& indices)
 {
-  std::string text;
-  if (!read_file(path, text)) return fail(PT_ERR_IO, std::string("Unable to load ") + path);
   std::vector<float> verts;
   verts.reserve(text.size() / 24);
   positions.clear();
@@ -449,6 +460,250 @@ static int parse_obj_file(const char* path, std::vector<float>& positions, std::
     p = line_end + 1;
   }
   if (indices.empty()) return fail(PT_ERR_PARSE, std::string("Unable to load ") + path);
+  return PT_OK;
+}
+
+// ---- parallel OBJ parser: the 10-M-triangle stress mesh is ~1.5 GB of text, 7 s on one thread.
+// The text is cut into chunks at line ends; three parallel sweeps (count, vertices, faces) with
+// prefix sums in between reproduce the serial reader exactly: same vertex numbering (negative
+// indices count back from the vertices seen so far), same triangle order, same cut-off at the first
+// o/g/usemtl statement that follows a face.
+namespace {
+struct ObjChunk {
+  const char* begin;
+  const char* end;
+  uint64_t n_v = 0, n_tri = 0;
+  const char* first_face = nullptr;       // first f line in the chunk
+  const char* first_group = nullptr;      // first o/g/usemtl line in the chunk
+  const char* group_after_face = nullptr; // first o/g/usemtl line after the chunk's first face
+  uint64_t v_base = 0, tri_base = 0;
+  bool bad_vertex = false, bad_face = false, range_error = false;
+};
+
+inline const char* obj_skip_sp(const char* q, const char* end)
+{
+  while (q < end && (*q == ' ' || *q == '\t')) ++q;
+  return q;
+}
+enum ObjLine { OBJ_OTHER, OBJ_V, OBJ_F, OBJ_GROUP };
+inline ObjLine obj_classify(const char* q, const char* line_end)
+{
+  if (q >= line_end) return OBJ_OTHER;
+  if (q[0] == 'v' && q + 1 < line_end && (q[1] == ' ' || q[1] == '\t')) return OBJ_V;
+  if (q[0] == 'f' && q + 1 < line_end && (q[1] == ' ' || q[1] == '\t')) return OBJ_F;
+  if (q[0] == 'o' || q[0] == 'g' || ((size_t)(line_end - q) >= 6 && !std::strncmp(q, "usemtl", 6))) return OBJ_GROUP;
+  return OBJ_OTHER;
+}
+// corners of a face line starting after the 'f'; returns false on a malformed index
+inline bool obj_face_corners(const char* q, const char* line_end, long long* out, int cap, int& n)
+{
+  n = 0;
+  for (;;) {
+    q = obj_skip_sp(q, line_end);
+    if (q >= line_end || *q == '\r' || *q == '#') break;
+    long long idx = 0;
+    auto r = std::from_chars(q, line_end, idx);
+    if (r.ec != std::errc()) return false;
+    q = r.ptr;
+    while (q < line_end && *q != ' ' && *q != '\t' && *q != '\r') ++q; // skip /vt/vn
+    if (n < cap) out[n] = idx;
+    ++n;
+  }
+  return true;
+}
+
+void obj_count(ObjChunk& c)
+{
+  c.n_v = c.n_tri = 0;
+  c.bad_face = false;
+  c.first_face = c.first_group = c.group_after_face = nullptr;
+  const char* p = c.begin;
+  while (p < c.end) {
+    const char* line_end = (const char*)std::memchr(p, '\n', c.end - p);
+    if (!line_end) line_end = c.end;
+    const char* q = obj_skip_sp(p, c.end);
+    switch (obj_classify(q, line_end)) {
+    case OBJ_V: ++c.n_v; break;
+    case OBJ_F: {
+      long long tmp[4];
+      int n = 0;
+      if (!obj_face_corners(q + 1, line_end, tmp, 0, n)) c.bad_face = true;
+      if (n >= 3) {
+        c.n_tri += (uint64_t)(n - 2);
+        if (!c.first_face) c.first_face = p;
+      }
+      break;
+    }
+    case OBJ_GROUP:
+      if (!c.first_group) c.first_group = p;
+      if (c.first_face && !c.group_after_face) c.group_after_face = p;
+      break;
+    default: break;
+    }
+    p = line_end + 1;
+  }
+}
+} // namespace
+
+static int parse_obj_file(const char* path, std::vector<float>& positions, std::vector<uint32_t>& indices)
+{
+  // the file is mapped, not copied: a 1.5 GB read into a cleared std::string costs a second
+  struct Mapping {
+    void* p = MAP_FAILED;
+    size_t n = 0;
+    int fd = -1;
+    ~Mapping()
+    {
+      if (p != MAP_FAILED) munmap(p, n);
+      if (fd >= 0) close(fd);
+    }
+  } map;
+  map.fd = open(path, O_RDONLY);
+  struct stat st;
+  if (map.fd < 0 || fstat(map.fd, &st) != 0 || !S_ISREG(st.st_mode))
+    return fail(PT_ERR_IO, std::string("Unable to load ") + path);
+  map.n = (size_t)st.st_size;
+  if (map.n == 0) return fail(PT_ERR_PARSE, std::string("Unable to load ") + path);
+  map.p = mmap(nullptr, map.n, PROT_READ, MAP_PRIVATE, map.fd, 0);
+  if (map.p == MAP_FAILED) return fail(PT_ERR_IO, std::string("Unable to load ") + path);
+  const TextView text{static_cast<const char*>(map.p), map.n};
+  const char* force = std::getenv("PT_OBJ_SERIAL");
+  if (text.size() < (1u << 20) || (force && std::atoi(force) != 0)) return parse_obj_serial(path, text, positions, indices);
+
+  const char* base = text.data();
+  const char* end = base + text.size();
+  int n_chunks = std::max(1, std::min<int>(256, (int)(text.size() >> 19)));
+  std::vector<ObjChunk> chunks;
+  {
+    const char* p = base;
+    for (int k = 0; k < n_chunks && p < end; ++k) {
+      const char* want = base + (size_t)((double)text.size() * (k + 1) / n_chunks);
+      const char* e = k + 1 == n_chunks ? end : (const char*)std::memchr(want, '\n', end - want);
+      e = e ? std::min(end, e + 1) : end;
+      if (e <= p) continue;
+      ObjChunk c;
+      c.begin = p;
+      c.end = e;
+      chunks.push_back(c);
+      p = e;
+    }
+  }
+  // sweep 1: counts
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int k = 0; k < (int)chunks.size(); ++k) obj_count(chunks[k]);
+  // cut-off: the first o/g/usemtl statement after the first face ends the (first) mesh
+  {
+    bool have_faces = false;
+    const char* cut = nullptr;
+    size_t cut_chunk = 0;
+    for (size_t k = 0; k < chunks.size() && !cut; ++k) {
+      const ObjChunk& c = chunks[k];
+      const char* g = have_faces ? c.first_group : c.group_after_face;
+      if (g) {
+        cut = g;
+        cut_chunk = k;
+      }
+      if (c.first_face) have_faces = true;
+    }
+    if (cut) {
+      chunks.resize(cut_chunk + 1);
+      chunks.back().end = cut;
+      obj_count(chunks.back());
+    }
+  }
+  uint64_t nv = 0, nt = 0;
+  bool bad_face = false;
+  for (auto& c : chunks) {
+    c.v_base = nv;
+    c.tri_base = nt;
+    nv += c.n_v;
+    nt += c.n_tri;
+    bad_face = bad_face || c.bad_face;
+  }
+  if (bad_face) return fail(PT_ERR_PARSE, std::string("bad face in ") + path);
+  if (nt == 0) return fail(PT_ERR_PARSE, std::string("Unable to load ") + path);
+  if (nt * 3 >= (1ull << 32)) return fail(PT_ERR_INVALID, std::string("too many triangles in ") + path);
+  std::vector<float> verts(nv * 3);
+  positions.resize(nt * 9);
+  indices.resize(nt * 3);
+  // sweep 2: vertices
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int k = 0; k < (int)chunks.size(); ++k) {
+    ObjChunk& c = chunks[k];
+    float* out = verts.data() + c.v_base * 3;
+    const char* p = c.begin;
+    while (p < c.end) {
+      const char* line_end = (const char*)std::memchr(p, '\n', c.end - p);
+      if (!line_end) line_end = c.end;
+      const char* q = obj_skip_sp(p, c.end);
+      if (obj_classify(q, line_end) == OBJ_V) {
+        ++q;
+        float v[3] = {0.f, 0.f, 0.f};
+        for (int i = 0; i < 3; ++i) {
+          q = obj_skip_sp(q, line_end);
+          if (q < line_end && *q == '+') ++q;
+          auto r = std::from_chars(q, line_end, v[i]);
+          if (r.ec != std::errc()) {
+            c.bad_vertex = true;
+            break;
+          }
+          q = r.ptr;
+        }
+        out[0] = v[0], out[1] = v[1], out[2] = v[2];
+        out += 3;
+      }
+      p = line_end + 1;
+    }
+  }
+  // sweep 3: faces (fan-triangulated, one vertex per corner)
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int k = 0; k < (int)chunks.size(); ++k) {
+    ObjChunk& c = chunks[k];
+    long long seen = (long long)c.v_base; // vertices defined before the current line
+    uint64_t tri = c.tri_base;
+    std::vector<long long> corner(64);
+    const char* p = c.begin;
+    while (p < c.end) {
+      const char* line_end = (const char*)std::memchr(p, '\n', c.end - p);
+      if (!line_end) line_end = c.end;
+      const char* q = obj_skip_sp(p, c.end);
+      const ObjLine kind = obj_classify(q, line_end);
+      if (kind == OBJ_V) {
+        ++seen;
+      } else if (kind == OBJ_F) {
+        int n = 0;
+        obj_face_corners(q + 1, line_end, corner.data(), (int)corner.size(), n);
+        if (n > (int)corner.size()) {
+          corner.resize(n);
+          obj_face_corners(q + 1, line_end, corner.data(), (int)corner.size(), n);
+        }
+        for (int i = 0; i < n; ++i) {
+          long long idx = corner[i];
+          if (idx < 0) idx = seen + idx; else idx -= 1;
+          if (idx < 0 || idx >= seen) c.range_error = true;
+          corner[i] = idx;
+        }
+        if (n >= 3 && !c.range_error) {
+          for (int j = 1; j + 1 < n; ++j) {
+            const long long t3[3] = {corner[0], corner[j], corner[j + 1]};
+            for (int cc = 0; cc < 3; ++cc) {
+              const uint64_t o = tri * 3 + (uint64_t)cc;
+              indices[o] = (uint32_t)o;
+              positions[o * 3 + 0] = verts[3 * t3[cc] + 0];
+              positions[o * 3 + 1] = verts[3 * t3[cc] + 1];
+              positions[o * 3 + 2] = verts[3 * t3[cc] + 2];
+            }
+            ++tri;
+          }
+        }
+      }
+      p = line_end + 1;
+    }
+  }
+  for (const auto& c : chunks) {
+    if (c.bad_vertex) return fail(PT_ERR_PARSE, std::string("bad vertex in ") + path);
+    if (c.range_error) return fail(PT_ERR_PARSE, std::string("face index out of range in ") + path);
+  }
   return PT_OK;
 }
 

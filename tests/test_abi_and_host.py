@@ -263,3 +263,65 @@ def test_binary_mesh_cache_round_trip(tmp_path, monkeypatch):
     rc, h, d, _ = _read(path)
     assert rc == 0 and d.n_indices == pt.bunny_like(1).indices.size
     pt.load_library().pt_scene_file_free(h)
+
+
+def _read_obj_scene(tmp_path, obj_text, monkeypatch, serial):
+    (tmp_path / "models").mkdir(exist_ok=True)
+    (tmp_path / "models" / "bunny.obj").write_text(obj_text)
+    if serial:
+        monkeypatch.setenv("PT_OBJ_SERIAL", "1")
+    else:
+        monkeypatch.delenv("PT_OBJ_SERIAL", raising=False)
+    rc, h, d, _ = _read(_write_scene(tmp_path, BUNNY_JSON))
+    if rc != 0:
+        return rc, None, None
+    pos = np.ctypeslib.as_array(d.positions, shape=(d.n_vertices * 3,)).copy()
+    idx = np.ctypeslib.as_array(d.indices, shape=(d.n_indices,)).copy()
+    pt.load_library().pt_scene_file_free(h)
+    return rc, pos, idx
+
+
+def test_parallel_obj_parser_equals_the_serial_reader(tmp_path, monkeypatch):
+    """Files above 1 MB go through the chunked three-sweep parser; it must reproduce the serial
+    reader (the Assimp-semantics restatement) byte for byte on a file that mixes polygons,
+    negative indices, v/vt/vn corners, comments, CRLF line ends and a group statement that cuts
+    the first mesh off."""
+    rng = np.random.default_rng(11)
+    lines = ["# header", "mtllib nothing.mtl"]
+    n_v = 0
+    for block in range(1500):
+        k = int(rng.integers(3, 9))
+        vs = rng.normal(size=(k, 3))
+        for v in vs:
+            lines.append(f"v {v[0]:.7g} {v[1]:+.7g} {v[2]:.7g}" + ("\r" if block % 7 == 0 else ""))
+            lines.append(f"vn 0 1 0")
+            if block % 3 == 0:
+                lines.append("vt 0.5 0.5")
+        n_v += k
+        style = block % 4
+        if style == 0:      # absolute polygon
+            lines.append("f " + " ".join(str(n_v - k + 1 + i) for i in range(k)))
+        elif style == 1:    # negative indices
+            lines.append("f " + " ".join(str(-k + i) for i in range(k)) + "  # relative")
+        elif style == 2:    # v/vt/vn corners, triangle fan of earlier vertices too
+            lines.append("f " + " ".join(f"{n_v - k + 1 + i}/1/1" for i in range(k)))
+            lines.append(f"f 1//1 {n_v}//1 {max(2, n_v - 1)}//1")
+        else:               # v//vn with tabs
+            lines.append("f\t" + "\t".join(f"{n_v - k + 1 + i}//{i + 1}" for i in range(k)))
+        lines.append("s off")
+    body = "\n".join(lines) + "\n"
+    filler = "".join(f"# padding line {i} ................................................\n" for i in range(22000))
+    tail = "g second_mesh\nv 9 9 9\nv 8 8 8\nv 7 7 7\nf -1 -2 -3\n"
+    text = filler[: len(filler) // 2] + body + filler[len(filler) // 2:] + tail
+    assert len(text) > (1 << 20)
+    rc_s, pos_s, idx_s = _read_obj_scene(tmp_path, text, monkeypatch, serial=True)
+    rc_p, pos_p, idx_p = _read_obj_scene(tmp_path, text, monkeypatch, serial=False)
+    assert rc_s == 0 and rc_p == 0
+    assert idx_s.size == idx_p.size and idx_s.size % 3 == 0 and idx_s.size > 3 * 1500
+    assert np.array_equal(idx_s, idx_p) and np.array_equal(pos_s, pos_p)
+    assert not np.any(np.all(pos_p.reshape(-1, 3) == [9, 9, 9], axis=1))      # cut off at "g"
+    # errors surface the same way
+    bad = text.replace("f -1 -2 -3", "f -1 -2 -3").replace("# header", "# header\nv 0 0 0\nf 1 2 99999999")
+    rc_s, _, _ = _read_obj_scene(tmp_path, bad, monkeypatch, serial=True)
+    rc_p, _, _ = _read_obj_scene(tmp_path, bad, monkeypatch, serial=False)
+    assert rc_s != 0 and rc_p != 0
