@@ -325,3 +325,24 @@ def test_parallel_obj_parser_equals_the_serial_reader(tmp_path, monkeypatch):
     rc_s, _, _ = _read_obj_scene(tmp_path, bad, monkeypatch, serial=True)
     rc_p, _, _ = _read_obj_scene(tmp_path, bad, monkeypatch, serial=False)
     assert rc_s != 0 and rc_p != 0
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle and the reference copy are test infrastructure: nothing under the package (or
+    the public header) may import, link, dlopen or even name them."""
+    pkg = os.path.join(ROOT, "cuda_path_tracer_b200")
+    offenders = []
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cpp", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(base, f), errors="replace").read()
+                for needle in ("liboracle", "oracle_lib", "oracle/", "libref_", "ref_lib", "orc_"):
+                    if needle in text:
+                        offenders.append((f, needle))
+    assert not offenders, offenders
+    hdr = open(os.path.join(ROOT, "include", "b200pt.h")).read()
+    assert "oracle" not in hdr.lower()
+    # and the shared library itself does not depend on either
+    import subprocess
+    ldd = subprocess.run(["ldd", pt.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in ldd and "libref" not in ldd
