@@ -256,6 +256,7 @@ def main():
         # end to end through the public API: host camera in, host RGBA8 image out
         tracer.set_sample_count(spp)
         host_img = None
+        pinned = torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True).numpy()  # D2H target
         t_e2e0 = torch.cuda.Event(enable_timing=True)
         t_e2e1 = torch.cuda.Event(enable_timing=True)
         barrier()
@@ -266,7 +267,7 @@ def main():
         for _ in range(args.steps):
             step()
             tracer.set_sample_count(spp * world)
-            host_img = tracer.send_to_preview(type=DB.color)  # tonemap + D2H + sync
+            host_img = tracer.send_to_preview(type=DB.color, out=pinned)  # tonemap + D2H (pinned) + sync
         t_e2e1.record(stream)
         barrier()
         wall_e2e = time.perf_counter() - wall0

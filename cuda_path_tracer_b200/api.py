@@ -232,14 +232,19 @@ class PathTracer:
         return int(n.value)
 
     # -- PathTracer::send_to_preview (path_tracer.cu:487-520)
-    def send_to_preview(self, dev_pbo=None, resolution=None, type: int = DisplayBufferType.final):
-        """Tonemap into an RGBA8 image.  dev_pbo: device pointer (int) or None -> numpy [H,W,4]."""
+    def send_to_preview(self, dev_pbo=None, resolution=None, type: int = DisplayBufferType.final, out=None):
+        """Tonemap into an RGBA8 image.  dev_pbo: device pointer (int); otherwise the image comes
+        back as numpy [H,W,4] — into `out` when given (e.g. a view of PINNED host memory, which
+        makes the device->host copy a plain DMA instead of a staged pageable copy)."""
         lib = load_library()
         w, h = self._res
         if dev_pbo is not None:
             check(lib.pt_resolve_rgba8(self._ctx, int(type), C.c_void_p(int(dev_pbo)), 1))
             return None
-        out = np.empty((h, w, 4), dtype=np.uint8)
+        if out is None:
+            out = np.empty((h, w, 4), dtype=np.uint8)
+        elif out.shape != (h, w, 4) or out.dtype != np.uint8 or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError("out must be a C-contiguous uint8 array of shape [H, W, 4]")
         check(lib.pt_resolve_rgba8(self._ctx, int(type), out.ctypes.data, 0))
         return out
 
