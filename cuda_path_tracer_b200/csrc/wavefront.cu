@@ -1240,9 +1240,14 @@ void launch_traverse_parked(const LaunchEnv& env, const DevScene& sc, const Pass
 void launch_chain(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb,
                   const PassParams& pp, uint32_t iter, uint32_t n_items_first, uint32_t max_depth)
 {
-  const uint32_t grid = (uint32_t)env.sms * 6u;
+  // CTAs per SM of the grid-stride loops (3 are resident at 77-80 registers).  Measured on the
+  // bunny frame: the primary launch likes a fine grid (its per-item cost varies with how many
+  // in-register bounces follow: 6 -> 4.03 ms, 24 -> 3.73 ms), the re-entry launches do not
+  // (6 -> 5.09 ms, 24 -> 5.17 ms).
+  const uint32_t grid = (uint32_t)env.sms * (uint32_t)tune("PT_CHAIN_GRID", 6);
+  const uint32_t grid_first = (uint32_t)env.sms * (uint32_t)tune("PT_CHAIN_GRID0", 24);
   if (iter == 0) {
-    chain_kernel<true><<<min(grid, cdiv(n_items_first, FULL_THREADS)), FULL_THREADS, 0, env.stream>>>(
+    chain_kernel<true><<<min(grid_first, cdiv(n_items_first, FULL_THREADS)), FULL_THREADS, 0, env.stream>>>(
         sc, pb.ps, pp, ParkBuf{}, nullptr, n_items_first, pb.park[0], pb.tcounters + 0, max_depth,
         pb.total_rays);
   } else {
