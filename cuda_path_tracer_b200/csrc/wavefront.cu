@@ -1,26 +1,31 @@
-// wavefront.cu — hand-written sm_100a kernels of the per-bounce wavefront.
+// wavefront.cu — hand-written sm_100a kernels of the path-tracing wavefront.
 //
-// One bounce = two launches, both free of host synchronisation:
+// Default scheduler (PT_RNG_PIXEL_STREAM, every path carries its own RNG stream):
 //
-//   traverse_kernel   BVH traversal ONLY, over the queue of rays whose slab test against the
-//                     mesh root box succeeded ("complex" rays).  Persistent warps, lane-level
-//                     refill with one atomic per warp, culled + ordered walk of 64-byte two-box
-//                     nodes over world-space baked triangles.  Replaces the mesh branch of
-//                     ray_scene_intersection_test (reference path_tracer.cu:36-76).
-//   shade_kernel      full-warp kernel over ALL live paths of the bounce: rebuilds the hit
-//                     (triangle / sphere / miss), evaluate_material + sky + G-buffer
-//                     (path_tracer.cu:29-34, 138-201, 292-315), writes the scattered ray, then
-//                     CLASSIFIES it for the next bounce (sphere tests, path_tracer.cu:87-98, and
-//                     the root-box test) and appends the path id to the next queue — and to the
-//                     traverse queue if it needs the BVH — with warp-aggregated atomics
-//                     (replaces thrust::stable_partition, path_tracer.cu:433-457).
-//   raygen_kernel     bounce 0: raygen_kernel/generate_ray (ray_gen.cu:11-61) + classification.
+//   chain_kernel<true>   raygen (ray_gen.cu:11-61) + classification of the primary rays + every
+//                        bounce that needs no BVH, shaded in registers: rebuilds the hit (sphere /
+//                        triangle / miss), evaluate_material + sky + G-buffer (path_tracer.cu:29-34,
+//                        138-201, 292-315), scatters, classifies the new ray (sphere tests,
+//                        path_tracer.cu:87-98, and a stack-free walk of the top of the BVH).  A path
+//                        whose next ray must enter the BVH is PARKED: its 68-byte state is appended
+//                        to the next list with one warp-aggregated atomic (replaces
+//                        thrust::stable_partition, path_tracer.cu:433-457).
+//   traverse_kernel      BVH traversal ONLY, over the parked rays.  Persistent warps, lane-level
+//                        refill with one atomic per warp, culled + ordered walk of 64-byte two-box
+//                        nodes over world-space baked triangles, while-while scheduling.  Replaces
+//                        the mesh branch of ray_scene_intersection_test (path_tracer.cu:36-76).
+//   chain_kernel<false>  the same chain loop for the paths whose ray was just traversed.
 //
-// Why the split: ncu showed the fused extend+shade kernel issue-bound with 9-10 of 32 lanes
-// active (profiles/r1_bounce_v2_*): in open scenes most rays never enter the BVH, and their
-// sphere tests + shading ran in the partially filled retire/refill phases of a warp whose other
-// lanes were long-running mesh rays.  Now everything that is not traversal runs at full warp
-// occupancy, and only rays that touch the mesh pay for the persistent machinery.
+// Streaming-compat scheduler (PT_RNG_SLOT_RESEED, bounce-synchronous like the reference):
+// raygen_kernel, traverse_kernel over an id queue, shade_kernel, stable scan compaction
+// (image_kernels.cu).
+//
+// Why traversal is split from everything else: ncu showed the fused extend+shade kernel
+// issue-bound with 9-10 of 32 lanes active (profiles/r1_bounce_v2_*): in open scenes most rays
+// never enter the BVH, and their sphere tests + shading ran in the partially filled retire/refill
+// phases of a warp whose other lanes were long-running mesh rays.  Now everything that is not
+// traversal runs at (near) full warp occupancy, and only rays that touch the mesh pay for the
+// persistent machinery.  Opt-in: traverse8_kernel over the compressed 8-wide tree (PT_BVH=8).
 #include "kernels.h"
 
 #include <float.h>
@@ -114,16 +119,6 @@ PT_D bool sphere_test(const DevSphere* __restrict__ sp, f3 o, f3 d, float tmin, 
   h.object = sp->object;
   h.prim = -1;
   return true;
-}
-
-// Only the t of a sphere hit (classification keeps 8 bytes per path, the full record is
-// rebuilt by shade with the same arithmetic).
-PT_D bool sphere_t(const DevSphere* __restrict__ sp, f3 o, f3 d, float tmin, float tmax, float& t)
-{
-  Hit h;
-  const bool r = sphere_test(sp, o, d, tmin, tmax, h);
-  t = h.t;
-  return r;
 }
 
 PT_D float safe_inv(float x)
