@@ -76,7 +76,8 @@ class pt_scene_info(C.Structure):
                 ("n_bvh_nodes", C.c_uint64), ("bvh_depth", C.c_uint32), ("n_objects", C.c_uint32),
                 ("n_spheres", C.c_uint32), ("n_materials", C.c_uint32), ("build_ms", C.c_double),
                 ("upload_ms", C.c_double), ("device_bytes", C.c_uint64),
-                ("n_bvh8_nodes", C.c_uint64), ("bvh8_depth", C.c_uint32), ("reserved", C.c_uint32)]
+                ("n_bvh8_nodes", C.c_uint64), ("bvh8_depth", C.c_uint32), ("device_build", C.c_uint32),
+                ("n_bvh_triangles", C.c_uint64)]
 
 
 class pt_scene_file_info(C.Structure):
@@ -92,6 +93,7 @@ SYMBOLS = {
     "pt_scene_create": (C.c_int, [C.POINTER(pt_scene_desc), C.c_int, C.POINTER(VP)]),
     "pt_scene_destroy": (C.c_int, [VP]),
     "pt_scene_get_info": (C.c_int, [VP, C.POINTER(pt_scene_info)]),
+    "pt_scene_copy_bvh": (C.c_int, [VP, VP, VP]),
     "pt_host_bvh_build": (C.c_int, [C.POINTER(pt_scene_desc), C.c_int, C.POINTER(VP), C.POINTER(pt_scene_info)]),
     "pt_host_bvh_validate": (C.c_int, [VP, C.POINTER(C.c_uint64)]),
     "pt_host_bvh_arrays": (C.c_int, [VP, C.POINTER(VP), C.POINTER(VP), C.POINTER(VP)]),

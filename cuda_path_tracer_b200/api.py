@@ -43,12 +43,15 @@ class EdgeAvoidingATrousDenoiser:
 class HostBVH:
     """Host-only build of both trees (no CUDA call): structure checks and build timing."""
 
-    def __init__(self, desc: SceneDescription, wide: bool = True):
+    def __init__(self, desc: SceneDescription, wide: bool = True, lbvh: bool = False):
+        """wide: also derive the compressed 8-wide tree; lbvh: build with the host restatement of
+        the device LBVH builder instead of the SAH builder."""
         lib = load_library()
         d, keep = desc.to_desc()
         self._h = C.c_void_p()
         self.info = _abi.pt_scene_info()
-        check(lib.pt_host_bvh_build(C.byref(d), 1 if wide else 0, C.byref(self._h), C.byref(self.info)))
+        mode = 2 if lbvh else (1 if wide else 0)
+        check(lib.pt_host_bvh_build(C.byref(d), mode, C.byref(self._h), C.byref(self.info)))
         del keep
 
     def violations(self) -> int:
@@ -67,7 +70,7 @@ class HostBVH:
                 return np.zeros((0, w), dtype=dt)
             return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(n, w)).astype(dt, copy=True)
 
-        n_tris = int(i.n_world_triangles) + (1 if int(i.n_bvh_nodes) == 1 else 0)
+        n_tris = int(i.n_bvh_triangles)
         return (view(a, int(i.n_bvh_nodes), 16, C.c_float, np.float32),
                 view(b, int(i.n_bvh8_nodes), 20, C.c_uint32, np.uint32),
                 view(t, n_tris, 12, C.c_float, np.float32))
@@ -114,6 +117,14 @@ class Scene:
         i = _abi.pt_scene_info()
         check(load_library().pt_scene_get_info(self._h, C.byref(i)))
         return i
+
+    def copy_bvh(self):
+        """(nodes [n,16] f32, triangles [t,12] f32) copied back from the device."""
+        i = self.info
+        nodes = np.zeros((int(i.n_bvh_nodes), 16), dtype=np.float32)
+        tris = np.zeros((int(i.n_bvh_triangles), 12), dtype=np.float32)
+        check(load_library().pt_scene_copy_bvh(self._h, nodes.ctypes.data, tris.ctypes.data))
+        return nodes, tris
 
     def trace_batch(self, rays8: np.ndarray) -> np.ndarray:
         """Closest hits of n rays {o, t_min, d, t_max} -> structured array of pt_hit."""

@@ -15,8 +15,9 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200pt.so")
 EXE = os.path.join(HERE, "cuda_pt")
 
-SOURCES = ["wavefront.cu", "image_kernels.cu", "context.cpp", "bvh_build.cpp", "hostmath.cpp", "scene_io.cpp", "cli.cpp"]
-HEADERS = ["common.cuh", "kernels.h", "internal.h", "bvh_build.h", "../../include/b200pt.h"]
+SOURCES = ["wavefront.cu", "image_kernels.cu", "context.cpp", "bvh_build.cpp", "lbvh_host.cpp", "lbvh.cu", "hostmath.cpp", "scene_io.cpp",
+           "cli.cpp"]
+HEADERS = ["common.cuh", "kernels.h", "internal.h", "bvh_build.h", "lbvh.h", "../../include/b200pt.h"]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",

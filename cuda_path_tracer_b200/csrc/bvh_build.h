@@ -56,6 +56,25 @@ struct FlatBVH {
 void build_bvh(const std::vector<BuildTri>& tris, FlatBVH& out, bool wide = true);
 
 
+// Sequential restatement of the device LBVH builder (lbvh.cu / lbvh.h) — CPU tests and the
+// node-for-node check of the device result.  Returns false when the scene is too small or the
+// tree too deep for the traversal stack (the caller then uses build_bvh).
+bool build_lbvh_host(const std::vector<BuildTri>& tris, FlatBVH& out);
+
+// Device LBVH builder (lbvh.cu).  h_tris: n world-space triangles in host memory.  With
+// out.built == true, out.nodes / out.tris are device allocations the caller owns; out.built ==
+// false (nothing allocated) means the builder declined (tiny scene, tree too deep) and the SAH
+// builder should run.  Returns a cudaError_t as int (0 = success).
+struct DeviceLBVH {
+  bool built = false;
+  float* nodes = nullptr; // 16 floats per node, device
+  float* tris = nullptr;  // 12 floats per triangle, device
+  uint32_t n_nodes = 0, n_tris = 0, depth = 0;
+  float root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0};
+  float device_ms = 0.f;
+};
+int build_lbvh_device_c(const BuildTri* h_tris, uint32_t n, DeviceLBVH& out);
+
 // Structural check of both trees against the triangle array: returns the number of violations
 // (0 = every triangle is referenced exactly once by each tree, every child box contains its
 // content, every reference is in range).

@@ -90,7 +90,8 @@ void print_help()
               "      --checkpoint arg   Save the progressive state (sums + iteration) to this file\n"
               "      --resume arg       Continue from a saved progressive state up to --spp\n"
               "      --all-meshes       Load every mesh a scene names (the reference loads the first)\n"
-              "      --mesh-cache       Keep a binary copy (<obj>.b200mesh) of every parsed OBJ\n\n");
+              "      --mesh-cache       Keep a binary copy (<obj>.b200mesh) of every parsed OBJ\n"
+              "      --fast-build       Build the BVH on the GPU (LBVH): faster start, slower rays\n\n");
 }
 
 } // namespace
@@ -192,6 +193,8 @@ extern "C" int pt_cli_main(int argc, char** argv)
       resume = v;
     } else if (a == "--all-meshes") {
       setenv("PT_ALL_MESHES", "1", 1);
+    } else if (a == "--fast-build") {
+      setenv("PT_BUILD", "lbvh", 1);
     } else if (a == "--mesh-cache") {
       setenv("PT_MESH_CACHE", "1", 1);
     } else if (a == "--filename" || eq("--filename", v)) {

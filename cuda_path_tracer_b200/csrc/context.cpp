@@ -205,8 +205,23 @@ int pt_scene_create(const pt_scene_desc* desc, int device, pt_scene** out)
   // slower, profiles/README.md); the default is the binary tree alone.
   const char* bvh_env = getenv("PT_BVH");
   const bool wide = bvh_env && atoi(bvh_env) == 8;
+  // PT_BUILD=lbvh (cuda_pt --fast-build): build on the device (lbvh.cu) instead of the host SAH
+  // builder — tens of milliseconds at 10 M triangles, a lower-quality tree
+  const char* build_env = getenv("PT_BUILD");
   FlatBVH bvh;
-  build_bvh(tris, bvh, wide);
+  DeviceLBVH dl;
+  if (build_env && !strcmp(build_env, "lbvh") && !wide) {
+    const int ce = build_lbvh_device_c(tris.data(), (uint32_t)tris.size(), dl);
+    if (ce != 0) return cuda_fail((cudaError_t)ce, "device LBVH build");
+  }
+  if (dl.built) {
+    bvh.n_nodes = dl.n_nodes;
+    bvh.n_tris = dl.n_tris;
+    bvh.depth = dl.depth;
+    for (int a = 0; a < 3; ++a) bvh.root_lo[a] = dl.root_lo[a], bvh.root_hi[a] = dl.root_hi[a];
+  } else {
+    build_bvh(tris, bvh, wide);
+  }
   const double t1 = now_ms();
 
   std::vector<DevMaterial> mats(desc->n_materials);
@@ -234,8 +249,15 @@ int pt_scene_create(const pt_scene_desc* desc, int device, pt_scene** out)
     return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
   };
   cudaError_t e = cudaSuccess;
-  if (e == cudaSuccess) e = upload(bvh.nodes.data(), bvh.nodes.size() * 4, &sc->d_nodes);
-  if (e == cudaSuccess) e = upload(bvh.tris.data(), bvh.tris.size() * 4, &sc->d_tris);
+  if (dl.built) {
+    sc->d_nodes = dl.nodes;
+    sc->d_tris = dl.tris;
+    sc->info.device_bytes += ((size_t)dl.n_nodes * 16 + (size_t)dl.n_tris * 12) * 4;
+    sc->info.device_build = 1;
+  } else {
+    if (e == cudaSuccess) e = upload(bvh.nodes.data(), bvh.nodes.size() * 4, &sc->d_nodes);
+    if (e == cudaSuccess) e = upload(bvh.tris.data(), bvh.tris.size() * 4, &sc->d_tris);
+  }
   if (e == cudaSuccess) e = upload(bvh.nodes8.data(), bvh.nodes8.size() * 4, &sc->d_nodes8);
   if (e == cudaSuccess) e = upload(spheres.data(), spheres.size() * sizeof(DevSphere), &sc->d_spheres);
   if (e == cudaSuccess) e = upload(mats.data(), mats.size() * sizeof(DevMaterial), &sc->d_materials);
@@ -266,6 +288,7 @@ int pt_scene_create(const pt_scene_desc* desc, int device, pt_scene** out)
   sc->info.n_triangles = n_tri;
   sc->info.n_world_triangles = n_world;
   sc->info.n_bvh_nodes = bvh.n_nodes;
+  sc->info.n_bvh_triangles = bvh.n_tris;
   sc->info.bvh_depth = bvh.depth;
   sc->info.n_objects = desc->n_objects;
   sc->info.n_spheres = (uint32_t)spheres.size();
@@ -297,13 +320,16 @@ int pt_host_bvh_build(const pt_scene_desc* desc, int wide, pt_host_bvh** out, pt
   const int rc = bake_triangles(desc, mesh_objects, tris);
   if (rc != PT_OK) return rc;
   auto* h = new pt_host_bvh_impl();
-  build_bvh(tris, h->bvh, wide != 0);
+  // wide: 0 = binary SAH tree, 1 = + compressed 8-wide tree, 2 = LBVH (host restatement of the
+  // device builder; falls back to the SAH builder for scenes it declines)
+  if (wide != 2 || !build_lbvh_host(tris, h->bvh)) build_bvh(tris, h->bvh, wide == 1);
   h->build_ms = now_ms() - t0;
   if (info) {
     *info = pt_scene_info{};
     info->n_triangles = desc->n_indices / 3;
     info->n_world_triangles = tris.size();
     info->n_bvh_nodes = h->bvh.n_nodes;
+    info->n_bvh_triangles = h->bvh.n_tris;
     info->bvh_depth = h->bvh.depth;
     info->n_bvh8_nodes = h->bvh.n_nodes8;
     info->bvh8_depth = h->bvh.depth8;
@@ -346,6 +372,17 @@ int pt_scene_destroy(pt_scene* sc)
   cudaFree(sc->d_spheres);
   cudaFree(sc->d_materials);
   delete sc;
+  return PT_OK;
+}
+
+int pt_scene_copy_bvh(const pt_scene* sc, float* nodes_out, float* tris_out)
+{
+  if (!sc) return fail(PT_ERR_INVALID, "pt_scene_copy_bvh: null scene");
+  PT_CUDA(cudaSetDevice(sc->device));
+  if (nodes_out && sc->dev.n_nodes)
+    PT_CUDA(cudaMemcpy(nodes_out, sc->d_nodes, (size_t)sc->dev.n_nodes * 64, cudaMemcpyDeviceToHost));
+  if (tris_out && sc->dev.n_tris)
+    PT_CUDA(cudaMemcpy(tris_out, sc->d_tris, (size_t)sc->dev.n_tris * 48, cudaMemcpyDeviceToHost));
   return PT_OK;
 }
 

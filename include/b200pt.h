@@ -191,7 +191,8 @@ typedef struct pt_scene_info {
   uint64_t device_bytes;
   uint64_t n_bvh8_nodes; /* compressed 8-wide tree (0 = not built) */
   uint32_t bvh8_depth;
-  uint32_t reserved;
+  uint32_t device_build; /* 1 = the tree was built on the device (PT_BUILD=lbvh) */
+  uint64_t n_bvh_triangles; /* entries of the leaf-ordered triangle array (incl. a null triangle) */
 } pt_scene_info;
 
 /* Result of loading a reference scene file (assets/json_parser.cpp:174-224). */
@@ -213,6 +214,10 @@ PT_API int pt_version(void);
 PT_API int pt_scene_create(const pt_scene_desc* desc, int device, pt_scene** out);
 PT_API int pt_scene_destroy(pt_scene* scene);
 PT_API int pt_scene_get_info(const pt_scene* scene, pt_scene_info* info);
+/* Copies the device-resident binary tree back: n_bvh_nodes x 16 floats and n_bvh_triangles x 12
+ * floats (either pointer may be NULL).  Test hook: a tree built on the device (PT_BUILD=lbvh)
+ * is compared node for node with the host restatement of the same algorithm. */
+PT_API int pt_scene_copy_bvh(const pt_scene* scene, float* nodes_out, float* tris_out);
 
 /* Host-only half of pt_scene_create (no CUDA call): bake the mesh instances and build both
  * trees; pt_host_bvh_validate walks them and counts structural violations (a triangle that is

@@ -187,3 +187,28 @@ def test_wide_tree_with_device_arithmetic_matches_oracle(name):
         if prim != ref["prim"][i]:      # ties between coincident/adjacent triangles only
             assert abs(t - ref["t"][i]) <= 1e-6 * abs(ref["t"][i])
     assert hits > n // 4
+
+
+@pytest.mark.parametrize("name", ["bunny_320", "bunny_5k", "bunny_20k", "terrain_5k", "flat_quads", "three_coincident"])
+def test_lbvh_restatement_is_structurally_valid(name):
+    """The host restatement of the device LBVH builder (lbvh.h shared with lbvh.cu): every triangle
+    referenced once, every stored child box contains its content, depth fits the traversal stack.
+    Scenes it declines (<= 4 triangles) fall back to the SAH builder."""
+    hb = HostBVH(_mesh_scene(MESHES[name]()), lbvh=True)
+    assert hb.violations() == 0
+    assert 1 <= int(hb.info.bvh_depth) <= 61
+    nodes, _, tris = hb.arrays()
+    assert nodes.shape[0] == int(hb.info.n_bvh_nodes) and tris.shape[0] == int(hb.info.n_bvh_triangles)
+
+
+def test_lbvh_orders_triangles_along_the_morton_curve():
+    mesh = MESHES["terrain_5k"]()
+    hb = HostBVH(_mesh_scene(mesh), lbvh=True)
+    _, _, tris = hb.arrays()
+    prim = tris[:, 3].copy().view(np.uint32)
+    assert sorted(prim.tolist()) == list(range(mesh.triangle_count))       # a permutation
+    cen = tris[:, 0:3] + (tris[:, 4:7] + tris[:, 8:11]) / 3.0
+    step = np.linalg.norm(np.diff(cen, axis=0), axis=1)
+    rng = np.random.default_rng(0)
+    shuffled = np.linalg.norm(np.diff(cen[rng.permutation(len(cen))], axis=0), axis=1)
+    assert step.mean() < 0.2 * shuffled.mean()                              # neighbours stay close
