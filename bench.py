@@ -301,6 +301,8 @@ def main():
             "config": {"workload": args.workload, **{k: v for k, v in wl.items() if k != "kind"},
                        "triangles_world": int(scene.info.n_world_triangles),
                        "bvh_nodes": int(scene.info.n_bvh_nodes),
+                       "scene_build_ms": round(float(scene.info.build_ms), 2),
+                       "scene_upload_ms": round(float(scene.info.upload_ms), 2),
                        "l2": "no flush: wavefront state (ray/hit/throughput planes, %d MB) exceeds the 126 MB L2"
                              % (tracer_state_mb(W, H, tracer)),
                        "parallelism": f"sample-range x{world}" if multi else "single"},

@@ -75,6 +75,19 @@ struct DeviceLBVH {
 };
 int build_lbvh_device_c(const BuildTri* h_tris, uint32_t n, DeviceLBVH& out);
 
+// Same, from the raw mesh: every mesh instance is baked to world space ON THE DEVICE (bit-identical
+// to the host bake: same operation order, no fused multiply-adds), so neither the host bake nor
+// the 48-byte-per-triangle upload happens.
+struct MeshInstance {
+  float m[16];                     // object -> world, column-major
+  uint64_t first_tri, n_tri;       // triangles of its mesh in the index buffer
+  uint64_t out_at;                 // first world triangle it produces
+  uint32_t object, material;
+};
+int build_lbvh_device_mesh_c(const float* h_positions, uint64_t n_vertices, const uint32_t* h_indices,
+                             uint64_t n_indices, const MeshInstance* inst, uint32_t n_inst, uint64_t n_world,
+                             DeviceLBVH& out);
+
 // Structural check of both trees against the triangle array: returns the number of violations
 // (0 = every triangle is referenced exactly once by each tree, every child box contains its
 // content, every reference is in range).

@@ -193,26 +193,41 @@ int pt_scene_create(const pt_scene_desc* desc, int device, pt_scene** out)
     }
   }
 
-  std::vector<BuildTri> tris;
-  {
-    const int rc = bake_triangles(desc, mesh_objects, tris);
-    if (rc != PT_OK) return rc;
-  }
-  const uint64_t n_world = tris.size();
-
   // PT_BVH=8 additionally derives the compressed 8-wide tree and traverses it (opt-in: on B200
   // it trades the binary walk's L1 wavefront bound for an ALU-pipe bound and measures 10-30 %
   // slower, profiles/README.md); the default is the binary tree alone.
   const char* bvh_env = getenv("PT_BVH");
   const bool wide = bvh_env && atoi(bvh_env) == 8;
-  // PT_BUILD=lbvh (cuda_pt --fast-build): build on the device (lbvh.cu) instead of the host SAH
-  // builder — tens of milliseconds at 10 M triangles, a lower-quality tree
+  // PT_BUILD=lbvh (cuda_pt --fast-build): bake the instances and build the tree on the device
+  // (lbvh.cu) instead of the host bake + SAH builder — tens of milliseconds at 10 M triangles, a
+  // lower-quality tree.  The device builder may decline (tiny scene, tree deeper than the
+  // traversal stack): the host path below then runs as usual.
   const char* build_env = getenv("PT_BUILD");
   FlatBVH bvh;
   DeviceLBVH dl;
-  if (build_env && !strcmp(build_env, "lbvh") && !wide) {
-    const int ce = build_lbvh_device_c(tris.data(), (uint32_t)tris.size(), dl);
+  uint64_t n_world = 0;
+  if (build_env && !strcmp(build_env, "lbvh") && !wide && !mesh_objects.empty()) {
+    std::vector<MeshInstance> inst(mesh_objects.size());
+    for (size_t k = 0; k < mesh_objects.size(); ++k) {
+      const pt_object& ob = desc->objects[mesh_objects[k]];
+      MeshInstance& mi = inst[k];
+      std::memcpy(mi.m, ob.m, sizeof(mi.m));
+      if (!mesh_range(desc, ob, mi.first_tri, mi.n_tri))
+        return fail(PT_ERR_INVALID, "mesh object refers to a mesh that does not exist");
+      mi.out_at = n_world;
+      mi.object = mesh_objects[k];
+      mi.material = ob.material;
+      n_world += mi.n_tri;
+    }
+    const int ce = build_lbvh_device_mesh_c(desc->positions, desc->n_vertices, desc->indices, desc->n_indices,
+                                            inst.data(), (uint32_t)inst.size(), n_world, dl);
     if (ce != 0) return cuda_fail((cudaError_t)ce, "device LBVH build");
+  }
+  std::vector<BuildTri> tris;
+  if (!dl.built) {
+    const int rc = bake_triangles(desc, mesh_objects, tris);
+    if (rc != PT_OK) return rc;
+    n_world = tris.size();
   }
   if (dl.built) {
     bvh.n_nodes = dl.n_nodes;

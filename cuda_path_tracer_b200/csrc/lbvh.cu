@@ -189,6 +189,37 @@ tris_kernel(const BuildTri* __restrict__ tris, int n, const uint32_t* __restrict
   dst[2] = make_float4(t.v2[0] - t.v0[0], t.v2[1] - t.v0[1], t.v2[2] - t.v0[2], __uint_as_float(t.material));
 }
 
+
+// transform_point (transform.hpp:37-42) with the host's operation order and NO fused
+// multiply-adds, so that a scene baked here equals the host-baked one bit for bit
+__device__ __forceinline__ void xform_point_exact(const float* m, const float* p, float* out)
+{
+  float v[4];
+  for (int r = 0; r < 4; ++r)
+    v[r] = __fadd_rn(__fadd_rn(__fmul_rn(m[0 * 4 + r], p[0]), __fmul_rn(m[1 * 4 + r], p[1])),
+                     __fadd_rn(__fmul_rn(m[2 * 4 + r], p[2]), __fmul_rn(m[3 * 4 + r], 1.0f)));
+  out[0] = __fdiv_rn(v[0], v[3]);
+  out[1] = __fdiv_rn(v[1], v[3]);
+  out[2] = __fdiv_rn(v[2], v[3]);
+}
+
+__global__ void __launch_bounds__(LB_THREADS)
+bake_kernel(const float* __restrict__ pos, const uint32_t* __restrict__ idx, const MeshInstance inst,
+            BuildTri* __restrict__ out)
+{
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= inst.n_tri) return;
+  const uint64_t g = inst.first_tri + t;
+  BuildTri bt;
+  xform_point_exact(inst.m, pos + 3 * (size_t)idx[3 * g + 0], bt.v0);
+  xform_point_exact(inst.m, pos + 3 * (size_t)idx[3 * g + 1], bt.v1);
+  xform_point_exact(inst.m, pos + 3 * (size_t)idx[3 * g + 2], bt.v2);
+  bt.prim = (uint32_t)g;
+  bt.object = inst.object;
+  bt.material = inst.material;
+  out[inst.out_at + t] = bt;
+}
+
 struct Scratch {
   std::vector<void*> ptrs;
   ~Scratch()
@@ -212,10 +243,21 @@ struct Scratch {
     if (e__ != cudaSuccess) return e__;                                                           \
   } while (0)
 
-// h_tris: host array of n world-space triangles.  On success with out.built == true, out.nodes /
-// out.tris are device allocations the caller owns (cudaFree).  out.built == false (and no
-// allocation) when the scene is too small or the tree would be too deep: use the SAH builder.
-static cudaError_t build_lbvh_device(const BuildTri* h_tris, uint32_t n_u, DeviceLBVH& out)
+// Source of the world-space triangles: a host array that is uploaded, or the raw mesh + instance
+// table, baked on the device.  On success with out.built == true, out.nodes / out.tris are device
+// allocations the caller owns (cudaFree).  out.built == false (and no allocation) when the scene
+// is too small or the tree would be too deep: use the SAH builder.
+struct TriSource {
+  const BuildTri* h_tris = nullptr;
+  const float* h_positions = nullptr;
+  uint64_t n_vertices = 0;
+  const uint32_t* h_indices = nullptr;
+  uint64_t n_indices = 0;
+  const MeshInstance* inst = nullptr;
+  uint32_t n_inst = 0;
+};
+
+static cudaError_t build_lbvh_device(const TriSource& src, uint32_t n_u, DeviceLBVH& out)
 {
   out = DeviceLBVH{};
   const int n = (int)n_u;
@@ -246,7 +288,21 @@ static cudaError_t build_lbvh_device(const BuildTri* h_tris, uint32_t n_u, Devic
   LB_TRY(sc.alloc(&real, (size_t)n));
   LB_TRY(sc.alloc(&index, (size_t)n));
   LB_TRY(sc.alloc(&flag, (size_t)n));
-  LB_TRY(cudaMemcpy(d_tris, h_tris, (size_t)n * sizeof(BuildTri), cudaMemcpyHostToDevice));
+  if (src.h_tris) {
+    LB_TRY(cudaMemcpy(d_tris, src.h_tris, (size_t)n * sizeof(BuildTri), cudaMemcpyHostToDevice));
+  } else {
+    float* d_pos;
+    uint32_t* d_idx;
+    LB_TRY(sc.alloc(&d_pos, (size_t)src.n_vertices * 3));
+    LB_TRY(sc.alloc(&d_idx, (size_t)src.n_indices));
+    LB_TRY(cudaMemcpy(d_pos, src.h_positions, (size_t)src.n_vertices * 12, cudaMemcpyHostToDevice));
+    LB_TRY(cudaMemcpy(d_idx, src.h_indices, (size_t)src.n_indices * 4, cudaMemcpyHostToDevice));
+    for (uint32_t k = 0; k < src.n_inst; ++k) {
+      const MeshInstance& mi = src.inst[k];
+      if (mi.n_tri == 0) continue;
+      bake_kernel<<<(unsigned)((mi.n_tri + LB_THREADS - 1) / LB_THREADS), LB_THREADS>>>(d_pos, d_idx, mi, d_tris);
+    }
+  }
   LB_TRY(cudaEventRecord(e0));
   {
     // ordered-int keys (f2key) of +FLT_MAX and -FLT_MAX: identities of the min / max reductions
@@ -321,7 +377,25 @@ static cudaError_t build_lbvh_device(const BuildTri* h_tris, uint32_t n_u, Devic
 
 int build_lbvh_device_c(const BuildTri* h_tris, uint32_t n, DeviceLBVH& out)
 {
-  return (int)build_lbvh_device(h_tris, n, out);
+  TriSource src;
+  src.h_tris = h_tris;
+  return (int)build_lbvh_device(src, n, out);
+}
+
+int build_lbvh_device_mesh_c(const float* h_positions, uint64_t n_vertices, const uint32_t* h_indices,
+                             uint64_t n_indices, const MeshInstance* inst, uint32_t n_inst, uint64_t n_world,
+                             DeviceLBVH& out)
+{
+  out = DeviceLBVH{};
+  if (n_world >= (1ull << 28)) return 0;
+  TriSource src;
+  src.h_positions = h_positions;
+  src.n_vertices = n_vertices;
+  src.h_indices = h_indices;
+  src.n_indices = n_indices;
+  src.inst = inst;
+  src.n_inst = n_inst;
+  return (int)build_lbvh_device(src, (uint32_t)n_world, out);
 }
 
 } // namespace pt
