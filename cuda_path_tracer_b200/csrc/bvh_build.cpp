@@ -20,6 +20,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 namespace pt {
 namespace {
@@ -146,6 +149,61 @@ struct Builder {
 
   static void bin_range(const Prim* p, uint32_t n, const Box& cb, const float* scale, BinSet& out)
   {
+#if defined(__SSE2__)
+    // four-lane version: one min/max pair per box instead of six scalar ones.  Lane 3 is a
+    // don't-care (it carries hi[0] / the id bits and is masked before any arithmetic).
+    struct VBin {
+      __m128 blo, bhi, clo, chi;
+    };
+    VBin vb[3][kBins];
+    uint32_t cnt[3][kBins];
+    const __m128 big = _mm_set1_ps(FLT_MAX), nbig = _mm_set1_ps(-FLT_MAX);
+    for (int a = 0; a < 3; ++a)
+      for (int k = 0; k < kBins; ++k) {
+        vb[a][k].blo = vb[a][k].clo = big;
+        vb[a][k].bhi = vb[a][k].chi = nbig;
+        cnt[a][k] = 0;
+      }
+    const __m128 mask3 = _mm_castsi128_ps(_mm_set_epi32(0, -1, -1, -1));
+    const __m128 cblo = _mm_set_ps(0.f, cb.lo[2], cb.lo[1], cb.lo[0]);
+    const __m128 sc4 = _mm_set_ps(0.f, scale[2], scale[1], scale[0]);
+    const __m128 half = _mm_set1_ps(0.5f), top = _mm_set1_ps((float)(kBins - 1));
+    for (uint32_t i = 0; i < n; ++i) {
+      const __m128 lo = _mm_and_ps(_mm_loadu_ps(p[i].b.lo), mask3);
+      const __m128 hi = _mm_and_ps(_mm_loadu_ps(p[i].b.hi), mask3);
+      const __m128 c = _mm_mul_ps(half, _mm_add_ps(lo, hi));
+      __m128 f = _mm_mul_ps(_mm_sub_ps(c, cblo), sc4);
+      f = _mm_min_ps(_mm_max_ps(f, _mm_setzero_ps()), top);
+      alignas(16) int bi[4];
+      _mm_store_si128(reinterpret_cast<__m128i*>(bi), _mm_cvttps_epi32(f));
+      for (int a = 0; a < 3; ++a) {
+        if (scale[a] == 0.f) continue;
+        VBin& v = vb[a][bi[a]];
+        v.blo = _mm_min_ps(v.blo, lo);
+        v.bhi = _mm_max_ps(v.bhi, hi);
+        v.clo = _mm_min_ps(v.clo, c);
+        v.chi = _mm_max_ps(v.chi, c);
+        cnt[a][bi[a]]++;
+      }
+    }
+    for (int a = 0; a < 3; ++a)
+      for (int k = 0; k < kBins; ++k) {
+        if (cnt[a][k] == 0) continue;
+        alignas(16) float t[4][4];
+        _mm_store_ps(t[0], vb[a][k].blo);
+        _mm_store_ps(t[1], vb[a][k].bhi);
+        _mm_store_ps(t[2], vb[a][k].clo);
+        _mm_store_ps(t[3], vb[a][k].chi);
+        Bin& bn = out.bin[a][k];
+        for (int x = 0; x < 3; ++x) {
+          bn.box.lo[x] = std::min(bn.box.lo[x], t[0][x]);
+          bn.box.hi[x] = std::max(bn.box.hi[x], t[1][x]);
+          bn.cbox.lo[x] = std::min(bn.cbox.lo[x], t[2][x]);
+          bn.cbox.hi[x] = std::max(bn.cbox.hi[x], t[3][x]);
+        }
+        bn.count += cnt[a][k];
+      }
+#else
     for (uint32_t i = 0; i < n; ++i) {
       const Prim& q = p[i];
       float c[3] = {q.c(0), q.c(1), q.c(2)};
@@ -159,6 +217,7 @@ struct Builder {
         bn.count++;
       }
     }
+#endif
   }
 
   // bounds of a primitive range (median-split fallback only)
