@@ -75,6 +75,16 @@ class HostBVH:
                 view(b, int(i.n_bvh8_nodes), 20, C.c_uint32, np.uint32),
                 view(t, n_tris, 12, C.c_float, np.float32))
 
+    def trace_stats(self, rays8: np.ndarray, wide: bool = False) -> dict:
+        """Host walk in the device kernels' order: what the rays cost in this tree (analysis tool)."""
+        rays = np.ascontiguousarray(rays8, dtype=np.float32).reshape(-1, 8)
+        out = np.zeros(5, dtype=np.uint64)
+        check(load_library().pt_host_bvh_trace_stats(self._h, rays.ctypes.data, rays.shape[0], 1 if wide else 0,
+                                                     out.ctypes.data))
+        n = max(1, rays.shape[0])
+        return {"rays": rays.shape[0], "inner_per_ray": float(out[0]) / n, "leaves_per_ray": float(out[1]) / n,
+                "tri_tests_per_ray": float(out[2]) / n, "hit_fraction": float(out[3]) / n, "max_stack": int(out[4])}
+
     def close(self):
         if self._h:
             load_library().pt_host_bvh_free(self._h)

@@ -954,4 +954,163 @@ uint64_t validate_bvh(const FlatBVH& bvh)
   return v.bad;
 }
 
+
+// ------------------------------------------------------------- traversal statistics
+// Host walk of either tree in the device kernels' visiting order (binary: nearer child first,
+// farther child stacked; wide: octant-ordered node groups), counting what a ray costs.  A tool for
+// choosing between tree layouts without GPU time: it does not compute images and nothing in the
+// product path calls it.
+namespace {
+inline float safe_inv_h(float x)
+{
+  const float e = 8.271806125530277e-25f;
+  return 1.0f / (std::fabs(x) > e ? x : std::copysign(e, x));
+}
+struct RayH {
+  float o[3], d[3], id[3], tmin, tbest;
+};
+inline bool tri_hit(const float* t, RayH& r)
+{
+  const float* v0 = t;
+  const float* e1 = t + 4;
+  const float* e2 = t + 8;
+  const float hx = r.d[1] * e2[2] - e2[1] * r.d[2], hy = r.d[2] * e2[0] - e2[2] * r.d[0],
+              hz = r.d[0] * e2[1] - e2[0] * r.d[1];
+  const float a = e1[0] * hx + e1[1] * hy + e1[2] * hz;
+  if (a > -1e-7f && a < 1e-7f) return false;
+  const float f = 1.0f / a;
+  const float sx = r.o[0] - v0[0], sy = r.o[1] - v0[1], sz = r.o[2] - v0[2];
+  const float u = f * (sx * hx + sy * hy + sz * hz);
+  if (u < 0.f || u > 1.f) return false;
+  const float qx = sy * e1[2] - e1[1] * sz, qy = sz * e1[0] - e1[2] * sx, qz = sx * e1[1] - e1[0] * sy;
+  const float v = f * (r.d[0] * qx + r.d[1] * qy + r.d[2] * qz);
+  if (v < 0.f || u + v > 1.f) return false;
+  const float tt = f * (e2[0] * qx + e2[1] * qy + e2[2] * qz);
+  if (tt < r.tmin || tt > r.tbest) return false;
+  r.tbest = tt;
+  return true;
+}
+inline bool slab(const float lo[3], const float hi[3], const RayH& r, float& tnear)
+{
+  float t0 = r.tmin, t1 = r.tbest;
+  for (int a = 0; a < 3; ++a) {
+    const float x0 = (lo[a] - r.o[a]) * r.id[a], x1 = (hi[a] - r.o[a]) * r.id[a];
+    t0 = std::max(t0, std::min(x0, x1));
+    t1 = std::min(t1, std::max(x0, x1));
+  }
+  tnear = t0;
+  return t1 * 1.0000004f >= t0;
+}
+} // namespace
+
+void trace_stats(const FlatBVH& b, const float* rays8, uint64_t n_rays, int wide, uint64_t out[5])
+{
+  uint64_t inner = 0, leaves = 0, tests = 0, hits = 0, max_stack = 0;
+  if (b.n_tris != 0) {
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : inner, leaves, tests, hits) reduction(max : max_stack)
+    for (long long i = 0; i < (long long)n_rays; ++i) {
+      RayH r;
+      const float* q = rays8 + 8 * i;
+      for (int a = 0; a < 3; ++a) r.o[a] = q[a], r.d[a] = q[4 + a], r.id[a] = safe_inv_h(q[4 + a]);
+      r.tmin = q[3];
+      r.tbest = q[7];
+      bool any = false;
+      if (!wide) {
+        int32_t stack[128];
+        int sp = 0;
+        int32_t node = 0;
+        for (;;) {
+          if (node >= 0) {
+            ++inner;
+            const float* nd = &b.nodes[(size_t)node * 16];
+            const float l0[3] = {nd[0], nd[2], nd[8]}, h0[3] = {nd[1], nd[3], nd[9]};
+            const float l1[3] = {nd[4], nd[6], nd[10]}, h1[3] = {nd[5], nd[7], nd[11]};
+            float n0, n1;
+            const bool t0 = slab(l0, h0, r, n0), t1 = slab(l1, h1, r, n1);
+            int32_t c0, c1;
+            std::memcpy(&c0, &nd[12], 4);
+            std::memcpy(&c1, &nd[13], 4);
+            if (!t0 && !t1) {
+              if (sp == 0) break;
+              node = stack[--sp];
+            } else {
+              const bool swap = t1 && (!t0 || n1 < n0);
+              node = swap ? c1 : c0;
+              if (t0 && t1 && sp < 128) stack[sp++] = swap ? c0 : c1;
+              max_stack = std::max<uint64_t>(max_stack, (uint64_t)sp);
+            }
+          } else {
+            ++leaves;
+            const uint32_t code = (uint32_t)~node, first = code >> 3, count = (code & 7u) + 1u;
+            for (uint32_t k = 0; k < count; ++k) {
+              ++tests;
+              if (tri_hit(&b.tris[(size_t)(first + k) * 12], r)) any = true;
+            }
+            if (sp == 0) break;
+            node = stack[--sp];
+          }
+        }
+      } else if (b.n_nodes8 != 0) {
+        struct G {
+          uint32_t base, bits;
+        } stack[64];
+        int sp = 0;
+        const uint32_t octm = (r.id[0] < 0.f ? 0u : 1u) | (r.id[1] < 0.f ? 0u : 2u) | (r.id[2] < 0.f ? 0u : 4u);
+        G ng{0u, 0x80000000u};
+        for (;;) {
+          // pop the highest-priority child of the current node group
+          const int bit = 31 - __builtin_clz(ng.bits);
+          const uint32_t rest = ng.bits & ~(1u << bit);
+          const uint32_t slot = (uint32_t)(bit - 24) ^ octm;
+          const uint32_t node = ng.base + (uint32_t)__builtin_popcount(ng.bits & 0xffu & ((1u << slot) - 1u));
+          const G rest_g{ng.base, rest};
+          ++inner;
+          const uint32_t* w = &b.nodes8[(size_t)node * 20];
+          float p[3];
+          std::memcpy(p, w, 12);
+          float scale[3];
+          for (int a = 0; a < 3; ++a) scale[a] = std::ldexp(1.0f, (int)((w[3] >> (8 * a)) & 0xffu) + 8 - 127);
+          const uint32_t imask = w[3] >> 24;
+          const uint8_t* meta = reinterpret_cast<const uint8_t*>(w + 6);
+          const uint8_t* qq = reinterpret_cast<const uint8_t*>(w + 8);
+          uint32_t hm = 0;
+          for (int s = 0; s < 8; ++s) {
+            if (meta[s] == 0) continue;
+            float lo[3], hi[3], tn;
+            for (int a = 0; a < 3; ++a) {
+              lo[a] = p[a] + qq[8 * a + s] * scale[a];
+              hi[a] = p[a] + qq[8 * (3 + a) + s] * scale[a];
+            }
+            if (!slab(lo, hi, r, tn)) continue;
+            uint32_t bi = meta[s] & 31u;
+            if (bi >= 24u) bi ^= octm;
+            hm |= (uint32_t)(meta[s] >> 5) << bi;
+          }
+          uint32_t tri_bits = hm & 0x00ffffffu;
+          if (tri_bits) ++leaves;
+          while (tri_bits) {
+            const int k = __builtin_ctz(tri_bits);
+            tri_bits &= tri_bits - 1;
+            ++tests;
+            if (tri_hit(&b.tris[(size_t)(w[5] + (uint32_t)k) * 12], r)) any = true;
+          }
+          const G ng2{w[4], (hm & 0xff000000u) | imask};
+          if (ng2.bits & 0xff000000u) {
+            if ((rest & 0xff000000u) && sp < 64) stack[sp++] = rest_g;
+            ng = ng2;
+          } else if (rest & 0xff000000u) {
+            ng = rest_g;
+          } else {
+            if (sp == 0) break;
+            ng = stack[--sp];
+          }
+          max_stack = std::max<uint64_t>(max_stack, (uint64_t)sp);
+        }
+      }
+      if (any) ++hits;
+    }
+  }
+  out[0] = inner, out[1] = leaves, out[2] = tests, out[3] = hits, out[4] = max_stack;
+}
+
 } // namespace pt

@@ -93,4 +93,10 @@ int build_lbvh_device_mesh_c(const float* h_positions, uint64_t n_vertices, cons
 // content, every reference is in range).
 uint64_t validate_bvh(const FlatBVH& bvh);
 
+
+// Host walk of a tree in the device kernels' visiting order; out = {inner-node visits, leaf visits,
+// triangle tests, rays that hit, deepest stack}.  wide = 0: binary tree, 1: compressed 8-wide tree.
+// Analysis tool only (tree-layout decisions without GPU time).
+void trace_stats(const FlatBVH& bvh, const float* rays8, uint64_t n_rays, int wide, uint64_t out[5]);
+
 } // namespace pt

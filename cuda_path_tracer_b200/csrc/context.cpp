@@ -371,6 +371,13 @@ int pt_host_bvh_arrays(const pt_host_bvh* hb, const float** nodes, const uint32_
   return PT_OK;
 }
 
+int pt_host_bvh_trace_stats(const pt_host_bvh* hb, const float* rays8, uint64_t n_rays, int wide, uint64_t* out5)
+{
+  if (!hb || !rays8 || !out5) return fail(PT_ERR_INVALID, "pt_host_bvh_trace_stats: null argument");
+  trace_stats(reinterpret_cast<const pt_host_bvh_impl*>(hb)->bvh, rays8, n_rays, wide, out5);
+  return PT_OK;
+}
+
 int pt_host_bvh_free(pt_host_bvh* hb)
 {
   delete reinterpret_cast<pt_host_bvh_impl*>(hb);

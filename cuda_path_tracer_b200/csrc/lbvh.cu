@@ -143,7 +143,8 @@ fit_kernel(int n, const int* __restrict__ first, const int* __restrict__ last, c
 }
 
 __global__ void __launch_bounds__(LB_THREADS)
-real_kernel(int n, const int* __restrict__ first, const int* __restrict__ last, uint32_t* __restrict__ real)
+real_kernel(int n, const int* __restrict__ first, const int* __restrict__ last, uint32_t* __restrict__ real,
+            int kLeafMax)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1) return;
@@ -153,7 +154,7 @@ real_kernel(int n, const int* __restrict__ first, const int* __restrict__ last, 
 __global__ void __launch_bounds__(LB_THREADS)
 emit_kernel(int n, const int* __restrict__ first, const int* __restrict__ last, const int* __restrict__ split,
             const uint32_t* __restrict__ order, const Box6* __restrict__ pbox, const Box6* __restrict__ nbox,
-            const uint32_t* __restrict__ index, float* __restrict__ nodes)
+            const uint32_t* __restrict__ index, float* __restrict__ nodes, int kLeafMax)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1) return;
@@ -261,7 +262,8 @@ static cudaError_t build_lbvh_device(const TriSource& src, uint32_t n_u, DeviceL
 {
   out = DeviceLBVH{};
   const int n = (int)n_u;
-  if (n <= kLeafMax || n_u >= (1u << 28)) return cudaSuccess;
+  const int kLeafMax = leaf_max_setting();
+  if (n <= 4 || n_u >= (1u << 28)) return cudaSuccess;
   cudaEvent_t e0, e1;
   LB_TRY(cudaEventCreate(&e0));
   LB_TRY(cudaEventCreate(&e1));
@@ -322,7 +324,7 @@ static cudaError_t build_lbvh_device(const TriSource& src, uint32_t n_u, DeviceL
   }
   hierarchy_kernel<<<grid, LB_THREADS>>>(codes2, n, first, last, split, parent);
   fit_kernel<<<grid, LB_THREADS>>>(n, first, last, split, parent, order2, pbox, nbox, depth, flag);
-  real_kernel<<<grid, LB_THREADS>>>(n, first, last, real);
+  real_kernel<<<grid, LB_THREADS>>>(n, first, last, real, kLeafMax);
   {
     size_t tmp_bytes = 0;
     LB_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, real, index, n - 1));
@@ -346,7 +348,7 @@ static cudaError_t build_lbvh_device(const TriSource& src, uint32_t n_u, DeviceL
     cudaFree(nodes);
     return e;
   }
-  emit_kernel<<<grid, LB_THREADS>>>(n, first, last, split, order2, pbox, nbox, index, nodes);
+  emit_kernel<<<grid, LB_THREADS>>>(n, first, last, split, order2, pbox, nbox, index, nodes, kLeafMax);
   tris_kernel<<<grid, LB_THREADS>>>(d_tris, n, order2, tris_out);
   e = cudaEventRecord(e1);
   if (e == cudaSuccess) e = cudaEventSynchronize(e1);

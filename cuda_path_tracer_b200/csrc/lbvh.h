@@ -13,6 +13,7 @@
 //   - the other internal nodes keep their Karras order, compacted by an exclusive scan.
 #pragma once
 #include <stdint.h>
+#include <stdlib.h>
 
 #ifdef __CUDACC__
 #define LB_HD __host__ __device__ __forceinline__
@@ -23,7 +24,17 @@
 namespace pt {
 namespace lbvh {
 
-constexpr int kLeafMax = 4;
+// Largest range that becomes a leaf (PT_LBVH_LEAF overrides, 1..4).  The instruction-cost model
+// (71 per inner visit + 119 per triangle test, scripts/tree_stats.py) prefers 2, the measured ray
+// rate does not care (bunny_1m 4 599 vs 4 640, terrain 1 432 vs 1 447 Mrays/s for 2 vs 4) and 4
+// keeps the node array 40 % smaller.
+constexpr int kLeafMaxDefault = 4;
+inline int leaf_max_setting()
+{
+  const char* v = getenv("PT_LBVH_LEAF");
+  const int k = v ? atoi(v) : kLeafMaxDefault;
+  return k < 1 ? 1 : (k > 4 ? 4 : k);
+}
 
 LB_HD int clz32(uint32_t x)
 {

@@ -26,7 +26,8 @@ bool build_lbvh_host(const std::vector<BuildTri>& tris, FlatBVH& out)
 {
   out = FlatBVH{};
   const int n = (int)tris.size();
-  if (n <= kLeafMax) return false; // tiny scenes stay with the SAH builder (root-leaf form)
+  const int kLeafMax = leaf_max_setting();
+  if (n <= 4) return false; // tiny scenes stay with the SAH builder (root-leaf form)
 
   // primitive boxes, centroid bounds
   std::vector<Box6> pbox(n);

@@ -229,6 +229,12 @@ PT_API int pt_host_bvh_build(const pt_scene_desc* desc, int wide, pt_host_bvh** 
 PT_API int pt_host_bvh_validate(const pt_host_bvh* bvh, uint64_t* violations);
 PT_API int pt_host_bvh_arrays(const pt_host_bvh* bvh, const float** nodes, const uint32_t** nodes8,
                               const float** tris);
+/* Analysis tool: walks the host-built tree for n rays {o, t_min, d, t_max} in the device kernels'
+ * visiting order and returns {inner-node visits, leaf visits, triangle tests, rays that hit,
+ * deepest stack} in out5.  wide = 0: binary tree, 1: compressed 8-wide tree.  No image is
+ * computed; the product path never calls it. */
+PT_API int pt_host_bvh_trace_stats(const pt_host_bvh* bvh, const float* rays8, uint64_t n_rays, int wide,
+                                   uint64_t* out5);
 PT_API int pt_host_bvh_free(pt_host_bvh* bvh);
 
 /* replaces read_scene/scene_from_json/load_obj (assets/scene_parser.cpp:6-22,
