@@ -75,11 +75,13 @@ class HostBVH:
                 view(b, int(i.n_bvh8_nodes), 20, C.c_uint32, np.uint32),
                 view(t, n_tris, 12, C.c_float, np.float32))
 
-    def trace_stats(self, rays8: np.ndarray, wide: bool = False) -> dict:
-        """Host walk in the device kernels' order: what the rays cost in this tree (analysis tool)."""
+    def trace_stats(self, rays8: np.ndarray, wide=False) -> dict:
+        """Host walk in the device kernels' order: what the rays cost in this tree (analysis tool).
+        wide: False/0 binary tree, True/1 compressed 8-wide tree, 2 a virtual 4-wide tree (every
+        other level of the binary tree collapsed)."""
         rays = np.ascontiguousarray(rays8, dtype=np.float32).reshape(-1, 8)
         out = np.zeros(5, dtype=np.uint64)
-        check(load_library().pt_host_bvh_trace_stats(self._h, rays.ctypes.data, rays.shape[0], 1 if wide else 0,
+        check(load_library().pt_host_bvh_trace_stats(self._h, rays.ctypes.data, rays.shape[0], int(wide),
                                                      out.ctypes.data))
         n = max(1, rays.shape[0])
         return {"rays": rays.shape[0], "inner_per_ray": float(out[0]) / n, "leaves_per_ray": float(out[1]) / n,

@@ -1050,6 +1050,63 @@ void trace_stats(const FlatBVH& b, const float* rays8, uint64_t n_rays, int wide
             node = stack[--sp];
           }
         }
+      } else if (wide == 2) {
+        // virtual 4-wide tree: a node = a binary node fused with its inner children (every other
+        // level collapsed); children tested together, visited nearest first
+        int32_t stack[256];
+        int sp = 0;
+        int32_t node = 0;
+        for (;;) {
+          if (node >= 0) {
+            ++inner;
+            int32_t ch[4];
+            float lo[4][3], hi[4][3];
+            int nc = 0;
+            const float* nd = &b.nodes[(size_t)node * 16];
+            for (int c = 0; c < 2; ++c) {
+              int32_t ref;
+              std::memcpy(&ref, &nd[12 + c], 4);
+              if (ref >= 0) { // inner child: take its two children instead
+                const float* gd = &b.nodes[(size_t)ref * 16];
+                for (int g = 0; g < 2; ++g) {
+                  std::memcpy(&ch[nc], &gd[12 + g], 4);
+                  const int o = g * 4, z = 8 + g * 2;
+                  lo[nc][0] = gd[o], hi[nc][0] = gd[o + 1], lo[nc][1] = gd[o + 2], hi[nc][1] = gd[o + 3];
+                  lo[nc][2] = gd[z], hi[nc][2] = gd[z + 1];
+                  ++nc;
+                }
+              } else {
+                ch[nc] = ref;
+                const int o = c * 4, z = 8 + c * 2;
+                lo[nc][0] = nd[o], hi[nc][0] = nd[o + 1], lo[nc][1] = nd[o + 2], hi[nc][1] = nd[o + 3];
+                lo[nc][2] = nd[z], hi[nc][2] = nd[z + 1];
+                ++nc;
+              }
+            }
+            float tn[4];
+            int order4[4], nh = 0;
+            for (int c = 0; c < nc; ++c)
+              if (slab(lo[c], hi[c], r, tn[c])) order4[nh++] = c;
+            std::sort(order4, order4 + nh, [&](int x, int y) { return tn[x] > tn[y]; }); // far first
+            if (nh == 0) {
+              if (sp == 0) break;
+              node = stack[--sp];
+            } else {
+              for (int k = 0; k + 1 < nh && sp < 256; ++k) stack[sp++] = ch[order4[k]];
+              node = ch[order4[nh - 1]];
+              max_stack = std::max<uint64_t>(max_stack, (uint64_t)sp);
+            }
+          } else {
+            ++leaves;
+            const uint32_t code = (uint32_t)~node, first = code >> 3, count = (code & 7u) + 1u;
+            for (uint32_t k = 0; k < count; ++k) {
+              ++tests;
+              if (tri_hit(&b.tris[(size_t)(first + k) * 12], r)) any = true;
+            }
+            if (sp == 0) break;
+            node = stack[--sp];
+          }
+        }
       } else if (b.n_nodes8 != 0) {
         struct G {
           uint32_t base, bits;

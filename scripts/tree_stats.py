@@ -62,12 +62,13 @@ def bounce_rays(tris, n):
 
 
 n = 200_000
-trees = {"sah_binary": (HostBVH(sd, wide=False), False), "sah_wide8": (HostBVH(sd, wide=True), True),
-         "lbvh_binary": (HostBVH(sd, lbvh=True), False)}
+_sah = HostBVH(sd, wide=False)
+trees = {"sah_binary": (_sah, 0), "sah_virtual4": (_sah, 2), "sah_wide8": (HostBVH(sd, wide=True), 1),
+         "lbvh_binary": (HostBVH(sd, lbvh=True), 0)}
 prim = camera_rays(n)
 sec = bounce_rays(trees["sah_binary"][0].arrays()[2], n)
 for kind, rays in (("primary", prim), ("diffuse bounce", sec)):
     for name, (hb, wide) in trees.items():
         st = hb.trace_stats(rays, wide=wide)
-        st.update(scene=which, rays_kind=kind, tree=name, nodes=int(hb.info.n_bvh8_nodes if wide else hb.info.n_bvh_nodes))
+        st.update(scene=which, rays_kind=kind, tree=name, nodes=int(hb.info.n_bvh8_nodes if wide == 1 else hb.info.n_bvh_nodes))
         print(json.dumps(st), flush=True)

@@ -212,3 +212,25 @@ def test_lbvh_orders_triangles_along_the_morton_curve():
     rng = np.random.default_rng(0)
     shuffled = np.linalg.norm(np.diff(cen[rng.permutation(len(cen))], axis=0), axis=1)
     assert step.mean() < 0.2 * shuffled.mean()                              # neighbours stay close
+
+
+def test_trace_stats_walks_agree_across_tree_layouts():
+    """The host walks of the analysis tool (binary, virtual 4-wide, compressed 8-wide, LBVH) find a
+    hit for exactly the rays the oracle's reference traversal hits, and the wider layouts visit
+    fewer nodes."""
+    sd = _mesh_scene(MESHES["bunny_5k"](), pt.translate((0.0, 0.0, -3.0)))
+    rng = np.random.default_rng(3)
+    n = 4000
+    o = rng.normal(size=(n, 3)) * 0.2
+    d = np.array([0, 0, -1.0]) + rng.normal(size=(n, 3)) * 0.35
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([o, np.full((n, 1), 1e-4), d, np.full((n, 1), 3.4e38)], axis=1).astype(np.float32)
+    ref_hits = float((load_oracle().scene(sd).trace_batch(rays)["t"] > 0).mean())
+    sah, wide, lb = HostBVH(sd, wide=False), HostBVH(sd, wide=True), HostBVH(sd, lbvh=True)
+    stats = {"binary": sah.trace_stats(rays, 0), "virtual4": sah.trace_stats(rays, 2),
+             "wide8": wide.trace_stats(rays, 1), "lbvh": lb.trace_stats(rays, 0)}
+    assert 0.2 < ref_hits < 1.0
+    for name, st in stats.items():
+        assert abs(st["hit_fraction"] - ref_hits) <= 2.0 / n, (name, st["hit_fraction"], ref_hits)
+    assert stats["wide8"]["inner_per_ray"] < stats["virtual4"]["inner_per_ray"] < stats["binary"]["inner_per_ray"]
+    assert stats["wide8"]["max_stack"] <= 32 and stats["binary"]["max_stack"] <= 60
