@@ -241,6 +241,7 @@ struct PassParams {
   uint32_t samples;
   uint32_t first_iteration;
   uint32_t rng_mode;
+  uint32_t stream_state; // path-state streams use the evict-first cache policy (PT_STREAM_STATE)
 };
 
 } // namespace pt

@@ -27,6 +27,20 @@ int cuda_fail(cudaError_t e, const char* what)
   return PT_ERR_CUDA;
 }
 
+// No C++ exception crosses the C ABI: host allocations of multi-gigabyte scenes can throw.
+template <typename F> static int guarded(const char* what, F&& body)
+{
+  try {
+    return body();
+  } catch (const std::bad_alloc&) {
+    return fail(PT_ERR_NOMEM, std::string(what) + ": out of host memory");
+  } catch (const std::exception& e) {
+    return fail(PT_ERR_INVALID, std::string(what) + ": " + e.what());
+  } catch (...) {
+    return fail(PT_ERR_INVALID, std::string(what) + ": unknown failure");
+  }
+}
+
 static double now_ms()
 {
   using namespace std::chrono;
@@ -59,8 +73,6 @@ static void rows3x4(const float* colmajor, float* out12)
 
 using namespace pt;
 
-// Every mesh instance baked to world space (the reference re-transforms three vertices per
-// leaf visit instead, path_tracer.cu:57-59).
 // Index range [first, first + 3 * count) of the mesh a mesh object instances.
 static bool mesh_range(const pt_scene_desc* desc, const pt_object& ob, uint64_t& first_tri, uint64_t& n_tri)
 {
@@ -143,7 +155,7 @@ void pt_denoise_params_default(pt_denoise_params* p)
 }
 
 // ------------------------------------------------------------------- scene
-int pt_scene_create(const pt_scene_desc* desc, int device, pt_scene** out)
+static int pt_scene_create_impl(const pt_scene_desc* desc, int device, pt_scene** out)
 {
   if (!desc || !out) return fail(PT_ERR_INVALID, "pt_scene_create: null argument");
   *out = nullptr;
@@ -151,9 +163,15 @@ int pt_scene_create(const pt_scene_desc* desc, int device, pt_scene** out)
   if (desc->n_objects && !desc->objects) return fail(PT_ERR_INVALID, "objects is null");
   if (desc->n_materials == 0 || !desc->materials)
     return fail(PT_ERR_INVALID, "scene needs at least one material");
+  if (desc->n_indices && (!desc->indices || !desc->positions))
+    return fail(PT_ERR_INVALID, "mesh arrays are null");
+  if (desc->n_spheres && !desc->spheres) return fail(PT_ERR_INVALID, "spheres is null");
   for (uint64_t i = 0; i < desc->n_indices; ++i)
     if (desc->indices[i] >= desc->n_vertices)
       return fail(PT_ERR_INVALID, "vertex index out of range");
+  for (uint32_t i = 0; i < desc->n_materials; ++i)
+    if (desc->materials[i].type < 0 || desc->materials[i].type > 2)
+      return fail(PT_ERR_INVALID, "unknown material type");
 
   int dev_count = 0;
   PT_CUDA(cudaGetDeviceCount(&dev_count));
@@ -246,7 +264,6 @@ int pt_scene_create(const pt_scene_desc* desc, int device, pt_scene** out)
     d.type = m.type;
     d.r = m.albedo[0], d.g = m.albedo[1], d.b = m.albedo[2];
     d.param = m.type == PT_MAT_METAL ? m.fuzz : (m.type == PT_MAT_DIELECTRIC ? m.refraction_index : 0.f);
-    if (m.type < 0 || m.type > 2) return fail(PT_ERR_INVALID, "unknown material type");
     mats[i] = d;
   }
 
@@ -314,13 +331,18 @@ int pt_scene_create(const pt_scene_desc* desc, int device, pt_scene** out)
   return PT_OK;
 }
 
+int pt_scene_create(const pt_scene_desc* desc, int device, pt_scene** out)
+{
+  return guarded("pt_scene_create", [&] { return pt_scene_create_impl(desc, device, out); });
+}
+
 // ---- host-only builder + structural validator (CPU tests, host build benchmark): no CUDA call
 struct pt_host_bvh_impl {
   FlatBVH bvh;
   double build_ms = 0.0;
 };
 
-int pt_host_bvh_build(const pt_scene_desc* desc, int wide, pt_host_bvh** out, pt_scene_info* info)
+static int pt_host_bvh_build_impl(const pt_scene_desc* desc, int wide, pt_host_bvh** out, pt_scene_info* info)
 {
   if (!desc || !out) return fail(PT_ERR_INVALID, "pt_host_bvh_build: null argument");
   *out = nullptr;
@@ -352,6 +374,11 @@ int pt_host_bvh_build(const pt_scene_desc* desc, int wide, pt_host_bvh** out, pt
   }
   *out = reinterpret_cast<pt_host_bvh*>(h);
   return PT_OK;
+}
+
+int pt_host_bvh_build(const pt_scene_desc* desc, int wide, pt_host_bvh** out, pt_scene_info* info)
+{
+  return guarded("pt_host_bvh_build", [&] { return pt_host_bvh_build_impl(desc, wide, out, info); });
 }
 
 int pt_host_bvh_validate(const pt_host_bvh* hb, uint64_t* violations)
@@ -434,7 +461,7 @@ static void desc_from_file(const SceneFile& sf, pt_scene_desc& d)
   }
 }
 
-int pt_scene_file_read(const char* json_path, pt_scene_file** out, pt_scene_desc* desc,
+static int pt_scene_file_read_impl(const char* json_path, pt_scene_file** out, pt_scene_desc* desc,
                        pt_scene_file_info* info)
 {
   if (!json_path || !out || !desc) return fail(PT_ERR_INVALID, "pt_scene_file_read: null argument");
@@ -458,13 +485,19 @@ int pt_scene_file_read(const char* json_path, pt_scene_file** out, pt_scene_desc
   return PT_OK;
 }
 
+int pt_scene_file_read(const char* json_path, pt_scene_file** out, pt_scene_desc* desc,
+                       pt_scene_file_info* info)
+{
+  return guarded("pt_scene_file_read", [&] { return pt_scene_file_read_impl(json_path, out, desc, info); });
+}
+
 int pt_scene_file_free(pt_scene_file* f)
 {
   delete f;
   return PT_OK;
 }
 
-int pt_scene_load_file(const char* json_path, int device, pt_scene** out, pt_scene_file_info* info)
+static int pt_scene_load_file_impl(const char* json_path, int device, pt_scene** out, pt_scene_file_info* info)
 {
   if (!json_path || !out) return fail(PT_ERR_INVALID, "pt_scene_load_file: null argument");
   const double t0 = now_ms();
@@ -472,17 +505,8 @@ int pt_scene_load_file(const char* json_path, int device, pt_scene** out, pt_sce
   int rc = load_scene_file(json_path, sf);
   if (rc != PT_OK) return rc;
   const double t1 = now_ms();
-  pt_scene_desc d{};
-  d.positions = sf.positions.data();
-  d.n_vertices = sf.positions.size() / 3;
-  d.indices = sf.indices.data();
-  d.n_indices = sf.indices.size();
-  d.objects = sf.objects.data();
-  d.n_objects = (uint32_t)sf.objects.size();
-  d.spheres = sf.spheres.data();
-  d.n_spheres = (uint32_t)sf.spheres.size();
-  d.materials = sf.materials.data();
-  d.n_materials = (uint32_t)sf.materials.size();
+  pt_scene_desc d;
+  desc_from_file(sf, d);
   rc = pt_scene_create(&d, device, out);
   if (rc != PT_OK) return rc;
   if (info) {
@@ -493,6 +517,11 @@ int pt_scene_load_file(const char* json_path, int device, pt_scene** out, pt_sce
     info->load_ms = t1 - t0;
   }
   return PT_OK;
+}
+
+int pt_scene_load_file(const char* json_path, int device, pt_scene** out, pt_scene_file_info* info)
+{
+  return guarded("pt_scene_load_file", [&] { return pt_scene_load_file_impl(json_path, device, out, info); });
 }
 
 // ----------------------------------------------------------------- context
@@ -596,7 +625,7 @@ static int alloc_image_buffers(pt_ctx* c, uint32_t width, uint32_t height)
   return PT_OK;
 }
 
-int pt_ctx_create(const pt_scene* scene, uint32_t width, uint32_t height, const pt_params* params,
+static int pt_ctx_create_impl(const pt_scene* scene, uint32_t width, uint32_t height, const pt_params* params,
                   void* stream, pt_ctx** out)
 {
   if (!scene || !out) return fail(PT_ERR_INVALID, "pt_ctx_create: null argument");
@@ -659,6 +688,12 @@ int pt_ctx_create(const pt_scene* scene, uint32_t width, uint32_t height, const 
   }
   *out = c;
   return PT_OK;
+}
+
+int pt_ctx_create(const pt_scene* scene, uint32_t width, uint32_t height, const pt_params* params,
+                  void* stream, pt_ctx** out)
+{
+  return guarded("pt_ctx_create", [&] { return pt_ctx_create_impl(scene, width, height, params, stream, out); });
 }
 
 int pt_ctx_destroy(pt_ctx* c)
@@ -806,6 +841,8 @@ static int render_pass(pt_ctx* c, const pt_camera& cam, uint32_t first_iteration
   pp.samples = samples;
   pp.first_iteration = first_iteration;
   pp.rng_mode = (uint32_t)c->params.rng_mode;
+  static const bool stream_state = getenv("PT_STREAM_STATE") && atoi(getenv("PT_STREAM_STATE")) != 0;
+  pp.stream_state = stream_state ? 1u : 0u;
   const uint32_t n0 = samples * pp.tiles_x * pp.tiles_y * 32u;
   const uint32_t max_depth = (uint32_t)c->params.max_depth;
   const bool stable = c->params.rng_mode == PT_RNG_SLOT_RESEED;
@@ -1063,7 +1100,7 @@ struct StateHeader {
 static_assert(sizeof(StateHeader) == 64, "state header is 64 bytes");
 } // namespace
 
-int pt_ctx_save_state(pt_ctx* c, const char* path)
+static int pt_ctx_save_state_impl(pt_ctx* c, const char* path)
 {
   if (!c || !path) return fail(PT_ERR_INVALID, "pt_ctx_save_state: null argument");
   PT_CUDA(cudaSetDevice(c->scene->device));
@@ -1086,7 +1123,12 @@ int pt_ctx_save_state(pt_ctx* c, const char* path)
   return PT_OK;
 }
 
-int pt_ctx_load_state(pt_ctx* c, const char* path)
+int pt_ctx_save_state(pt_ctx* c, const char* path)
+{
+  return guarded("pt_ctx_save_state", [&] { return pt_ctx_save_state_impl(c, path); });
+}
+
+static int pt_ctx_load_state_impl(pt_ctx* c, const char* path)
 {
   if (!c || !path) return fail(PT_ERR_INVALID, "pt_ctx_load_state: null argument");
   FILE* f = std::fopen(path, "rb");
@@ -1112,6 +1154,11 @@ int pt_ctx_load_state(pt_ctx* c, const char* path)
   c->iteration = (int)h.iteration;
   c->final_rgb = nullptr;
   return PT_OK;
+}
+
+int pt_ctx_load_state(pt_ctx* c, const char* path)
+{
+  return guarded("pt_ctx_load_state", [&] { return pt_ctx_load_state_impl(c, path); });
 }
 
 int pt_ctx_upload_frame(pt_ctx* c, const float* color3, const float* normal3, const float* depth1,

@@ -38,6 +38,32 @@ namespace pt {
 PT_D f3 xyz(const float4& v) { return mk3(v.x, v.y, v.z); }
 PT_D float4 mk4(f3 v, float w) { return make_float4(v.x, v.y, v.z, w); }
 PT_D float4 ldg4(const float4* p) { return __ldg(p); }
+// Path-state streams are written once and read once, gigabytes per pass: with `cs` set they use
+// the evict-first cache policy (ld/st.global.cs) so that they do not displace the scene in L1/L2.
+PT_D float4 ld_state(const float4* p, uint32_t cs) { return cs ? __ldcs(p) : *p; }
+PT_D uint4 ld_state(const uint4* p, uint32_t cs) { return cs ? __ldcs(p) : *p; }
+PT_D uint32_t ld_state(const uint32_t* p, uint32_t cs) { return cs ? __ldcs(p) : *p; }
+PT_D void st_state(float4* p, float4 v, uint32_t cs)
+{
+  if (cs)
+    __stcs(p, v);
+  else
+    *p = v;
+}
+PT_D void st_state(uint4* p, uint4 v, uint32_t cs)
+{
+  if (cs)
+    __stcs(p, v);
+  else
+    *p = v;
+}
+PT_D void st_state(uint32_t* p, uint32_t v, uint32_t cs)
+{
+  if (cs)
+    __stcs(p, v);
+  else
+    *p = v;
+}
 
 struct Hit {
   float t;
@@ -270,6 +296,9 @@ struct Trav {
   int best; // best triangle slot or -1
 };
 
+// (A hybrid stack — the first 8 or 16 entries in shared memory laid out [entry][thread], one
+// conflict-free wavefront per warp access, the rest in local memory — was measured and rejected:
+// traverse 15.27 -> 15.82 / 16.10 ms on the bunny frame, profiles/README.md.)
 PT_D void trav_init(Trav& T, f3 o, f3 d, float tmin, float tbest, int start, int* stack)
 {
   T.o = o;
@@ -477,12 +506,14 @@ enum { SRC_QUEUE = 1, SRC_BATCH = 2 };
 // (Staging the hottest nodes of the binary tree in shared memory — area-ordered prefix, 80-byte
 // stride against bank conflicts, up to 200 KB per SM — was measured and rejected: 15.6-17.1 ms
 // against 15.7 ms for plain L1-cached loads on the bunny frame, profiles/README.md.)
+//
+// stream_state: the parked ray state is fetched with the evict-first policy (ld_state).
 template <int SRC>
 __global__ void __launch_bounds__(EXT_THREADS, EXT_MIN_BLOCKS)
 traverse_kernel(const DevScene sc, const PathState ps, const uint32_t* __restrict__ tq,
                 const uint32_t* __restrict__ n_ptr, uint32_t n_host, uint32_t* __restrict__ work,
                 const float4* __restrict__ batch_rays, HitRecord* __restrict__ batch_out,
-                int refill_min, int inner_min)
+                int refill_min, int inner_min, int stream_state)
 {
   const uint32_t n = SRC == SRC_QUEUE ? *n_ptr : n_host;
   const uint32_t lane = threadIdx.x & 31u;
@@ -508,9 +539,9 @@ traverse_kernel(const DevScene sc, const PathState ps, const uint32_t* __restric
         if (idx < n) {
           if (SRC == SRC_QUEUE) {
             pid = tq ? tq[idx] : idx; // no list: the state is compacted, slot == index
-            const float4 ro = ps.ray[2 * (size_t)pid];
-            const float4 rd = ps.ray[2 * (size_t)pid + 1];
-            const uint4 ax = ps.aux[pid];
+            const float4 ro = ld_state(ps.ray + 2 * (size_t)pid, (uint32_t)stream_state);
+            const float4 rd = ld_state(ps.ray + 2 * (size_t)pid + 1, (uint32_t)stream_state);
+            const uint4 ax = ld_state(ps.aux + pid, (uint32_t)stream_state);
             trav_init(T, xyz(ro), xyz(rd), ro.w, __uint_as_float(ax.x), (int)ax.z, stack);
             has = true;
           } else {
@@ -1027,6 +1058,7 @@ chain_kernel(const DevScene sc, const PathState ps, const PassParams pp, const P
   const uint32_t n_round = (n + 31u) & ~31u;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t cs = pp.stream_state;
   uint32_t rays_local = 0;
   for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_round; idx += stride) {
     uint32_t pid = 0, pixel, s, px, py;
@@ -1053,11 +1085,11 @@ chain_kernel(const DevScene sc, const PathState ps, const PassParams pp, const P
         need_traversal = classify(sc, o, d, tmin, FLT_MAX, tbest, code, start, h);
         have_hit = true;
       } else {
-        const float4 ro = in.ray[2 * (size_t)idx];
-        const float4 rd = in.ray[2 * (size_t)idx + 1];
-        const float4 th = in.thr[idx];
-        const uint4 ax = in.aux[idx];
-        pid = in.pid[idx];
+        const float4 ro = ld_state(in.ray + 2 * (size_t)idx, cs);
+        const float4 rd = ld_state(in.ray + 2 * (size_t)idx + 1, cs);
+        const float4 th = ld_state(in.thr + idx, cs);
+        const uint4 ax = ld_state(in.aux + idx, cs);
+        pid = ld_state(in.pid + idx, cs);
         o = xyz(ro), d = xyz(rd);
         tmin = ro.w;
         color = xyz(th);
@@ -1077,8 +1109,8 @@ chain_kernel(const DevScene sc, const PathState ps, const PassParams pp, const P
         // root as resolve_hit would pick); traversed rays rebuild theirs from the aux word
         const bool hit = have_hit ? code != 0u : resolve_hit(sc, o, d, tmin, tbest, code, h);
         if (depth == 0u) {
-          ps.gbuf[pid] = hit ? make_float4(h.n.x, h.n.y, h.n.z, h.t)
-                             : make_float4(-d.x, -d.y, -d.z, 1e6f);
+          st_state(ps.gbuf + pid,
+                   hit ? make_float4(h.n.x, h.n.y, h.n.z, h.t) : make_float4(-d.x, -d.y, -d.z, 1e6f), cs);
         }
         if (!hit) {
           color = color * sky_color(d);
@@ -1090,15 +1122,15 @@ chain_kernel(const DevScene sc, const PathState ps, const PassParams pp, const P
         need_traversal = classify(sc, o, d, tmin, FLT_MAX, tbest, code, start, h);
         have_hit = true;
       }
-      if (!park) ps.thr[pid] = mk4(color, __uint_as_float(rng)); // the path's contribution
+      if (!park) st_state(ps.thr + pid, mk4(color, __uint_as_float(rng)), cs); // the path's contribution
     }
     const uint32_t slot = warp_slot(park, out_count, lane);
     if (park) {
-      out.ray[2 * (size_t)slot] = mk4(o, tmin);
-      out.ray[2 * (size_t)slot + 1] = mk4(d, FLT_MAX);
-      out.thr[slot] = mk4(color, __uint_as_float(rng));
-      out.aux[slot] = make_uint4(__float_as_uint(tbest), code, (uint32_t)start, depth);
-      out.pid[slot] = pid;
+      st_state(out.ray + 2 * (size_t)slot, mk4(o, tmin), cs);
+      st_state(out.ray + 2 * (size_t)slot + 1, mk4(d, FLT_MAX), cs);
+      st_state(out.thr + slot, mk4(color, __uint_as_float(rng)), cs);
+      st_state(out.aux + slot, make_uint4(__float_as_uint(tbest), code, (uint32_t)start, depth), cs);
+      st_state(out.pid + slot, pid, cs);
     }
   }
   // one 64-bit atomic per warp for the ray counter
@@ -1151,7 +1183,9 @@ static uint32_t persistent_grid(K kern, const LaunchEnv& env, int threads, size_
   cudaGetDevice(&dev);
   dev &= 63;
   if (cache_nb[dev] == 0 || cache_smem[dev] != smem) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+    // (only kernels that stage into dynamic shared memory: with static shared memory on top, the
+    // full window would exceed the per-CTA limit and the call would fail with "invalid argument")
+    if (smem > 0) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem) != cudaSuccess || nb <= 0) nb = 1;
     cache_nb[dev] = nb;
@@ -1171,7 +1205,8 @@ static void launch_t2(const LaunchEnv& env, const DevScene& sc, const PathState&
   const uint32_t grid = min(persistent_grid(kern, env, EXT_THREADS, 0, nb, sm), max_grid);
   kern<<<grid, EXT_THREADS, 0, env.stream>>>(sc, ps, tq, n_ptr, n_host, work, rays, out,
                                              tune("PT_REFILL", EXT_REFILL),
-                                             tune("PT_INNER_MIN", EXT_INNER_MIN));
+                                             tune("PT_INNER_MIN", EXT_INNER_MIN),
+                                             tune("PT_STREAM_STATE", 0));
 }
 
 template <int SRC, int THREADS, int BLOCKS>

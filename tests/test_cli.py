@@ -116,3 +116,29 @@ def test_cli_render_equals_api_and_resume_equals_one_run(tmp_path):
               "scenes/bunny.json"], cwd)
     assert r.returncode == 0 and "Denoising" in r.stdout
     assert _read_png(str(tmp_path / "d.png")).shape == img.shape
+
+
+@pytest.mark.gpu
+def test_cli_all_meshes_gives_every_mesh_object_its_own_mesh(tmp_path):
+    """`--all-meshes` (extension): the scene file's mesh table reaches the scene upload, so the two
+    mesh objects instance b.obj and a.obj; the default keeps the reference's first-mesh-only rule
+    (scene_description.cpp:95)."""
+    _, cwd = _assets(tmp_path, res=(96, 54))
+    a, b = pt.bunny_like(1), pt.bunny_like(2)
+    models = tmp_path / "assets" / "models"
+    pt.write_obj(str(models / "a.obj"), a)
+    pt.write_obj(str(models / "b.obj"), b)
+    scene = tmp_path / "assets" / "scenes" / "bunny.json"
+    js = json.loads(scene.read_text())
+    js["surfaces"][1]["filename"] = "../models/b.obj"
+    js["surfaces"][2]["filename"] = "../models/a.obj"
+    scene.write_text(json.dumps(js))
+    stats = str(tmp_path / "stats.json")
+    r = _run(["--output", str(tmp_path / "one.png"), "--spp", "1", "--stats-json", stats, "scenes/bunny.json"], cwd)
+    assert r.returncode == 0, r.stderr
+    assert json.load(open(stats))["triangles"] == 2 * a.triangle_count
+    r = _run(["--output", str(tmp_path / "all.png"), "--spp", "1", "--all-meshes", "--stats-json", stats,
+              "scenes/bunny.json"], cwd)
+    assert r.returncode == 0, r.stderr
+    assert json.load(open(stats))["triangles"] == a.triangle_count + b.triangle_count
+    assert (_read_png(str(tmp_path / "one.png")) != _read_png(str(tmp_path / "all.png"))).any()
