@@ -97,8 +97,16 @@ struct JParser {
     ++p;
     return true;
   }
+  int depth = 0; // nesting guard: the parser recurses once per '{' / '['
+  struct DepthGuard {
+    int& d;
+    explicit DepthGuard(int& d_) : d(d_) { ++d; }
+    ~DepthGuard() { --d; }
+  };
   bool parse(JPtr& out)
   {
+    const DepthGuard guard(depth);
+    if (depth > 256) return fail("JSON nested deeper than 256 levels");
     ws();
     if (p >= end) return fail("unexpected end of JSON");
     out = std::make_shared<JValue>();
@@ -715,6 +723,8 @@ int load_scene_file(const char* json_path, SceneFile& out)
     return fail(PT_ERR_IO, std::string("Json Parser: Cannot open file ") + json_path);
   JParser jp{text.data(), text.data() + text.size(), {}};
   JPtr root;
+  // (`file >> json`, json_parser.cpp:166-167, reads ONE value and leaves what follows unread:
+  // text after the document is not an error)
   if (!jp.parse(root) || root->kind != JValue::Obj)
     return fail(PT_ERR_PARSE, "Json Parser: " + (jp.err.empty() ? std::string("root is not an object") : jp.err));
 

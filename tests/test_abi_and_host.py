@@ -142,6 +142,16 @@ def test_scene_reader_errors(tmp_path):
     (tmp_path / "scenes" / "broken.json").write_text("{ \"camera\": ")
     rc, *_ = _read(str(tmp_path / "scenes" / "broken.json"))
     assert rc == 4
+    # `file >> json` (json_parser.cpp:166-167) reads one value and ignores what follows; so do we
+    pt.write_obj(str(tmp_path / "models" / "bunny.obj"), pt.bunny_like(0))
+    (tmp_path / "scenes" / "trailing.json").write_text(json.dumps(BUNNY_JSON) + " x")
+    rc, h, *_ = _read(str(tmp_path / "scenes" / "trailing.json"))
+    assert rc == 0
+    lib.pt_scene_file_free(h)
+    # pathological nesting is an error, not a stack overflow
+    (tmp_path / "scenes" / "deep.json").write_text("[" * 100000)
+    rc, *_ = _read(str(tmp_path / "scenes" / "deep.json"))
+    assert rc == 4 and b"nested deeper" in lib.pt_last_error()
 
 
 def test_obj_reader_polygons_negative_indices_and_first_mesh(tmp_path):
