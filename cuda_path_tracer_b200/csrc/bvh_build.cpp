@@ -73,28 +73,35 @@ struct Prim {
 };
 
 struct Bin {
-  Box box;  // bounds of the primitives
-  Box cbox; // bounds of their centroids
+  Box box; // bounds of the primitives
   uint32_t count;
-  void reset()
-  {
-    box.reset();
-    cbox.reset();
-    count = 0;
-  }
   void merge(const Bin& o)
   {
     box.grow(o.box);
-    cbox.grow(o.cbox);
     count += o.count;
   }
 };
+// Bins are SPARSE: only the bins named in mask[axis] hold data.  Most nodes of a tree are small
+// (a 10-M-triangle tree has 5 M nodes of a handful of primitives each), and clearing, merging and
+// sweeping 48 bins per node cost more than binning the node's primitives.  Skipping empty bins
+// changes no result: growing a box by an empty bin is a no-op, and a split candidate that ends
+// on an empty bin repeats the previous candidate's cost, which the strict `<` never prefers.
 struct BinSet {
   Bin bin[3][kBins];
-  void reset()
+  uint32_t mask[3];
+  void reset() { mask[0] = mask[1] = mask[2] = 0u; }
+  void merge(const BinSet& o)
   {
-    for (int a = 0; a < 3; ++a)
-      for (int b = 0; b < kBins; ++b) bin[a][b].reset();
+    for (int a = 0; a < 3; ++a) {
+      for (uint32_t m = o.mask[a]; m; m &= m - 1u) {
+        const int b = __builtin_ctz(m);
+        if (mask[a] >> b & 1u)
+          bin[a][b].merge(o.bin[a][b]);
+        else
+          bin[a][b] = o.bin[a][b];
+      }
+      mask[a] |= o.mask[a];
+    }
   }
 };
 
@@ -105,6 +112,8 @@ struct BuildNode {
   uint32_t left, right;  // children (inner) ...
   uint32_t first, count; // ... or primitive range (leaf, count > 0)
   uint32_t inner;        // inner nodes in this subtree, itself included (0 for a leaf)
+  uint32_t height;       // edges to the deepest leaf below (0 for a leaf)
+  float sah;             // sum over the subtree of area x (leaf ? count x C_isect : C_trav), not normalised
 };
 
 template <typename T> struct RawArray {
@@ -132,38 +141,39 @@ struct Builder {
   int kLeafMax = 4; // 3 when the compressed 8-wide tree is derived from this one
   RawArray<Prim> prims;
   RawArray<BuildNode> nodes;
-  std::atomic<uint32_t> n_nodes{0};
-  std::atomic<uint32_t> max_depth{0};
+  // Node slots are handed out by RANGE, not by a shared counter: the subtree over `count`
+  // primitives rooted at slot ni owns slots [ni, ni + 2 count - 1) — the root of its left child
+  // (lc primitives) is ni + 1 and that of its right child ni + 2 lc.  No atomic, no cache line
+  // shared between the threads building different subtrees, and the array position of every node
+  // is independent of scheduling.  Unused slots stay uninitialised and are never read (every
+  // consumer follows left/right).
 
-  uint32_t alloc_node() { return n_nodes.fetch_add(1, std::memory_order_relaxed); }
-
-  void make_leaf(uint32_t ni, uint32_t first, uint32_t count, int depth)
+  void make_leaf(uint32_t ni, uint32_t first, uint32_t count)
   {
-    nodes[ni].first = first;
-    nodes[ni].count = count;
-    nodes[ni].left = nodes[ni].right = 0;
-    nodes[ni].inner = 0;
-    uint32_t d = (uint32_t)depth, cur = max_depth.load(std::memory_order_relaxed);
-    while (d > cur && !max_depth.compare_exchange_weak(cur, d)) {}
+    BuildNode& nd = nodes[ni];
+    nd.first = first;
+    nd.count = count;
+    nd.left = nd.right = 0;
+    nd.inner = 0;
+    nd.height = 0;
+    nd.sah = nd.box.area() * (float)count * kIsectCost;
   }
 
+  // Bins `n` primitives on the three axes at once into `out` (reset by the caller's contract: this
+  // call OVERWRITES out; chunks are combined with BinSet::merge).
   static void bin_range(const Prim* p, uint32_t n, const Box& cb, const float* scale, BinSet& out)
   {
+    out.reset();
 #if defined(__SSE2__)
     // four-lane version: one min/max pair per box instead of six scalar ones.  Lane 3 is a
     // don't-care (it carries hi[0] / the id bits and is masked before any arithmetic).
     struct VBin {
-      __m128 blo, bhi, clo, chi;
+      __m128 blo, bhi;
     };
-    VBin vb[3][kBins];
+    VBin vb[3][kBins]; // initialised on first touch (mask)
     uint32_t cnt[3][kBins];
-    const __m128 big = _mm_set1_ps(FLT_MAX), nbig = _mm_set1_ps(-FLT_MAX);
-    for (int a = 0; a < 3; ++a)
-      for (int k = 0; k < kBins; ++k) {
-        vb[a][k].blo = vb[a][k].clo = big;
-        vb[a][k].bhi = vb[a][k].chi = nbig;
-        cnt[a][k] = 0;
-      }
+    uint32_t mask[3] = {0u, 0u, 0u};
+    const bool use[3] = {scale[0] != 0.f, scale[1] != 0.f, scale[2] != 0.f};
     const __m128 mask3 = _mm_castsi128_ps(_mm_set_epi32(0, -1, -1, -1));
     const __m128 cblo = _mm_set_ps(0.f, cb.lo[2], cb.lo[1], cb.lo[0]);
     const __m128 sc4 = _mm_set_ps(0.f, scale[2], scale[1], scale[0]);
@@ -177,32 +187,35 @@ struct Builder {
       alignas(16) int bi[4];
       _mm_store_si128(reinterpret_cast<__m128i*>(bi), _mm_cvttps_epi32(f));
       for (int a = 0; a < 3; ++a) {
-        if (scale[a] == 0.f) continue;
-        VBin& v = vb[a][bi[a]];
-        v.blo = _mm_min_ps(v.blo, lo);
-        v.bhi = _mm_max_ps(v.bhi, hi);
-        v.clo = _mm_min_ps(v.clo, c);
-        v.chi = _mm_max_ps(v.chi, c);
-        cnt[a][bi[a]]++;
+        if (!use[a]) continue;
+        const int k = bi[a];
+        VBin& v = vb[a][k];
+        if (mask[a] >> k & 1u) {
+          v.blo = _mm_min_ps(v.blo, lo);
+          v.bhi = _mm_max_ps(v.bhi, hi);
+          cnt[a][k]++;
+        } else {
+          v.blo = lo, v.bhi = hi;
+          cnt[a][k] = 1;
+          mask[a] |= 1u << k;
+        }
       }
     }
-    for (int a = 0; a < 3; ++a)
-      for (int k = 0; k < kBins; ++k) {
-        if (cnt[a][k] == 0) continue;
-        alignas(16) float t[4][4];
+    for (int a = 0; a < 3; ++a) {
+      out.mask[a] = mask[a];
+      for (uint32_t m = mask[a]; m; m &= m - 1u) {
+        const int k = __builtin_ctz(m);
+        alignas(16) float t[2][4];
         _mm_store_ps(t[0], vb[a][k].blo);
         _mm_store_ps(t[1], vb[a][k].bhi);
-        _mm_store_ps(t[2], vb[a][k].clo);
-        _mm_store_ps(t[3], vb[a][k].chi);
         Bin& bn = out.bin[a][k];
         for (int x = 0; x < 3; ++x) {
-          bn.box.lo[x] = std::min(bn.box.lo[x], t[0][x]);
-          bn.box.hi[x] = std::max(bn.box.hi[x], t[1][x]);
-          bn.cbox.lo[x] = std::min(bn.cbox.lo[x], t[2][x]);
-          bn.cbox.hi[x] = std::max(bn.cbox.hi[x], t[3][x]);
+          bn.box.lo[x] = t[0][x];
+          bn.box.hi[x] = t[1][x];
         }
-        bn.count += cnt[a][k];
+        bn.count = cnt[a][k];
       }
+    }
 #else
     for (uint32_t i = 0; i < n; ++i) {
       const Prim& q = p[i];
@@ -212,8 +225,12 @@ struct Builder {
         int b = (int)((c[a] - cb.lo[a]) * scale[a]);
         b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
         Bin& bn = out.bin[a][b];
+        if (!(out.mask[a] >> b & 1u)) {
+          bn.box.reset();
+          bn.count = 0;
+          out.mask[a] |= 1u << b;
+        }
         bn.box.grow(q.b);
-        bn.cbox.grow(c);
         bn.count++;
       }
     }
@@ -232,11 +249,79 @@ struct Builder {
     }
   }
 
+  // Partitions p[0, n) into the primitives whose centroid falls into bins <= bb of `axis`, then the
+  // rest, and returns the size of the first part.  Element order is std::partition's (libstdc++,
+  // bidirectional iterators: converge from both ends, swap), and every element is classified
+  // exactly once — which is where the children's primitive and centroid bounds are accumulated, in
+  // registers, instead of in the per-bin records of the binning pass.
+  static uint32_t partition_by_bin(Prim* p, uint32_t n, int axis, float lo, float sc, int bb, Box& lbox,
+                                   Box& lcb, Box& rbox, Box& rcb)
+  {
+#if defined(__SSE2__)
+    const __m128 big = _mm_set1_ps(FLT_MAX), nbig = _mm_set1_ps(-FLT_MAX), half = _mm_set1_ps(0.5f);
+    __m128 llo = big, lhi = nbig, lclo = big, lchi = nbig, rlo = big, rhi = nbig, rclo = big, rchi = nbig;
+    auto goes_left = [&](const Prim& q) -> bool {
+      const __m128 qlo = _mm_loadu_ps(q.b.lo), qhi = _mm_loadu_ps(q.b.hi); // lane 3: don't care
+      const __m128 c = _mm_mul_ps(half, _mm_add_ps(qlo, qhi));
+      int b = (int)((q.c(axis) - lo) * sc);
+      b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
+      if (b <= bb) {
+        llo = _mm_min_ps(llo, qlo), lhi = _mm_max_ps(lhi, qhi);
+        lclo = _mm_min_ps(lclo, c), lchi = _mm_max_ps(lchi, c);
+        return true;
+      }
+      rlo = _mm_min_ps(rlo, qlo), rhi = _mm_max_ps(rhi, qhi);
+      rclo = _mm_min_ps(rclo, c), rchi = _mm_max_ps(rchi, c);
+      return false;
+    };
+#else
+    lbox.reset(), lcb.reset(), rbox.reset(), rcb.reset();
+    auto goes_left = [&](const Prim& q) -> bool {
+      const float c[3] = {q.c(0), q.c(1), q.c(2)};
+      int b = (int)((c[axis] - lo) * sc);
+      b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
+      (b <= bb ? lbox : rbox).grow(q.b);
+      (b <= bb ? lcb : rcb).grow(c);
+      return b <= bb;
+    };
+#endif
+    Prim* f = p;
+    Prim* l = p + n;
+    for (;;) {
+      for (;;) {
+        if (f == l) goto done;
+        if (!goes_left(*f)) break;
+        ++f;
+      }
+      --l;
+      for (;;) {
+        if (f == l) goto done;
+        if (goes_left(*l)) break;
+        --l;
+      }
+      std::swap(*f, *l);
+      ++f;
+    }
+  done:
+#if defined(__SSE2__)
+    {
+      alignas(16) float t[8][4];
+      _mm_store_ps(t[0], llo), _mm_store_ps(t[1], lhi), _mm_store_ps(t[2], lclo), _mm_store_ps(t[3], lchi);
+      _mm_store_ps(t[4], rlo), _mm_store_ps(t[5], rhi), _mm_store_ps(t[6], rclo), _mm_store_ps(t[7], rchi);
+      for (int x = 0; x < 3; ++x) {
+        lbox.lo[x] = t[0][x], lbox.hi[x] = t[1][x], lcb.lo[x] = t[2][x], lcb.hi[x] = t[3][x];
+        rbox.lo[x] = t[4][x], rbox.hi[x] = t[5][x], rcb.lo[x] = t[6][x], rcb.hi[x] = t[7][x];
+      }
+    }
+#endif
+    return (uint32_t)(f - p);
+  }
+
   void build(uint32_t ni, uint32_t first, uint32_t count, int depth, const Box& nb, const Box& cb)
   {
     nodes[ni].box = nb;
     if (count == 1) {
-      make_leaf(ni, first, count, depth);
+      make_leaf(ni, first, count);
       return;
     }
     const float ext[3] = {cb.hi[0] - cb.lo[0], cb.hi[1] - cb.lo[1], cb.hi[2] - cb.lo[2]};
@@ -249,8 +334,8 @@ struct Builder {
       float scale[3];
       for (int a = 0; a < 3; ++a) scale[a] = ext[a] > 0.0f ? (float)kBins / ext[a] : 0.f;
       BinSet bins;
-      bins.reset();
       if (count >= kParallelBin) {
+        bins.reset();
         const int chunks = (int)std::min<uint32_t>(64, count / (kParallelBin / 4));
         std::vector<BinSet> part(chunks);
         const Prim* base = prims.data() + first;
@@ -258,42 +343,44 @@ struct Builder {
         for (int c = 0; c < chunks; ++c) {
           const uint32_t b0 = (uint32_t)((uint64_t)count * c / chunks);
           const uint32_t b1 = (uint32_t)((uint64_t)count * (c + 1) / chunks);
-          part[c].reset();
           bin_range(base + b0, b1 - b0, cb, scale, part[c]);
         }
-        for (int c = 0; c < chunks; ++c)
-          for (int a = 0; a < 3; ++a)
-            for (int b = 0; b < kBins; ++b) bins.bin[a][b].merge(part[c].bin[a][b]);
+        for (int c = 0; c < chunks; ++c) bins.merge(part[c]);
       } else {
         bin_range(prims.data() + first, count, cb, scale, bins);
       }
 
+      // SAH sweep over the non-empty bins of every axis (see BinSet: same winner as a sweep over
+      // all 16 bins)
       float best_cost = FLT_MAX;
       int best_axis = -1, best_bin = -1;
       for (int axis = 0; axis < 3; ++axis) {
-        if (scale[axis] == 0.f) continue;
+        const uint32_t used = bins.mask[axis];
+        if ((used & (used - 1u)) == 0u) continue; // everything in one bin: no candidate
+        int idx[kBins];
+        int k = 0;
+        for (uint32_t m = used; m; m &= m - 1u) idx[k++] = __builtin_ctz(m);
         float right_area[kBins];
         uint32_t right_cnt[kBins];
         Box acc;
         acc.reset();
         uint32_t c = 0;
-        for (int b = kBins - 1; b > 0; --b) {
-          acc.grow(bins.bin[axis][b].box);
-          c += bins.bin[axis][b].count;
-          right_area[b] = acc.area();
-          right_cnt[b] = c;
+        for (int j = k - 1; j > 0; --j) {
+          acc.grow(bins.bin[axis][idx[j]].box);
+          c += bins.bin[axis][idx[j]].count;
+          right_area[j] = acc.area();
+          right_cnt[j] = c;
         }
         acc.reset();
         c = 0;
-        for (int b = 0; b < kBins - 1; ++b) {
-          acc.grow(bins.bin[axis][b].box);
-          c += bins.bin[axis][b].count;
-          if (c == 0 || right_cnt[b + 1] == 0) continue;
-          const float cost = acc.area() * (float)c + right_area[b + 1] * (float)right_cnt[b + 1];
+        for (int j = 0; j + 1 < k; ++j) {
+          acc.grow(bins.bin[axis][idx[j]].box);
+          c += bins.bin[axis][idx[j]].count;
+          const float cost = acc.area() * (float)c + right_area[j + 1] * (float)right_cnt[j + 1];
           if (cost < best_cost) {
             best_cost = cost;
             best_axis = axis;
-            best_bin = b;
+            best_bin = idx[j];
           }
         }
       }
@@ -302,35 +389,17 @@ struct Builder {
         const float split_cost = kTravCost + (area > 0.f ? best_cost / area : 0.f) * kIsectCost;
         const float leaf_cost = (float)count * kIsectCost;
         if (count <= (uint32_t)kLeafMax && leaf_cost <= split_cost) {
-          make_leaf(ni, first, count, depth);
+          make_leaf(ni, first, count);
           return;
         }
-        const float sc = scale[best_axis];
-        const float lo = cb.lo[best_axis];
-        const int ax = best_axis, bb = best_bin;
-        Prim* b0 = prims.data() + first;
-        Prim* m = std::partition(b0, b0 + count, [=](const Prim& q) {
-          int b = (int)((q.c(ax) - lo) * sc);
-          b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
-          return b <= bb;
-        });
-        mid = (uint32_t)(m - prims.data());
+        mid = first + partition_by_bin(prims.data() + first, count, best_axis, cb.lo[best_axis],
+                                       scale[best_axis], best_bin, lbox, lcb, rbox, rcb);
         have_split = mid > first && mid < first + count;
-        if (have_split) {
-          // child bounds come from the bins: no extra pass over the primitives
-          lbox.reset(), lcb.reset(), rbox.reset(), rcb.reset();
-          for (int b = 0; b < kBins; ++b) {
-            const Bin& bn = bins.bin[best_axis][b];
-            if (bn.count == 0) continue;
-            (b <= best_bin ? lbox : rbox).grow(bn.box);
-            (b <= best_bin ? lcb : rcb).grow(bn.cbox);
-          }
-        }
       }
     }
     if (!have_split) {
       if (count <= (uint32_t)kLeafMax) {
-        make_leaf(ni, first, count, depth);
+        make_leaf(ni, first, count);
         return;
       }
       // balanced median split (degenerate centroids or depth guard)
@@ -344,13 +413,12 @@ struct Builder {
       range_bounds(mid, first + count - mid, rbox, rcb);
     }
 
-    const uint32_t l = alloc_node();
-    const uint32_t r = alloc_node();
+    const uint32_t lc = mid - first, rc = first + count - mid;
+    const uint32_t l = ni + 1u, r = ni + 2u * lc;
     nodes[ni].left = l;
     nodes[ni].right = r;
     nodes[ni].count = 0;
     nodes[ni].first = first;
-    const uint32_t lc = mid - first, rc = first + count - mid;
     if (count >= kTaskMin) {
 #pragma omp task default(shared) firstprivate(l, first, lc, depth, lbox, lcb)
       build(l, first, lc, depth + 1, lbox, lcb);
@@ -362,6 +430,8 @@ struct Builder {
       build(r, mid, rc, depth + 1, rbox, rcb);
     }
     nodes[ni].inner = 1u + nodes[l].inner + nodes[r].inner;
+    nodes[ni].height = 1u + std::max(nodes[l].height, nodes[r].height);
+    nodes[ni].sah = nodes[ni].box.area() * kTravCost + (nodes[l].sah + nodes[r].sah);
   }
 };
 
@@ -555,7 +625,7 @@ struct WideBuilder {
 
   void run(uint32_t root, uint32_t n_prims, FlatBVH& out)
   {
-    new_first.assign(B.n_nodes.load(), 0u);
+    new_first.assign(B.nodes.n, 0u);
     order.assign(n_prims, 0u);
     bnode.clear();
     bnode.push_back(root);
@@ -646,7 +716,7 @@ void build_bvh(const std::vector<BuildTri>& tris, FlatBVH& out, bool wide)
     }
   }
   lap("primitive boxes");
-  const uint32_t root = B.alloc_node();
+  const uint32_t root = 0; // owns slots [0, 2n - 1)
 #pragma omp parallel
   {
 #pragma omp single
@@ -715,7 +785,6 @@ void build_bvh(const std::vector<BuildTri>& tris, FlatBVH& out, bool wide)
   // DFS pre-order index of an inner node = its parent's + 1 (left child) or + 1 + the left
   // subtree's inner-node count (right child): known without a sequential walk, so the nodes are
   // emitted by parallel tasks
-  const uint32_t total = B.n_nodes.load();
   const uint32_t n_inner = B.nodes[root].inner;
   out.n_nodes = n_inner;
   out.nodes.resize((size_t)n_inner * 16);
@@ -775,17 +844,9 @@ void build_bvh(const std::vector<BuildTri>& tris, FlatBVH& out, bool wide)
 #pragma omp single
     emit.run(root, 0u);
   }
-  double sah = 0.0;
-  const double root_area = B.nodes[root].box.area();
-  if (root_area > 0) {
-#pragma omp parallel for schedule(static) reduction(+ : sah)
-    for (long long ni = 0; ni < (long long)total; ++ni) {
-      const BuildNode& nd = B.nodes[ni];
-      sah += (double)nd.box.area() / root_area * (nd.count != 0 ? nd.count * kIsectCost : kTravCost);
-    }
-  }
-  out.sah_cost = sah;
-  out.depth = B.max_depth.load() + 1;
+  const float root_area = B.nodes[root].box.area();
+  out.sah_cost = root_area > 0.f ? (double)B.nodes[root].sah / root_area : 0.0;
+  out.depth = B.nodes[root].height + 1;
   lap("flatten");
 }
 
