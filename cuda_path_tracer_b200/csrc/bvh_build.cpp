@@ -142,11 +142,14 @@ struct Builder {
   RawArray<Prim> prims;
   RawArray<BuildNode> nodes;
   // Node slots are handed out by RANGE, not by a shared counter: the subtree over `count`
-  // primitives rooted at slot ni owns slots [ni, ni + 2 count - 1) — the root of its left child
-  // (lc primitives) is ni + 1 and that of its right child ni + 2 lc.  No atomic, no cache line
-  // shared between the threads building different subtrees, and the array position of every node
-  // is independent of scheduling.  Unused slots stay uninitialised and are never read (every
-  // consumer follows left/right).
+  // primitives rooted at slot ni owns slots [ni, ni + 2 count - 1).  Subtrees big enough to be
+  // tasks split their range (left child at ni + 1, right child at ni + 2 lc); a subtree that is
+  // built sequentially fills the front of its range through a private bump counter, so the
+  // touched memory stays compact.  No atomic, no cache line shared between the threads building
+  // different subtrees, and the array position of every node is independent of scheduling.
+  // Unused slots stay uninitialised and are never read (every consumer follows left/right).
+  // (A chunk-parallel partition of the biggest nodes was measured as well: no gain at 10 M
+  // triangles on 8 threads — the build is bound by per-primitive work, not by the serial top.)
 
   void make_leaf(uint32_t ni, uint32_t first, uint32_t count)
   {
@@ -317,8 +320,11 @@ struct Builder {
     return (uint32_t)(f - p);
   }
 
-  void build(uint32_t ni, uint32_t first, uint32_t count, int depth, const Box& nb, const Box& cb)
+  void build(uint32_t ni, uint32_t first, uint32_t count, int depth, const Box& nb, const Box& cb,
+             uint32_t* bump = nullptr)
   {
+    uint32_t local_next = ni + 1u;
+    if (!bump && count < kTaskMin) bump = &local_next; // sequential from here down
     nodes[ni].box = nb;
     if (count == 1) {
       make_leaf(ni, first, count);
@@ -414,7 +420,14 @@ struct Builder {
     }
 
     const uint32_t lc = mid - first, rc = first + count - mid;
-    const uint32_t l = ni + 1u, r = ni + 2u * lc;
+    uint32_t l, r;
+    if (bump) {
+      l = (*bump)++;
+      r = (*bump)++;
+    } else {
+      l = ni + 1u;
+      r = ni + 2u * lc;
+    }
     nodes[ni].left = l;
     nodes[ni].right = r;
     nodes[ni].count = 0;
@@ -426,8 +439,8 @@ struct Builder {
       build(r, mid, rc, depth + 1, rbox, rcb);
 #pragma omp taskwait
     } else {
-      build(l, first, lc, depth + 1, lbox, lcb);
-      build(r, mid, rc, depth + 1, rbox, rcb);
+      build(l, first, lc, depth + 1, lbox, lcb, bump);
+      build(r, mid, rc, depth + 1, rbox, rcb, bump);
     }
     nodes[ni].inner = 1u + nodes[l].inner + nodes[r].inner;
     nodes[ni].height = 1u + std::max(nodes[l].height, nodes[r].height);
@@ -669,7 +682,7 @@ struct WideBuilder {
 
 } // namespace
 
-void build_bvh(const std::vector<BuildTri>& tris, FlatBVH& out, bool wide)
+void build_bvh(const BuildTris& tris, FlatBVH& out, bool wide)
 {
   out = FlatBVH{};
   const size_t n = tris.size();

@@ -30,6 +30,8 @@ template <typename T> struct DefaultInitAlloc : std::allocator<T> {
   }
 };
 template <typename T> using RawVector = std::vector<T, DefaultInitAlloc<T>>;
+// the baked world-space triangles: 480 MB at 10 M triangles, filled by a parallel loop
+using BuildTris = RawVector<BuildTri>;
 
 struct FlatBVH {
   RawVector<float> nodes; // 16 floats per node  (layout: common.cuh)
@@ -53,13 +55,13 @@ struct FlatBVH {
 // wide = true additionally collapses the binary tree into the compressed 8-wide tree
 // (<= 3 triangles per leaf then, the triangle array is laid out wide-node by wide-node and the
 // binary tree's leaves reference the same array).
-void build_bvh(const std::vector<BuildTri>& tris, FlatBVH& out, bool wide = true);
+void build_bvh(const BuildTris& tris, FlatBVH& out, bool wide = true);
 
 
 // Sequential restatement of the device LBVH builder (lbvh.cu / lbvh.h) — CPU tests and the
 // node-for-node check of the device result.  Returns false when the scene is too small or the
 // tree too deep for the traversal stack (the caller then uses build_bvh).
-bool build_lbvh_host(const std::vector<BuildTri>& tris, FlatBVH& out);
+bool build_lbvh_host(const BuildTris& tris, FlatBVH& out);
 
 // Device LBVH builder (lbvh.cu).  h_tris: n world-space triangles in host memory.  With
 // out.built == true, out.nodes / out.tris are device allocations the caller owns; out.built ==

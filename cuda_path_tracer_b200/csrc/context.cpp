@@ -92,7 +92,7 @@ static bool mesh_range(const pt_scene_desc* desc, const pt_object& ob, uint64_t&
 // Every mesh instance baked to world space (the reference re-transforms three vertices per
 // leaf visit instead, path_tracer.cu:57-59).
 static int bake_triangles(const pt_scene_desc* desc, const std::vector<uint32_t>& mesh_objects,
-                          std::vector<BuildTri>& tris)
+                          BuildTris& tris)
 {
   std::vector<uint64_t> first(mesh_objects.size()), count(mesh_objects.size()), out_at(mesh_objects.size());
   uint64_t n_world = 0;
@@ -241,7 +241,7 @@ static int pt_scene_create_impl(const pt_scene_desc* desc, int device, pt_scene*
                                             inst.data(), (uint32_t)inst.size(), n_world, dl);
     if (ce != 0) return cuda_fail((cudaError_t)ce, "device LBVH build");
   }
-  std::vector<BuildTri> tris;
+  BuildTris tris;
   if (!dl.built) {
     const int rc = bake_triangles(desc, mesh_objects, tris);
     if (rc != PT_OK) return rc;
@@ -353,7 +353,7 @@ static int pt_host_bvh_build_impl(const pt_scene_desc* desc, int wide, pt_host_b
   for (uint32_t i = 0; i < desc->n_objects; ++i)
     if (desc->objects[i].type == PT_OBJ_MESH) mesh_objects.push_back(i);
   const double t0 = now_ms();
-  std::vector<BuildTri> tris;
+  BuildTris tris;
   const int rc = bake_triangles(desc, mesh_objects, tris);
   if (rc != PT_OK) return rc;
   auto* h = new pt_host_bvh_impl();

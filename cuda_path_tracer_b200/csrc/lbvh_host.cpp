@@ -22,7 +22,7 @@ static inline float u2f(uint32_t u)
   return f;
 }
 
-bool build_lbvh_host(const std::vector<BuildTri>& tris, FlatBVH& out)
+bool build_lbvh_host(const BuildTris& tris, FlatBVH& out)
 {
   out = FlatBVH{};
   const int n = (int)tris.size();
