@@ -234,3 +234,41 @@ def test_trace_stats_walks_agree_across_tree_layouts():
         assert abs(st["hit_fraction"] - ref_hits) <= 2.0 / n, (name, st["hit_fraction"], ref_hits)
     assert stats["wide8"]["inner_per_ray"] < stats["virtual4"]["inner_per_ray"] < stats["binary"]["inner_per_ray"]
     assert stats["wide8"]["max_stack"] <= 32 and stats["binary"]["max_stack"] <= 60
+
+
+_DIGEST_SCRIPT = r"""
+import hashlib, sys
+import numpy as np
+import cuda_path_tracer_b200 as pt
+from cuda_path_tracer_b200.api import HostBVH
+sd = pt.SceneDescription()
+sd.add_material("m", pt.Material.lambertian((.5, .5, .5)))
+sd.add_mesh("mesh", pt.heightfield(int(sys.argv[1])))
+sd.add_mesh_object("mesh", pt.translate((0, 0, 0)), "m")
+for wide in (False, True):
+    hb = HostBVH(sd, wide=wide)
+    nodes, nodes8, tris = hb.arrays()
+    h = hashlib.md5()
+    for a in (nodes, tris) + ((nodes8,) if wide else ()):
+        h.update(np.ascontiguousarray(a).tobytes())
+    print(h.hexdigest(), int(hb.info.n_bvh_nodes), int(hb.info.bvh_depth))
+"""
+
+
+def test_host_tree_does_not_depend_on_the_thread_count(tmp_path):
+    """Node slots are handed out by range and the flattener derives DFS indices from subtree
+    counts, so the built arrays (binary nodes, triangle order, wide nodes) are byte-identical for
+    any number of OpenMP threads — 90 000 triangles is enough for subtrees to become tasks."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for threads in ("1", "3", "8"):
+        env = dict(os.environ, OMP_NUM_THREADS=threads, PYTHONPATH=root)
+        r = subprocess.run([sys.executable, "-c", _DIGEST_SCRIPT, "212"], env=env, capture_output=True, text=True,
+                           timeout=300)
+        assert r.returncode == 0, r.stderr
+        outs.append(r.stdout)
+    assert outs[0] == outs[1] == outs[2], outs
+    assert len(outs[0].split()) == 6
