@@ -162,63 +162,127 @@ struct Builder {
     nd.sah = nd.box.area() * (float)count * kIsectCost;
   }
 
-  // Bins `n` primitives on the three axes at once into `out` (reset by the caller's contract: this
-  // call OVERWRITES out; chunks are combined with BinSet::merge).
+#if defined(__SSE2__)
+  // Four-lane binning: one min/max pair per box instead of six scalar ones.  Lane 3 is a
+  // don't-care (it carries hi[0] / the id bits and is masked before any arithmetic).
+  struct VBins {
+    struct VBin {
+      __m128 blo, bhi;
+    };
+    VBin vb[3][kBins];
+    uint32_t cnt[3][kBins];
+    uint32_t mask[3];
+  };
+  struct BinXform {
+    __m128 mask3, cblo, sc4, half, top;
+    BinXform(const Box& cb, const float* scale)
+        : mask3(_mm_castsi128_ps(_mm_set_epi32(0, -1, -1, -1))), cblo(_mm_set_ps(0.f, cb.lo[2], cb.lo[1], cb.lo[0])),
+          sc4(_mm_set_ps(0.f, scale[2], scale[1], scale[0])), half(_mm_set1_ps(0.5f)),
+          top(_mm_set1_ps((float)(kBins - 1)))
+    {
+    }
+    // bin indices of the centroid on the three axes (lanes 0-2), clamped to [0, kBins)
+    __m128i bins_of(const Prim& q, __m128& lo, __m128& hi) const
+    {
+      lo = _mm_and_ps(_mm_loadu_ps(q.b.lo), mask3);
+      hi = _mm_and_ps(_mm_loadu_ps(q.b.hi), mask3);
+      const __m128 c = _mm_mul_ps(half, _mm_add_ps(lo, hi));
+      __m128 f = _mm_mul_ps(_mm_sub_ps(c, cblo), sc4);
+      f = _mm_min_ps(_mm_max_ps(f, _mm_setzero_ps()), top);
+      return _mm_cvttps_epi32(f);
+    }
+  };
+  static void store_bins(const VBins& v, BinSet& out)
+  {
+    for (int a = 0; a < 3; ++a) {
+      out.mask[a] = v.mask[a];
+      for (uint32_t m = v.mask[a]; m; m &= m - 1u) {
+        const int k = __builtin_ctz(m);
+        alignas(16) float t[2][4];
+        _mm_store_ps(t[0], v.vb[a][k].blo);
+        _mm_store_ps(t[1], v.vb[a][k].bhi);
+        Bin& bn = out.bin[a][k];
+        for (int c = 0; c < 3; ++c) {
+          bn.box.lo[c] = t[0][c];
+          bn.box.hi[c] = t[1][c];
+        }
+        bn.count = v.cnt[a][k];
+      }
+    }
+  }
+  // Big nodes: every bin is initialised up front and the loop is branch-free (measured: 16 against
+  // 36 TSC ticks per primitive for the first-touch loop on spatially coherent input).
+  __attribute__((noinline)) static void bin_dense(const Prim* p, uint32_t n, const BinXform& x, const bool* use,
+                                                  BinSet& out)
+  {
+    VBins v;
+    const __m128 big = _mm_set1_ps(FLT_MAX), nbig = _mm_set1_ps(-FLT_MAX);
+    for (int a = 0; a < 3; ++a)
+      for (int k = 0; k < kBins; ++k) {
+        v.vb[a][k].blo = big;
+        v.vb[a][k].bhi = nbig;
+        v.cnt[a][k] = 0;
+      }
+    for (uint32_t i = 0; i < n; ++i) {
+      __m128 lo, hi;
+      const __m128i bi = x.bins_of(p[i], lo, hi);
+      const int k0 = _mm_cvtsi128_si32(bi);
+      const int k1 = _mm_cvtsi128_si32(_mm_shuffle_epi32(bi, 0x55));
+      const int k2 = _mm_cvtsi128_si32(_mm_shuffle_epi32(bi, 0xAA));
+      v.vb[0][k0].blo = _mm_min_ps(v.vb[0][k0].blo, lo), v.vb[0][k0].bhi = _mm_max_ps(v.vb[0][k0].bhi, hi);
+      v.vb[1][k1].blo = _mm_min_ps(v.vb[1][k1].blo, lo), v.vb[1][k1].bhi = _mm_max_ps(v.vb[1][k1].bhi, hi);
+      v.vb[2][k2].blo = _mm_min_ps(v.vb[2][k2].blo, lo), v.vb[2][k2].bhi = _mm_max_ps(v.vb[2][k2].bhi, hi);
+      v.cnt[0][k0]++, v.cnt[1][k1]++, v.cnt[2][k2]++;
+    }
+    for (int a = 0; a < 3; ++a) {
+      v.mask[a] = 0u;
+      if (!use[a]) continue; // a flat axis (scale 0) puts everything into bin 0: not a candidate
+      for (int k = 0; k < kBins; ++k)
+        if (v.cnt[a][k]) v.mask[a] |= 1u << k;
+    }
+    store_bins(v, out);
+  }
+  // Small nodes (most of the tree): bins are initialised on first touch, so the cost follows the
+  // node's size, not the 48 bins.
+  static void bin_sparse(const Prim* p, uint32_t n, const BinXform& x, const bool* use, BinSet& out)
+  {
+    VBins v;
+    v.mask[0] = v.mask[1] = v.mask[2] = 0u;
+    for (uint32_t i = 0; i < n; ++i) {
+      __m128 lo, hi;
+      alignas(16) int bi[4];
+      _mm_store_si128(reinterpret_cast<__m128i*>(bi), x.bins_of(p[i], lo, hi));
+      for (int a = 0; a < 3; ++a) {
+        if (!use[a]) continue;
+        const int k = bi[a];
+        VBins::VBin& b = v.vb[a][k];
+        if (v.mask[a] >> k & 1u) {
+          b.blo = _mm_min_ps(b.blo, lo);
+          b.bhi = _mm_max_ps(b.bhi, hi);
+          v.cnt[a][k]++;
+        } else {
+          b.blo = lo, b.bhi = hi;
+          v.cnt[a][k] = 1;
+          v.mask[a] |= 1u << k;
+        }
+      }
+    }
+    store_bins(v, out);
+  }
+#endif
+
+  // Bins `n` primitives on the three axes at once into `out` (this call OVERWRITES out; chunks are
+  // combined with BinSet::merge).
   static void bin_range(const Prim* p, uint32_t n, const Box& cb, const float* scale, BinSet& out)
   {
     out.reset();
 #if defined(__SSE2__)
-    // four-lane version: one min/max pair per box instead of six scalar ones.  Lane 3 is a
-    // don't-care (it carries hi[0] / the id bits and is masked before any arithmetic).
-    struct VBin {
-      __m128 blo, bhi;
-    };
-    VBin vb[3][kBins]; // initialised on first touch (mask)
-    uint32_t cnt[3][kBins];
-    uint32_t mask[3] = {0u, 0u, 0u};
+    const BinXform x(cb, scale);
     const bool use[3] = {scale[0] != 0.f, scale[1] != 0.f, scale[2] != 0.f};
-    const __m128 mask3 = _mm_castsi128_ps(_mm_set_epi32(0, -1, -1, -1));
-    const __m128 cblo = _mm_set_ps(0.f, cb.lo[2], cb.lo[1], cb.lo[0]);
-    const __m128 sc4 = _mm_set_ps(0.f, scale[2], scale[1], scale[0]);
-    const __m128 half = _mm_set1_ps(0.5f), top = _mm_set1_ps((float)(kBins - 1));
-    for (uint32_t i = 0; i < n; ++i) {
-      const __m128 lo = _mm_and_ps(_mm_loadu_ps(p[i].b.lo), mask3);
-      const __m128 hi = _mm_and_ps(_mm_loadu_ps(p[i].b.hi), mask3);
-      const __m128 c = _mm_mul_ps(half, _mm_add_ps(lo, hi));
-      __m128 f = _mm_mul_ps(_mm_sub_ps(c, cblo), sc4);
-      f = _mm_min_ps(_mm_max_ps(f, _mm_setzero_ps()), top);
-      alignas(16) int bi[4];
-      _mm_store_si128(reinterpret_cast<__m128i*>(bi), _mm_cvttps_epi32(f));
-      for (int a = 0; a < 3; ++a) {
-        if (!use[a]) continue;
-        const int k = bi[a];
-        VBin& v = vb[a][k];
-        if (mask[a] >> k & 1u) {
-          v.blo = _mm_min_ps(v.blo, lo);
-          v.bhi = _mm_max_ps(v.bhi, hi);
-          cnt[a][k]++;
-        } else {
-          v.blo = lo, v.bhi = hi;
-          cnt[a][k] = 1;
-          mask[a] |= 1u << k;
-        }
-      }
-    }
-    for (int a = 0; a < 3; ++a) {
-      out.mask[a] = mask[a];
-      for (uint32_t m = mask[a]; m; m &= m - 1u) {
-        const int k = __builtin_ctz(m);
-        alignas(16) float t[2][4];
-        _mm_store_ps(t[0], vb[a][k].blo);
-        _mm_store_ps(t[1], vb[a][k].bhi);
-        Bin& bn = out.bin[a][k];
-        for (int x = 0; x < 3; ++x) {
-          bn.box.lo[x] = t[0][x];
-          bn.box.hi[x] = t[1][x];
-        }
-        bn.count = cnt[a][k];
-      }
-    }
+    if (n >= 64)
+      bin_dense(p, n, x, use, out);
+    else
+      bin_sparse(p, n, x, use, out);
 #else
     for (uint32_t i = 0; i < n; ++i) {
       const Prim& q = p[i];
