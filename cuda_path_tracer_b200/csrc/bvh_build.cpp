@@ -279,7 +279,7 @@ struct Builder {
 #if defined(__SSE2__)
     const BinXform x(cb, scale);
     const bool use[3] = {scale[0] != 0.f, scale[1] != 0.f, scale[2] != 0.f};
-    if (n >= 64)
+    if (n >= 32) // break-even of initialising all 48 bins against the first-touch branches
       bin_dense(p, n, x, use, out);
     else
       bin_sparse(p, n, x, use, out);
