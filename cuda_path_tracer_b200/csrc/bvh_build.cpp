@@ -30,7 +30,6 @@ namespace {
 constexpr int kBins = 16;
 constexpr int kSahDepthLimit = 32; // beyond this depth: balanced median splits
 constexpr float kTravCost = 1.0f;
-constexpr float kIsectCost = 1.0f;
 constexpr uint32_t kParallelBin = 1u << 18; // nodes at least this big are binned by chunks
 constexpr uint32_t kTaskMin = 1u << 13;     // subtrees at least this big become tasks
 
@@ -139,6 +138,10 @@ template <typename T> struct RawArray {
 
 struct Builder {
   int kLeafMax = 4; // 3 when the compressed 8-wide tree is derived from this one
+  // SAH cost of one triangle test relative to one inner-node visit.  1.0 is what every measured
+  // number of this round was taken with; PT_SAH_ISECT / PT_SAH_LEAF are experiment knobs (the
+  // traversal kernel spends 71 SASS instructions per inner visit and ~119 per triangle test).
+  float kIsectCost = 1.0f;
   RawArray<Prim> prims;
   RawArray<BuildNode> nodes;
   // Node slots are handed out by RANGE, not by a shared counter: the subtree over `count`
@@ -764,6 +767,10 @@ void build_bvh(const BuildTris& tris, FlatBVH& out, bool wide)
   };
   Builder B;
   B.kLeafMax = wide ? 3 : 4;
+  if (!wide) {
+    if (const char* v = std::getenv("PT_SAH_LEAF")) B.kLeafMax = std::min(8, std::max(1, std::atoi(v)));
+    if (const char* v = std::getenv("PT_SAH_ISECT")) B.kIsectCost = std::min(16.f, std::max(0.0625f, (float)std::atof(v)));
+  }
   B.prims.resize(n);
   B.nodes.resize(2 * n);
   Box root_box, root_cb;
