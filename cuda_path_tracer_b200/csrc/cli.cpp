@@ -96,7 +96,7 @@ void print_help()
 
 } // namespace
 
-extern "C" int pt_write_png_rgba8(const char* path, const void* rgba, uint32_t width, uint32_t height)
+static int write_png_rgba8(const char* path, const void* rgba, uint32_t width, uint32_t height)
 {
   if (!path || !rgba || !width || !height) return fail(PT_ERR_INVALID, "pt_write_png_rgba8: bad argument");
   const size_t stride = (size_t)width * 4;
@@ -131,7 +131,12 @@ extern "C" int pt_write_png_rgba8(const char* path, const void* rgba, uint32_t w
   return PT_OK;
 }
 
-extern "C" int pt_cli_main(int argc, char** argv)
+extern "C" int pt_write_png_rgba8(const char* path, const void* rgba, uint32_t width, uint32_t height)
+{
+  return guarded("pt_write_png_rgba8", [&] { return write_png_rgba8(path, rgba, width, height); });
+}
+
+static int cli_main(int argc, char** argv)
 {
   std::optional<std::string> filename, output, stats_json, checkpoint, resume;
   std::optional<int> spp;
@@ -316,4 +321,13 @@ extern "C" int pt_cli_main(int argc, char** argv)
   pt_ctx_destroy(ctx);
   pt_scene_destroy(scene);
   return rc;
+}
+
+extern "C" int pt_cli_main(int argc, char** argv)
+{
+  // an exception anywhere in the command-line front end is a failed run, like the reference's panic()
+  const int rc = guarded("cuda_pt", [&] { return cli_main(argc, argv); });
+  if (rc != 0 && std::strstr(pt_last_error(), "cuda_pt: ") == pt_last_error())
+    std::fprintf(stderr, "Panic: %s\n", pt_last_error());
+  return rc == 0 ? 0 : 1;
 }

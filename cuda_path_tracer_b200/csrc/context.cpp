@@ -27,20 +27,6 @@ int cuda_fail(cudaError_t e, const char* what)
   return PT_ERR_CUDA;
 }
 
-// No C++ exception crosses the C ABI: host allocations of multi-gigabyte scenes can throw.
-template <typename F> static int guarded(const char* what, F&& body)
-{
-  try {
-    return body();
-  } catch (const std::bad_alloc&) {
-    return fail(PT_ERR_NOMEM, std::string(what) + ": out of host memory");
-  } catch (const std::exception& e) {
-    return fail(PT_ERR_INVALID, std::string(what) + ": " + e.what());
-  } catch (...) {
-    return fail(PT_ERR_INVALID, std::string(what) + ": unknown failure");
-  }
-}
-
 static double now_ms()
 {
   using namespace std::chrono;

@@ -3,6 +3,8 @@
 #include "../../include/b200pt.h"
 #include "kernels.h"
 
+#include <exception>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -11,6 +13,20 @@ namespace pt {
 void set_error(const std::string& msg);
 int fail(int code, const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what);
+
+// No C++ exception crosses the C ABI: host allocations of multi-gigabyte scenes can throw.
+template <typename F> int guarded(const char* what, F&& body)
+{
+  try {
+    return body();
+  } catch (const std::bad_alloc&) {
+    return fail(PT_ERR_NOMEM, std::string(what) + ": out of host memory");
+  } catch (const std::exception& e) {
+    return fail(PT_ERR_INVALID, std::string(what) + ": " + e.what());
+  } catch (...) {
+    return fail(PT_ERR_INVALID, std::string(what) + ": unknown failure");
+  }
+}
 
 #define PT_CUDA(call)                                                                            \
   do {                                                                                           \
