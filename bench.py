@@ -149,13 +149,10 @@ def run_reference(args, wl, sd):
             "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, **{k: v for k, v in wl.items() if k != "kind"}}}
+    why = None
     try:
         from tests.ref_lib import load_ref_cuda
         ref = load_ref_cuda()
-    except Exception as e:  # no reference build on this box: time the CPU oracle port instead
-        ref = None
-        why = str(e)
-    if ref is not None:
         import torch
         torch.cuda.init()
         rt = ref.tracer(sd, wl["w"], wl["h"], wl["depth"])
@@ -173,7 +170,9 @@ def run_reference(args, wl, sd):
                                   "sample": "full workload on the reference's own CUDA build (oracle/_ref/libref_cuda.so, "
                                             "sm_100, streaming mode); 1 host thread drives it"},
                     e2e={"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
-    else:
+    except Exception as e:  # no reference build or no device on this box: time the CPU oracle port instead
+        why = f"{type(e).__name__}: {e}".splitlines()[0]
+    if why is not None:
         cb = cpu_baseline(sd, wl)
         cb["sample"] += f" [reference CUDA build unavailable: {why}]"
         line.update(value=cb["value"], ms_per_step=None, cpu_baseline=cb,
