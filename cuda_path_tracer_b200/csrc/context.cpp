@@ -159,11 +159,6 @@ static int pt_scene_create_impl(const pt_scene_desc* desc, int device, pt_scene*
     if (desc->materials[i].type < 0 || desc->materials[i].type > 2)
       return fail(PT_ERR_INVALID, "unknown material type");
 
-  int dev_count = 0;
-  PT_CUDA(cudaGetDeviceCount(&dev_count));
-  if (device < 0 || device >= dev_count) return fail(PT_ERR_INVALID, "no such CUDA device");
-  PT_CUDA(cudaSetDevice(device));
-
   const double t0 = now_ms();
   const uint64_t n_tri = desc->n_indices / 3;
 
@@ -196,6 +191,12 @@ static int pt_scene_create_impl(const pt_scene_desc* desc, int device, pt_scene*
       return fail(PT_ERR_INVALID, "unknown object type");
     }
   }
+
+  // every argument check is done: only now is the device touched
+  int dev_count = 0;
+  PT_CUDA(cudaGetDeviceCount(&dev_count));
+  if (device < 0 || device >= dev_count) return fail(PT_ERR_INVALID, "no such CUDA device");
+  PT_CUDA(cudaSetDevice(device));
 
   // PT_BVH=8 additionally derives the compressed 8-wide tree and traverses it (opt-in: on B200
   // it trades the binary walk's L1 wavefront bound for an ALU-pipe bound and measures 10-30 %

@@ -356,3 +356,51 @@ def test_product_never_touches_the_oracle():
     import subprocess
     ldd = subprocess.run(["ldd", pt.LIB_PATH], capture_output=True, text=True).stdout
     assert "oracle" not in ldd and "libref" not in ldd
+
+
+def test_scene_create_rejects_bad_descriptors_before_touching_the_device():
+    """Argument validation comes first and reports through pt_last_error (the reference would
+    read out of bounds or panic): it needs no device, so it is checked here."""
+    lib = pt.load_library()
+    sd = pt.bunny_scene(pt.bunny_like(0), 16, 16)
+
+    def create(mutate):
+        d, keep = sd.to_desc()
+        undo = mutate(d)
+        h = C.c_void_p()
+        rc = lib.pt_scene_create(C.byref(d), 0, C.byref(h))
+        msg = lib.pt_last_error()
+        if undo:
+            undo()
+        assert not h.value
+        return rc, msg
+
+    def null_indices(d):
+        d.indices = None
+    def null_positions(d):
+        d.positions = None
+    def ragged(d):
+        d.n_indices -= 1
+    def bad_index(d):
+        idx = np.ctypeslib.as_array(d.indices, shape=(d.n_indices,))   # the mesh's own array: restored below
+        saved = int(idx[5])
+        idx[5] = d.n_vertices
+        return lambda: idx.__setitem__(5, saved)
+    def bad_material_type(d):
+        d.materials[0].type = 7
+    def bad_object_material(d):
+        d.objects[1].material = d.n_materials
+    def no_materials(d):
+        d.n_materials = 0
+    def null_spheres(d):
+        d.spheres = None
+    def projective(d):
+        d.objects[1].m[3] = 0.5
+
+    for mutate, needle in [(null_indices, b"null"), (null_positions, b"null"), (ragged, b"multiple of 3"),
+                           (bad_index, b"out of range"), (bad_material_type, b"material type"),
+                           (bad_object_material, b"material index"), (no_materials, b"material"),
+                           (null_spheres, b"spheres"), (projective, b"projective")]:
+        rc, msg = create(mutate)
+        assert rc == 1 and needle in msg, (mutate.__name__, rc, msg)
+    assert lib.pt_scene_create(None, 0, None) == 1
