@@ -164,3 +164,29 @@ def test_denoiser_matches_reference_kernel(oracle, ref, filter_size):
     assert err[~taint].max() <= 1e-4, err[~taint].max()
     # the oracle agrees with the reference kernel too (pins oracle.c's denoiser)
     assert np.abs(oref - theirs).max(axis=2)[~taint].max() <= 1e-4
+
+
+@pytest.mark.xfail(strict=False, reason="staged after this round's GPU budget was spent: same code path as "
+                                        "test_denoiser_matches_reference_kernel, not yet run at this size on a device")
+def test_full_size_denoiser_matches_reference_kernel(ref):
+    """BASELINE configs[2] at full size: 1920x1080, A-Trous filter_size 16 (5 iterations), the
+    reference's denoising_kernel vs the product on the reference's own 1-spp frame, max-abs <= 1e-4.
+    The reference reads past the last image row for taps below it (undefined values); what that
+    spoils moves up by 2*step per iteration, 62 rows in total, so the bottom 64 rows are masked."""
+    w, h = 1920, 1080
+    sd = pt.three_balls(w, h)
+    rt = ref.tracer(sd, w, h, 5, megakernel=True)
+    rt.render_timed(sd.camera, 1, 5)
+    c, n, d = rt.download(1), rt.download(2), rt.download(3)
+    rt.upload_frame(c, n, d, sd.camera)
+    rt.denoise(16)
+    theirs = rt.download(4)
+    tr = pt.PathTracer(max_depth=5)
+    tr.create_buffers((w, h), sd)
+    tr.upload_frame(c, n, d, sd.camera)
+    tr.atrous_denoiser.filter_size = 16
+    tr.denoise()
+    ours = tr.download(DB.denoised)
+    err = np.abs(ours - theirs).max(axis=2)[: h - 64]
+    assert np.isfinite(ours[: h - 64]).all()
+    assert err.max() <= 1e-4, (err.max(), np.unravel_index(err.argmax(), err.shape))
