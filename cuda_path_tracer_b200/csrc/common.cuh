@@ -154,7 +154,11 @@ struct DevSphere {
   float cx, cy, cz, radius;
   uint32_t material;
   int32_t object;
-  uint32_t pad[2];
+  // Conservative world-space bound for the pre-reject in sphere_test (set only when the object
+  // transform is a similarity, pre_ok = 1): centre, radius, |centre|_1.
+  float wl1;
+  uint32_t pre_ok;
+  float wx, wy, wz, wr;
 };
 
 struct DevMaterial {
@@ -238,6 +242,9 @@ struct PassParams {
   uint32_t tile_y0;          // first tile row of the band (row-band sharding), else 0
   uint32_t pixel_begin, pixel_end; // pixel range of the band (accumulate)
   FastDiv fd_per_sample, fd_tiles_x, fd_width; // divisors of the bounce-0 index map
+  FastDiv fd_samples, fd_sbx;                  // (tile-major orders)
+  uint32_t sbx;     // 8x8-tile super-blocks per row (order 2)
+  uint32_t order;   // bounce-0 item order: 0 sample-major, 1 tile-major, 2 tile-major in 8x8-tile blocks
   uint32_t samples;
   uint32_t first_iteration;
   uint32_t rng_mode;

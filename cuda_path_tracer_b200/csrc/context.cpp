@@ -55,6 +55,42 @@ static void rows3x4(const float* colmajor, float* out12)
     for (int c = 0; c < 4; ++c) out12[r * 4 + c] = colmajor[c * 4 + r];
 }
 
+// World-space bounding sphere for sphere_test's conservative pre-reject.  Only for similarity
+// transforms (rotation x uniform scale + translation, columns orthogonal and of equal length to
+// 1e-5): there the object-space test's rounding noise has the same relative size in world space,
+// which is what the margins in sphere_test assume.  Anything else keeps the exact test alone.
+static void sphere_world_bound(const float* m, const pt_sphere& s, DevSphere& d)
+{
+  double col[3][3], len2[3];
+  for (int c = 0; c < 3; ++c) {
+    len2[c] = 0.0;
+    for (int r = 0; r < 3; ++r) {
+      col[c][r] = m[c * 4 + r];
+      len2[c] += col[c][r] * col[c][r];
+    }
+  }
+  const double sc2 = (len2[0] + len2[1] + len2[2]) / 3.0;
+  bool ok = sc2 > 0.0 && std::isfinite(sc2) && s.radius > 0.f;
+  for (int a = 0; ok && a < 3; ++a) {
+    if (std::fabs(len2[a] - sc2) > 1e-5 * sc2) ok = false;
+    const int b = (a + 1) % 3;
+    const double dot = col[a][0] * col[b][0] + col[a][1] * col[b][1] + col[a][2] * col[b][2];
+    if (std::fabs(dot) > 1e-5 * sc2) ok = false;
+  }
+  float cw[3];
+  xform_point(m, s.center, cw);
+  d.wx = cw[0], d.wy = cw[1], d.wz = cw[2];
+  d.wr = (float)(std::sqrt(sc2) * (double)s.radius * (1.0 + 1e-5));
+  // magnitudes the world->object transform of a point rounds against: the translation, the
+  // world-space centre and the (scaled) object-space centre
+  d.wl1 = (float)(std::fabs(cw[0]) + std::fabs(cw[1]) + std::fabs(cw[2]) + std::fabs(m[12]) + std::fabs(m[13]) +
+                  std::fabs(m[14]) +
+                  std::sqrt(sc2) * (std::fabs(s.center[0]) + std::fabs(s.center[1]) + std::fabs(s.center[2])));
+  ok = ok && std::isfinite(d.wr) && std::isfinite(d.wl1);
+  static const bool disabled = getenv("PT_SPHERE_PREREJECT") && atoi(getenv("PT_SPHERE_PREREJECT")) == 0;
+  d.pre_ok = ok && !disabled ? 1u : 0u;
+}
+
 } // namespace pt
 
 using namespace pt;
@@ -183,6 +219,7 @@ static int pt_scene_create_impl(const pt_scene_desc* desc, int device, pt_scene*
       d.radius = s.radius;
       d.material = ob.material;
       d.object = (int32_t)i;
+      sphere_world_bound(ob.m, s, d);
       (seen_mesh ? sph_after : sph_before).push_back(d);
     } else if (ob.type == PT_OBJ_MESH) {
       seen_mesh = true;
@@ -694,6 +731,7 @@ int pt_ctx_destroy(pt_ctx* c)
   for (auto ev : c->bounce_events)
     if (ev) cudaEventDestroy(ev);
   for (auto ev : c->prof_events) cudaEventDestroy(ev);
+  for (auto ev : c->prof_pool) cudaEventDestroy(ev);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return PT_OK;
@@ -774,9 +812,16 @@ enum { TAG_EXT0 = 0, TAG_EXT, TAG_SHADE, TAG_COMPACT, TAG_ACC, TAG_DENOISE, TAG_
 static void prof_begin(pt_ctx* c, int tag)
 {
   if (!c->params.profile) return;
-  cudaEvent_t a, b;
-  cudaEventCreate(&a);
-  cudaEventCreate(&b);
+  // events come from a per-context pool: no cudaEventCreate/Destroy on the launch path
+  cudaEvent_t a = nullptr, b = nullptr;
+  for (cudaEvent_t* e : {&a, &b}) {
+    if (!c->prof_pool.empty()) {
+      *e = c->prof_pool.back();
+      c->prof_pool.pop_back();
+    } else {
+      cudaEventCreate(e);
+    }
+  }
   cudaEventRecord(a, c->stream);
   c->prof_events.push_back(a);
   c->prof_events.push_back(b);
@@ -803,8 +848,8 @@ static void prof_collect(pt_ctx* c)
     case TAG_DENOISE: c->stats.ms_denoise += ms; break;
     case TAG_RESOLVE: c->stats.ms_resolve += ms; break;
     }
-    cudaEventDestroy(c->prof_events[2 * i]);
-    cudaEventDestroy(c->prof_events[2 * i + 1]);
+    c->prof_pool.push_back(c->prof_events[2 * i]);
+    c->prof_pool.push_back(c->prof_events[2 * i + 1]);
   }
   c->prof_events.clear();
   c->prof_tags.clear();
@@ -828,9 +873,17 @@ static int render_pass(pt_ctx* c, const pt_camera& cam, uint32_t first_iteration
   pp.samples = samples;
   pp.first_iteration = first_iteration;
   pp.rng_mode = (uint32_t)c->params.rng_mode;
-  static const bool stream_state = getenv("PT_STREAM_STATE") && atoi(getenv("PT_STREAM_STATE")) != 0;
-  pp.stream_state = stream_state ? 1u : 0u;
-  const uint32_t n0 = samples * pp.tiles_x * pp.tiles_y * 32u;
+  pp.stream_state = tunable_stream_state() ? 1u : 0u;
+  pp.order = (uint32_t)tunable_order();
+  pp.fd_samples = make_fastdiv(samples);
+  pp.sbx = (pp.tiles_x + 7) / 8;
+  pp.fd_sbx = make_fastdiv(pp.sbx);
+  // bounce-0 work items: whole warps (8x4 tiles), order 2 pads the tile grid to 8x8-tile blocks
+  const uint64_t n_tiles = pp.order == 2u ? (uint64_t)pp.sbx * ((pp.tiles_y + 7) / 8) * 64u
+                                          : (uint64_t)pp.tiles_x * pp.tiles_y;
+  const uint64_t n0_64 = (uint64_t)samples * n_tiles * 32u;
+  if (n0_64 >= (1ull << 31)) return fail(PT_ERR_INVALID, "wavefront too large: lower samples_per_pass");
+  const uint32_t n0 = (uint32_t)n0_64;
   const uint32_t max_depth = (uint32_t)c->params.max_depth;
   const bool stable = c->params.rng_mode == PT_RNG_SLOT_RESEED;
   if (stable && (c->row_begin != 0 || c->row_end != c->height))

@@ -110,5 +110,6 @@ struct pt_ctx {
 
   pt_stats stats{};
   std::vector<cudaEvent_t> prof_events; // profile=1: pairs, tagged
+  std::vector<cudaEvent_t> prof_pool;   // recycled events
   std::vector<int> prof_tags;
 };

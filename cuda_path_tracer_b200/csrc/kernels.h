@@ -24,6 +24,10 @@ struct PassBuffers {
   uint32_t capacity;   // paths
 };
 
+// experiment switches read once from the environment (wavefront.cu)
+int tunable_order();        // PT_ORDER: bounce-0 item order, see PassParams::order
+int tunable_stream_state(); // PT_STREAM_STATE
+
 // bounce 0: raygen + classification of the primary rays (fills the traverse queue).
 void launch_raygen(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb,
                    const PassParams& pp, uint32_t n_items);

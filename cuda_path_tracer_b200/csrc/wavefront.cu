@@ -90,6 +90,23 @@ struct Hit {
 PT_D bool sphere_test(const DevSphere* __restrict__ sp, f3 o, f3 d, float tmin, float tmax,
                       Hit& h)
 {
+  // Conservative pre-reject in world space (similarity transforms only).  The exact test below
+  // costs two IEEE divisions and a square root before its first early-out; most rays either pass
+  // a sphere by far or leave it behind.  A ray is dropped here only when the exact test must
+  // reject it too: (a) its LINE misses the bounding sphere by more than 64e-6 of the magnitudes
+  // the discriminant is formed from (the exact test's own rounding is ~1e-6 of them; the radius is
+  // widened by 2e-6 of the coordinate magnitudes for the error of the world->object transform),
+  // or (b) the origin lies outside by the same margin and the ray points away, so both roots are
+  // negative and fail t >= t_min > 0.  NaN/inf operands fail both comparisons and fall through.
+  if (sp->pre_ok) {
+    const f3 ocw = o - mk3(sp->wx, sp->wy, sp->wz);
+    const float dd2 = dot3(d, d), bq = dot3(ocw, d), oc2 = dot3(ocw, ocw);
+    const float re = fmaf(fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + sp->wl1, 2e-6f, sp->wr);
+    const float cq = oc2 - re * re;
+    const float b2 = bq * bq, m2 = dd2 * oc2;
+    if (b2 - dd2 * cq < -64e-6f * (b2 + m2)) return false;
+    if (cq > 64e-6f * oc2 && bq > 0.0f && b2 > 1e-8f * m2) return false;
+  }
   const float* I = sp->inv;
   // transform_point(inverse): affine, w == 1 exactly
   f3 oo;
@@ -186,6 +203,26 @@ PT_D void node_test(const DevScene& sc, int node, f3 id, f3 od, float tmin, floa
   t1 = c1max * 1.0000004f >= c1min;
   c0 = __float_as_int(n3.x);
   c1 = __float_as_int(n3.y);
+}
+
+// 64-byte node fetch: four 128-bit loads, or (L256) two 256-bit loads (LDG.E.256: one L1
+// data-pipe pass per 32-byte sector instead of two).
+template <bool L256>
+PT_D void load_node(const float4* __restrict__ np, float4& n0, float4& n1, float4& n2, float4& n3)
+{
+  if (L256) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(n0.x), "=f"(n0.y), "=f"(n0.z), "=f"(n0.w), "=f"(n1.x), "=f"(n1.y), "=f"(n1.z), "=f"(n1.w)
+                 : "l"(np));
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(n2.x), "=f"(n2.y), "=f"(n2.z), "=f"(n2.w), "=f"(n3.x), "=f"(n3.y), "=f"(n3.z), "=f"(n3.w)
+                 : "l"(np + 2));
+  } else {
+    n0 = ldg4(np + 0);
+    n1 = ldg4(np + 1);
+    n2 = ldg4(np + 2);
+    n3 = ldg4(np + 3);
+  }
 }
 
 #define PREFIX_MAX 6
@@ -319,13 +356,11 @@ PT_D void trav_init(Trav& T, f3 o, f3 d, float tmin, float tbest, int start, int
 
 // Inner-node visit: two slab tests against the children's boxes stored in the node, ordered
 // descent (nearer child first), farther child pushed.
+template <bool L256>
 PT_D void trav_inner(const DevScene& sc, Trav& T, int* stack)
 {
-  const float4* np = sc.nodes + (size_t)T.node * 4;
-  const float4 n0 = ldg4(np + 0);
-  const float4 n1 = ldg4(np + 1);
-  const float4 n2 = ldg4(np + 2);
-  const float4 n3 = ldg4(np + 3);
+  float4 n0, n1, n2, n3;
+  load_node<L256>(sc.nodes + (size_t)T.node * 4, n0, n1, n2, n3);
   const float c0lox = n0.x * T.idx - T.odx, c0hix = n0.y * T.idx - T.odx;
   const float c0loy = n0.z * T.idy - T.ody, c0hiy = n0.w * T.idy - T.ody;
   const float c0loz = n2.x * T.idz - T.odz, c0hiz = n2.y * T.idz - T.odz;
@@ -393,11 +428,32 @@ PT_D void trav_leaf(const DevScene& sc, Trav& T, int* stack)
 PT_D bool first_item(const PassParams& pp, uint32_t idx, uint32_t& pid, uint32_t& pixel,
                      uint32_t& s, uint32_t& x, uint32_t& y)
 {
-  const uint32_t per_sample = pp.tiles_x * pp.tiles_y * 32u;
-  s = fd_div(idx, pp.fd_per_sample);
-  const uint32_t r = idx - s * per_sample;
-  const uint32_t tile = r >> 5, lane = r & 31u;
-  const uint32_t ty = fd_div(tile, pp.fd_tiles_x), tx = tile - ty * pp.tiles_x;
+  uint32_t tx, ty;
+  const uint32_t lane = idx & 31u;
+  if (pp.order == 0u) {
+    // sample-major: all tiles of sample 0, then sample 1, ...
+    const uint32_t per_sample = pp.tiles_x * pp.tiles_y * 32u;
+    s = fd_div(idx, pp.fd_per_sample);
+    const uint32_t tile = (idx - s * per_sample) >> 5;
+    ty = fd_div(tile, pp.fd_tiles_x), tx = tile - ty * pp.tiles_x;
+  } else {
+    // tile-major: the pass's samples of one tile are consecutive warps, so the paths in flight at
+    // any moment (and the parked lists they append to) cover a compact patch of the image
+    // instead of a full-width band — a smaller scene working set for L1/L2.  Order 2 also walks
+    // the tiles in 8x8-tile blocks.  The path id, hence every result, is unchanged.
+    const uint32_t group = idx >> 5;
+    uint32_t tile = fd_div(group, pp.fd_samples);
+    s = group - tile * pp.samples;
+    if (pp.order == 1u) {
+      ty = fd_div(tile, pp.fd_tiles_x), tx = tile - ty * pp.tiles_x;
+    } else {
+      const uint32_t sb = tile >> 6, in = tile & 63u;
+      const uint32_t sby = fd_div(sb, pp.fd_sbx), sbxi = sb - sby * pp.sbx;
+      tx = sbxi * 8u + (in & 7u);
+      ty = sby * 8u + (in >> 3);
+      if (tx >= pp.tiles_x || ty >= pp.tiles_y) return false;
+    }
+  }
   x = tx * 8u + (lane & 7u);
   y = (ty + pp.tile_y0) * 4u + (lane >> 3);
   pixel = y * pp.cam.width + x;
@@ -500,6 +556,9 @@ PT_D void stage_prefix(void* smem_dst, const void* gsrc, uint32_t bytes, unsigne
 #endif
 #define EXT_REFILL 16
 #define EXT_INNER_MIN 8
+#ifndef PT_DEFAULT_ORDER
+#define PT_DEFAULT_ORDER 0
+#endif
 
 enum { SRC_QUEUE = 1, SRC_BATCH = 2 };
 
@@ -508,8 +567,11 @@ enum { SRC_QUEUE = 1, SRC_BATCH = 2 };
 // against 15.7 ms for plain L1-cached loads on the bunny frame, profiles/README.md.)
 //
 // stream_state: the parked ray state is fetched with the evict-first policy (ld_state).
-template <int SRC>
-__global__ void __launch_bounds__(EXT_THREADS, EXT_MIN_BLOCKS)
+// MINB: resident CTAs per SM the register allocation is bounded for (8 -> 64 registers, 50 % of
+// the warp slots; 10 -> 48; 12 -> 40); L256: node fetch with two 256-bit loads.  Both are
+// run-time choices between instantiations (PT_TRAV="minb,l256"), measured in profiles/README.md.
+template <int SRC, int MINB, bool L256>
+__global__ void __launch_bounds__(EXT_THREADS, MINB)
 traverse_kernel(const DevScene sc, const PathState ps, const uint32_t* __restrict__ tq,
                 const uint32_t* __restrict__ n_ptr, uint32_t n_host, uint32_t* __restrict__ work,
                 const float4* __restrict__ batch_rays, HitRecord* __restrict__ batch_out,
@@ -575,7 +637,7 @@ traverse_kernel(const DevScene sc, const PathState ps, const uint32_t* __restric
         const uint32_t m_leaf = __ballot_sync(0xffffffffu, has && T.node < 0);
         if (m_inner == 0u) break;
         if (__popc(m_inner) < inner_min && m_leaf != 0u) break;
-        if (inner) trav_inner(sc, T, stack);
+        if (inner) trav_inner<L256>(sc, T, stack);
       }
       if (has && T.node < 0) trav_leaf(sc, T, stack);
     }
@@ -1141,11 +1203,38 @@ chain_kernel(const DevScene sc, const PathState ps, const PassParams pp, const P
 // ================================================================ launchers
 static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
-static int tune(const char* name, int dflt)
+// Experiment switches, read from the environment ONCE per process (not per launch).
+struct Tunables {
+  int refill, inner_min, stream_state, node_min, tri_min, chain_grid, chain_grid0;
+  int trav_minb, trav_l256; // traverse_kernel instantiation (PT_TRAV="minb,l256")
+  int order;                // bounce-0 item order (PT_ORDER)
+};
+static int env_int(const char* name, int dflt)
 {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
 }
+static const Tunables& tunables()
+{
+  static const Tunables t = [] {
+    Tunables t{};
+    t.refill = env_int("PT_REFILL", EXT_REFILL);
+    t.inner_min = env_int("PT_INNER_MIN", EXT_INNER_MIN);
+    t.stream_state = env_int("PT_STREAM_STATE", 0);
+    t.node_min = env_int("PT_NODE_MIN", 12);
+    t.tri_min = env_int("PT_TRI_MIN", 4);
+    t.chain_grid = env_int("PT_CHAIN_GRID", 6);
+    t.chain_grid0 = env_int("PT_CHAIN_GRID0", 24);
+    t.trav_minb = EXT_MIN_BLOCKS;
+    t.trav_l256 = 0;
+    if (const char* v = getenv("PT_TRAV")) sscanf(v, "%d,%d", &t.trav_minb, &t.trav_l256);
+    t.order = env_int("PT_ORDER", PT_DEFAULT_ORDER);
+    return t;
+  }();
+  return t;
+}
+int tunable_order() { return tunables().order; }
+int tunable_stream_state() { return tunables().stream_state; }
 
 void launch_raygen(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb,
                    const PassParams& pp, uint32_t n_items)
@@ -1194,19 +1283,37 @@ static uint32_t persistent_grid(K kern, const LaunchEnv& env, int threads, size_
   return (uint32_t)(env.sms * cache_nb[dev]);
 }
 
+template <int SRC, int MINB, bool L256>
+static void launch_t2v(const LaunchEnv& env, const DevScene& sc, const PathState& ps, const uint32_t* tq,
+                       const uint32_t* n_ptr, uint32_t n_host, uint32_t* work, const float4* rays,
+                       HitRecord* out, uint32_t max_grid)
+{
+  auto kern = traverse_kernel<SRC, MINB, L256>;
+  static int nb[64] = {0};
+  static size_t sm[64] = {0};
+  const Tunables& t = tunables();
+  const uint32_t grid = min(persistent_grid(kern, env, EXT_THREADS, 0, nb, sm), max_grid);
+  kern<<<grid, EXT_THREADS, 0, env.stream>>>(sc, ps, tq, n_ptr, n_host, work, rays, out, t.refill,
+                                             t.inner_min, t.stream_state);
+}
+
 template <int SRC>
 static void launch_t2(const LaunchEnv& env, const DevScene& sc, const PathState& ps, const uint32_t* tq,
                       const uint32_t* n_ptr, uint32_t n_host, uint32_t* work, const float4* rays,
                       HitRecord* out, uint32_t max_grid)
 {
-  auto kern = traverse_kernel<SRC>;
-  static int nb[64] = {0};
-  static size_t sm[64] = {0};
-  const uint32_t grid = min(persistent_grid(kern, env, EXT_THREADS, 0, nb, sm), max_grid);
-  kern<<<grid, EXT_THREADS, 0, env.stream>>>(sc, ps, tq, n_ptr, n_host, work, rays, out,
-                                             tune("PT_REFILL", EXT_REFILL),
-                                             tune("PT_INNER_MIN", EXT_INNER_MIN),
-                                             tune("PT_STREAM_STATE", 0));
+  const Tunables& t = tunables();
+#define PT_T2_CASE(B, L)                                                                           \
+  if (t.trav_minb == B && t.trav_l256 == L)                                                        \
+    return launch_t2v<SRC, B, L != 0>(env, sc, ps, tq, n_ptr, n_host, work, rays, out, max_grid);
+  PT_T2_CASE(8, 0)
+  PT_T2_CASE(8, 1)
+  PT_T2_CASE(10, 0)
+  PT_T2_CASE(10, 1)
+  PT_T2_CASE(12, 0)
+  PT_T2_CASE(12, 1)
+#undef PT_T2_CASE
+  launch_t2v<SRC, EXT_MIN_BLOCKS, false>(env, sc, ps, tq, n_ptr, n_host, work, rays, out, max_grid);
 }
 
 template <int SRC, int THREADS, int BLOCKS>
@@ -1221,8 +1328,8 @@ static void launch_t8(const LaunchEnv& env, const DevScene& sc, const PathState&
   static size_t sm[64] = {0};
   const uint32_t grid = min(persistent_grid(kern, env, THREADS, smem, nb, sm), max_grid);
   kern<<<grid, THREADS, smem, env.stream>>>(sc, ps, tq, n_ptr, n_host, work, rays, out,
-                                            tune("PT_REFILL", EXT_REFILL), tune("PT_NODE_MIN", 12),
-                                            tune("PT_TRI_MIN", 4), n_staged, 0x4B000000u);
+                                            tunables().refill, tunables().node_min,
+                                            tunables().tri_min, n_staged, 0x4B000000u);
 }
 
 template <int SRC>
@@ -1274,8 +1381,8 @@ void launch_chain(const LaunchEnv& env, const DevScene& sc, const PassBuffers& p
   // bunny frame: the primary launch likes a fine grid (its per-item cost varies with how many
   // in-register bounces follow: 6 -> 4.03 ms, 24 -> 3.73 ms), the re-entry launches do not
   // (6 -> 5.09 ms, 24 -> 5.17 ms).
-  const uint32_t grid = (uint32_t)env.sms * (uint32_t)tune("PT_CHAIN_GRID", 6);
-  const uint32_t grid_first = (uint32_t)env.sms * (uint32_t)tune("PT_CHAIN_GRID0", 24);
+  const uint32_t grid = (uint32_t)env.sms * (uint32_t)tunables().chain_grid;
+  const uint32_t grid_first = (uint32_t)env.sms * (uint32_t)tunables().chain_grid0;
   if (iter == 0) {
     chain_kernel<true><<<min(grid_first, cdiv(n_items_first, FULL_THREADS)), FULL_THREADS, 0, env.stream>>>(
         sc, pb.ps, pp, ParkBuf{}, nullptr, n_items_first, pb.park[0], pb.tcounters + 0, max_depth,

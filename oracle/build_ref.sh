@@ -38,10 +38,25 @@ sed -e 's/i < max_bounces \&\& paths_count > 0/i < g_ref_max_bounces \&\& paths_
 for pat in g_ref_max_bounces c_ref_max_bounces REF_STACK_SIZE g_ref_ray_count; do
   grep -q "$pat" "$TMP/path_tracer.cu" || { echo "build_ref.sh: patch '$pat' did not apply" >&2; exit 1; }
 done
-# the reference's flags (cmake/compiler.cmake:65-72) + the arch it never sets (src/lib/CMakeLists.txt:69)
-"$NVCC" -std=c++20 -O3 -DNDEBUG -arch=sm_100 -rdc=true --expt-relaxed-constexpr --extended-lambda -lineinfo \
-  -Xcompiler -fPIC,-fvisibility=hidden -shared \
-  -DREF_PATCHED_PATH_TRACER="\"$TMP/path_tracer.cu\"" -DREF_STACK_SIZE="${REF_STACK_SIZE:-64}" \
-  -I "$HERE/ref_shim" -I "$REF/src/lib" -I "$REF/src" \
-  -o "$OUT/libref_cuda.so" "$HERE/ref_cuda_wrap.cu"
-echo "built $OUT/libref_host.so $OUT/libref_cuda.so"
+# the reference's flags (cmake/compiler.cmake:65-72) + the arch it never sets (src/lib/CMakeLists.txt:69).
+# -rdc=true stays: it IS the reference's configuration (CUDA_SEPARABLE_COMPILATION ON,
+# src/lib/CMakeLists.txt:70, src/CMakeLists.txt:8) and its sources do not compile without it
+# (constant_memory.cuh:6 declares `inline __constant__ GPUCamera`, which nvcc rejects in
+# whole-program mode).  This is a unity build, so the device link sees one object and can inline
+# across the reference's files exactly as its own build's device link does.
+# Two libraries from the same sources:
+#   libref_cuda.so        traversal stack 64: the PARITY CHECKER (deep trees, e.g. 10 M triangles)
+#   libref_cuda_stock.so  traversal stack 24 = the reference's own value: the TIMED BASELINE of
+#                         bench.py --impl reference wherever the reference's tree is at most 23 deep
+build_cuda() { # $1 = stack size, $2 = output
+  "$NVCC" -std=c++20 -O3 -DNDEBUG -arch=sm_100 -rdc=true --expt-relaxed-constexpr --extended-lambda -lineinfo \
+    -Xcompiler -fPIC,-fvisibility=hidden -shared \
+    -DREF_PATCHED_PATH_TRACER="\"$TMP/path_tracer.cu\"" -DREF_STACK_SIZE="$1" \
+    -I "$HERE/ref_shim" -I "$REF/src/lib" -I "$REF/src" \
+    -o "$2" "$HERE/ref_cuda_wrap.cu"
+}
+build_cuda "${REF_STACK_SIZE:-64}" "$OUT/libref_cuda.so" &
+build_cuda 24 "$OUT/libref_cuda_stock.so" &
+wait
+[ -s "$OUT/libref_cuda.so" ] && [ -s "$OUT/libref_cuda_stock.so" ] || { echo "build_ref.sh: CUDA reference build failed" >&2; exit 1; }
+echo "built $OUT/libref_host.so $OUT/libref_cuda.so $OUT/libref_cuda_stock.so"

@@ -2,8 +2,9 @@
 // TEST INFRASTRUCTURE / BASELINE ONLY (built into oracle/_ref/libref_cuda.so by build_ref.sh).
 //
 // This translation unit #includes the reference's sources where they lie under
-// /root/reference/src/lib (unity build: one TU, so no -rdc is needed for the cross-file
-// __device__ generate_ray and the inline __constant__ camera).  No reference source is copied
+// /root/reference/src/lib (unity build: one TU; -rdc=true is still passed because the reference's
+// `inline __constant__` camera, constant_memory.cuh:6, does not compile in whole-program mode and
+// separable compilation is the reference's own setting, src/lib/CMakeLists.txt:70).  No reference source is copied
 // into the repository.  path_tracer.cu alone is included from a build-time patched copy in a
 // temporary directory (REF_PATCHED_DIR) with three sed edits, listed in build_ref.sh:
 //   1. the streaming loop bound  `i < max_bounces`  reads the run-time g_ref_max_bounces
@@ -281,6 +282,34 @@ __attribute__((visibility("default"))) int ref_trace_batch(void* p, const float*
   cudaFree(d_out);
   return e == cudaSuccess ? 0 : 2;
 }
+
+// Depth of the reference's own BVH for a mesh (root = depth 1).  ray_mesh_intersection_test pushes
+// both children of every inner node it enters onto StaticStack<unsigned, 24> (path_tracer.cu:46-73)
+// and never checks for overflow, so the stock stack is correct exactly when depth <= 23.
+__attribute__((visibility("default"))) int ref_bvh_depth(const float* positions, uint64_t n_vertices,
+                                                         const uint32_t* indices, uint64_t n_indices)
+{
+  Mesh mesh;
+  for (uint64_t i = 0; i < n_vertices; ++i)
+    mesh.positions.emplace_back(positions[3 * i], positions[3 * i + 1], positions[3 * i + 2]);
+  mesh.indices.assign(indices, indices + n_indices);
+  const auto bvh = bvh_from_mesh(mesh);
+  std::vector<std::pair<uint32_t, int>> todo{{0u, 1}};
+  int depth = 0;
+  while (!todo.empty()) {
+    const auto [node, d] = todo.back();
+    todo.pop_back();
+    depth = std::max(depth, d);
+    if (!bvh[node].is_leaf()) {
+      todo.push_back({bvh[node].first_child_or_primitive, d + 1});
+      todo.push_back({bvh[node].first_child_or_primitive + 1, d + 1});
+    }
+  }
+  return depth;
+}
+
+// what this library was compiled with (recorded in bench.py's reference line)
+__attribute__((visibility("default"))) int ref_stack_size(void) { return REF_STACK_SIZE; }
 
 // host-side scene build timing (the "Initialization" stage, cli.cpp:86-94): bvh_from_mesh only
 __attribute__((visibility("default"))) double ref_bvh_build_seconds(const float* positions, uint64_t n_vertices,

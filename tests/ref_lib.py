@@ -14,7 +14,8 @@ from cuda_path_tracer_b200.scene_description import Camera, SceneDescription
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 REF_HOST = os.path.join(REF_DIR, "libref_host.so")
-REF_CUDA = os.path.join(REF_DIR, "libref_cuda.so")
+REF_CUDA = os.path.join(REF_DIR, "libref_cuda.so")              # traversal stack 64: the parity checker
+REF_CUDA_STOCK = os.path.join(REF_DIR, "libref_cuda_stock.so")  # stack 24 = the reference's own: the timed baseline
 VP = C.c_void_p
 BVH_NODE_DTYPE = np.dtype([("min", "<f4", 3), ("max", "<f4", 3), ("first", "<u4"), ("count", "<u4")])
 
@@ -108,8 +109,9 @@ class RefCudaTracer:
 
 
 class RefCuda:
-    def __init__(self):
-        L = C.CDLL(REF_CUDA)
+    def __init__(self, path=REF_CUDA):
+        L = C.CDLL(path)
+        self.path = path
         L.ref_tracer_create.restype = VP
         L.ref_tracer_create.argtypes = [C.POINTER(_abi.pt_scene_desc), C.c_uint32, C.c_uint32, C.c_int, C.c_int]
         L.ref_tracer_destroy.argtypes = [VP]
@@ -128,7 +130,11 @@ class RefCuda:
         L.ref_trace_batch.argtypes = [VP, VP, C.c_uint64, VP]
         L.ref_bvh_build_seconds.restype = C.c_double
         L.ref_bvh_build_seconds.argtypes = [VP, C.c_uint64, VP, C.c_uint64, C.POINTER(C.c_uint64)]
+        L.ref_bvh_depth.restype = C.c_int
+        L.ref_bvh_depth.argtypes = [VP, C.c_uint64, VP, C.c_uint64]
+        L.ref_stack_size.restype = C.c_int
         self.lib = L
+        self.stack_size = int(L.ref_stack_size())
 
     def tracer(self, desc, w, h, max_bounces=50, megakernel=False):
         return RefCudaTracer(self.lib, desc, w, h, max_bounces, megakernel)
@@ -141,8 +147,17 @@ class RefCuda:
         return float(s), int(n.value)
 
 
+    def bvh_depth(self, mesh):
+        """Depth of the reference's own tree for `mesh` (host only; root = 1).  The reference's
+        unchecked 24-entry traversal stack is correct exactly when this is <= 23."""
+        pos = np.ascontiguousarray(mesh.positions, dtype=np.float32).reshape(-1, 3)
+        idx = np.ascontiguousarray(mesh.indices, dtype=np.uint32).reshape(-1)
+        return int(self.lib.ref_bvh_depth(pos.ctypes.data, pos.shape[0], idx.ctypes.data, idx.size))
+
+
 _host = None
 _cuda = None
+_cuda_stock = None
 
 
 def have_ref_host():
@@ -160,6 +175,20 @@ def load_ref_host() -> RefHost:
             raise FileNotFoundError(f"{REF_HOST} not built (oracle/build_ref.sh needs /root/reference)")
         _host = RefHost()
     return _host
+
+
+def have_ref_cuda_stock():
+    return os.path.exists(REF_CUDA_STOCK)
+
+
+def load_ref_cuda_stock() -> RefCuda:
+    """The reference with its own traversal stack size (24): the timed baseline."""
+    global _cuda_stock
+    if _cuda_stock is None:
+        if not have_ref_cuda_stock():
+            raise FileNotFoundError(f"{REF_CUDA_STOCK} not built (oracle/build_ref.sh needs /root/reference)")
+        _cuda_stock = RefCuda(REF_CUDA_STOCK)
+    return _cuda_stock
 
 
 def load_ref_cuda() -> RefCuda:

@@ -166,8 +166,6 @@ def test_denoiser_matches_reference_kernel(oracle, ref, filter_size):
     assert np.abs(oref - theirs).max(axis=2)[~taint].max() <= 1e-4
 
 
-@pytest.mark.xfail(strict=False, reason="staged after this round's GPU budget was spent: same code path as "
-                                        "test_denoiser_matches_reference_kernel, not yet run at this size on a device")
 def test_full_size_denoiser_matches_reference_kernel(ref):
     """BASELINE configs[2] at full size: 1920x1080, A-Trous filter_size 16 (5 iterations), the
     reference's denoising_kernel vs the product on the reference's own 1-spp frame, max-abs <= 1e-4.
