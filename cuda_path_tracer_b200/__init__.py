@@ -6,9 +6,10 @@ and this thin ctypes mirror of the reference's PathTracer interface.  No CPU fal
 from ._abi import (BUF_COLOR, BUF_DENOISED, BUF_DEPTH, BUF_FINAL, BUF_NORMAL, LIB_PATH,
                    LibraryMissing, PTError, load_library)
 from .api import (DisplayBufferType, EdgeAvoidingATrousDenoiser, GPUMethod, HIT_DTYPE, PathTracer,
-                  Scene, cli_main, write_image_file)
+                  PathTracerGroup, Scene, cli_main, write_image_file)
 from .scene_description import (Camera, Material, Mesh, SceneDescription, bunny_like, bunny_scene,
-                                compose, heightfield, rotate, scale, terrain_scene, three_balls,
+                                compose, heightfield, many_materials_scene, rotate, scale, terrain_scene,
+                                three_balls,
                                 translate, write_obj)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -129,6 +129,19 @@ SYMBOLS = {
     "pt_ctx_load_state": (C.c_int, [VP, C.c_char_p]),
     "pt_get_stats": (C.c_int, [VP, C.POINTER(pt_stats)]),
     "pt_reset_stats": (C.c_int, [VP]),
+    "pt_group_create": (C.c_int, [C.POINTER(pt_scene_desc), C.POINTER(C.c_int), C.c_int, C.c_uint32, C.c_uint32,
+                                  C.POINTER(pt_params), C.POINTER(VP)]),
+    "pt_group_destroy": (C.c_int, [VP]),
+    "pt_group_size": (C.c_int, [VP]),
+    "pt_group_ctx": (VP, [VP, C.c_int]),
+    "pt_group_device": (C.c_int, [VP, C.c_int]),
+    "pt_group_scene_info": (C.c_int, [VP, C.POINTER(pt_scene_info)]),
+    "pt_group_restart": (C.c_int, [VP]),
+    "pt_group_iteration": (C.c_int, [VP]),
+    "pt_group_render": (C.c_int, [VP, C.POINTER(pt_camera), C.c_int, C.c_int]),
+    "pt_group_render_bands": (C.c_int, [VP, C.POINTER(pt_camera), C.c_int, C.c_int]),
+    "pt_group_sync": (C.c_int, [VP]),
+    "pt_group_get_stats": (C.c_int, [VP, C.POINTER(pt_stats)]),
     "pt_trace_batch": (C.c_int, [VP, VP, C.c_uint64, VP]),
     "pt_write_png_rgba8": (C.c_int, [C.c_char_p, VP, C.c_uint32, C.c_uint32]),
     "pt_cli_main": (C.c_int, [C.c_int, C.POINTER(C.c_char_p)]),

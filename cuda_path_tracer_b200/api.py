@@ -318,12 +318,82 @@ class PathTracer:
         check(load_library().pt_reset_stats(self._ctx))
 
     def _destroy_ctx(self):
-        if self._ctx:
+        if self._ctx and not getattr(self, "_borrowed", False):
             load_library().pt_ctx_destroy(self._ctx)
-            self._ctx = None
+        self._ctx = None
 
     def close(self):
         self._destroy_ctx()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PathTracerGroup:
+    """One process, N GPUs (pt_group_*): a scene replica and a PathTracer context per device,
+    sample-range sharding + one NCCL reduce (render), or row bands of one frame (render_bands).
+    The frame ends up in `root`, an ordinary PathTracer view of device 0's context."""
+
+    def __init__(self, desc: SceneDescription, resolution, devices=None, n_devices: int = 0,
+                 max_depth: int = 50, samples_per_pass: int = 0, profile: bool = False):
+        lib = load_library()
+        d, keep = desc.to_desc()
+        p = _abi.pt_params()
+        lib.pt_params_default(C.byref(p))
+        p.max_depth = max_depth
+        p.samples_per_pass = samples_per_pass
+        p.profile = 1 if profile else 0
+        devs = None
+        if devices is not None:
+            n_devices = len(devices)
+            devs = (C.c_int * n_devices)(*[int(x) for x in devices])
+        h = C.c_void_p()
+        w, hh = int(resolution[0]), int(resolution[1])
+        check(lib.pt_group_create(C.byref(d), devs, int(n_devices), w, hh, C.byref(p), C.byref(h)))
+        del keep
+        self._g = h
+        self._res = (w, hh)
+        self.root = PathTracer(max_depth=max_depth)
+        self.root._ctx = C.c_void_p(lib.pt_group_ctx(self._g, 0))
+        self.root._res = (w, hh)
+        self.root._borrowed = True
+
+    def __len__(self):
+        return int(load_library().pt_group_size(self._g))
+
+    def devices(self):
+        return [int(load_library().pt_group_device(self._g, i)) for i in range(len(self))]
+
+    def restart(self):
+        check(load_library().pt_group_restart(self._g))
+
+    def iteration(self) -> int:
+        return int(load_library().pt_group_iteration(self._g))
+
+    def render(self, camera: Camera, first_iteration: int, n_iterations: int):
+        cam = camera.to_c()
+        check(load_library().pt_group_render(self._g, C.byref(cam), int(first_iteration), int(n_iterations)))
+
+    def render_bands(self, camera: Camera, first_iteration: int, n_iterations: int):
+        cam = camera.to_c()
+        check(load_library().pt_group_render_bands(self._g, C.byref(cam), int(first_iteration), int(n_iterations)))
+
+    def synchronize(self):
+        check(load_library().pt_group_sync(self._g))
+
+    def stats(self) -> _abi.pt_stats:
+        s = _abi.pt_stats()
+        check(load_library().pt_group_get_stats(self._g, C.byref(s)))
+        return s
+
+    def close(self):
+        if self._g:
+            self.root._ctx = None
+            load_library().pt_group_destroy(self._g)
+            self._g = None
 
     def __del__(self):
         try:

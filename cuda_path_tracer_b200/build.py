@@ -16,7 +16,7 @@ LIB = os.path.join(HERE, "libb200pt.so")
 EXE = os.path.join(HERE, "cuda_pt")
 
 SOURCES = ["wavefront.cu", "image_kernels.cu", "context.cpp", "bvh_build.cpp", "lbvh_host.cpp", "lbvh.cu", "hostmath.cpp", "scene_io.cpp",
-           "cli.cpp"]
+           "cli.cpp", "group.cpp"]
 HEADERS = ["common.cuh", "kernels.h", "internal.h", "bvh_build.h", "lbvh.h", "../../include/b200pt.h"]
 
 NVCC_FLAGS = [

@@ -2,7 +2,7 @@
 // the PNG writer.  Mirrors src/main.cpp:9-25, src/lib/configurations.cpp:7-45,
 // src/cli/cli.cpp:62-115, src/lib/assets/assets.cpp:6-23, src/lib/image.cpp:9-22.
 // Additive flags only: --max-depth, --filter-size (enables the denoiser),
-// --device, --rng-mode, --stats-json.
+// --device, --gpus (the reference hard-codes device 0, cli.cpp:71), --rng-mode, --stats-json.
 #include "internal.h"
 
 #include <chrono>
@@ -86,6 +86,8 @@ void print_help()
               "      --filter-size arg  Run the A-Trous denoiser with this filter size\n"
               "      --rng-mode arg     0 = per-pixel stream (megakernel order), 1 = streaming re-seed\n"
               "      --device arg       CUDA device (default 0)\n"
+              "      --gpus arg         Render on this many GPUs of the node (0 = all): sample ranges\n"
+              "                         + one NCCL reduce; row bands when spp < gpus\n"
               "      --stats-json arg   Write run statistics to this file\n"
               "      --checkpoint arg   Save the progressive state (sums + iteration) to this file\n"
               "      --resume arg       Continue from a saved progressive state up to --spp\n"
@@ -140,7 +142,7 @@ static int cli_main(int argc, char** argv)
 {
   std::optional<std::string> filename, output, stats_json, checkpoint, resume;
   std::optional<int> spp;
-  int max_depth = 50, filter_size = 0, device = 0, rng_mode = 0;
+  int max_depth = 50, filter_size = 0, device = 0, rng_mode = 0, gpus = 1;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
     auto value = [&](const char* name) -> const char* {
@@ -184,6 +186,13 @@ static int cli_main(int argc, char** argv)
     } else if (a == "--device" || eq("--device", v)) {
       if (v.empty()) { const char* s = value("device"); if (!s) return 1; v = s; }
       device = std::atoi(v.c_str());
+    } else if (a == "--gpus" || eq("--gpus", v)) {
+      if (v.empty()) { const char* s = value("gpus"); if (!s) return 1; v = s; }
+      gpus = std::atoi(v.c_str());
+      if (gpus < 0) {
+        std::fprintf(stderr, "Option 'gpus' needs a count >= 0 (0 = every visible GPU)\n");
+        return 1;
+      }
     } else if (a == "--rng-mode" || eq("--rng-mode", v)) {
       if (v.empty()) { const char* s = value("rng-mode"); if (!s) return 1; v = s; }
       rng_mode = std::atoi(v.c_str());
@@ -227,6 +236,12 @@ static int cli_main(int argc, char** argv)
     return 1;
   }
 
+  if (std::filesystem::path(*output).extension() != ".png") {
+    // checked before anything is rendered: write_image_file (image.cpp:9-22) fails on these
+    std::fprintf(stderr, "%s has an unrecognized extension\n", output->c_str());
+    return 1;
+  }
+
   Stopwatch sw;
   std::error_code ec;
   const std::filesystem::path scene_path = std::filesystem::canonical(assets / *filename, ec);
@@ -238,9 +253,20 @@ static int cli_main(int argc, char** argv)
     std::fprintf(stderr, "Panic: Unsupported file extension %s!\n", scene_path.extension().string().c_str());
     return 1;
   }
+  // one device: the scene goes straight to it; several: a group (one replica + context per
+  // device, one host thread each, NCCL reduce / gather into the root context)
+  const bool use_group = gpus != 1;
   pt_scene* scene = nullptr;
+  pt_scene_file* sfile = nullptr;
+  pt_group* group = nullptr;
   pt_scene_file_info finfo{};
-  if (pt_scene_load_file(scene_path.string().c_str(), device, &scene, &finfo) != PT_OK) {
+  pt_scene_desc desc{};
+  if (use_group) {
+    if (pt_scene_file_read(scene_path.string().c_str(), &sfile, &desc, &finfo) != PT_OK) {
+      std::fprintf(stderr, "Panic: %s\n", pt_last_error());
+      return 1;
+    }
+  } else if (pt_scene_load_file(scene_path.string().c_str(), device, &scene, &finfo) != PT_OK) {
     std::fprintf(stderr, "Panic: %s\n", pt_last_error());
     return 1;
   }
@@ -252,22 +278,53 @@ static int cli_main(int argc, char** argv)
   params.max_depth = max_depth;
   params.rng_mode = rng_mode;
   pt_ctx* ctx = nullptr;
-  if (pt_ctx_create(scene, (uint32_t)finfo.width, (uint32_t)finfo.height, &params, nullptr, &ctx) != PT_OK) {
+  auto cleanup = [&] {
+    if (group) {
+      pt_group_destroy(group);
+    } else {
+      pt_ctx_destroy(ctx);
+      pt_scene_destroy(scene);
+    }
+    pt_scene_file_free(sfile);
+  };
+  if (use_group) {
+    if (pt_group_create(&desc, nullptr, gpus, (uint32_t)finfo.width, (uint32_t)finfo.height, &params, &group) != PT_OK) {
+      std::fprintf(stderr, "Panic: %s\n", pt_last_error());
+      cleanup();
+      return 1;
+    }
+    ctx = pt_group_ctx(group, 0);
+    gpus = pt_group_size(group);
+  } else if (pt_ctx_create(scene, (uint32_t)finfo.width, (uint32_t)finfo.height, &params, nullptr, &ctx) != PT_OK) {
     std::fprintf(stderr, "Panic: %s\n", pt_last_error());
-    pt_scene_destroy(scene);
+    cleanup();
     return 1;
   }
   pt_sync(ctx);
   std::printf("Start path tracing\n");
   std::printf("spp: %d\n", n_spp);
   std::printf("width: %d, height: %d\n", finfo.width, finfo.height);
+  if (group) std::printf("gpus: %d\n", gpus);
   sw.end_stage("Initialization");
 
   int rc = 0;
   if (resume && pt_ctx_load_state(ctx, resume->c_str()) != PT_OK) rc = 1;
-  pt_ctx_set_max_iterations(ctx, n_spp);
-  // pt_render clips at max_iterations: a resumed context only renders what is missing
-  if (!rc && (pt_render(ctx, &finfo.camera, n_spp) != PT_OK || pt_sync(ctx) != PT_OK)) rc = 1;
+  if (!rc && group) {
+    // a resumed root context only renders what is missing
+    const int done = pt_ctx_iteration(ctx), todo = std::max(0, n_spp - done);
+    if (done > 0) pt_ctx_set_sample_count(ctx, done);
+    int r = PT_OK;
+    if (todo >= gpus || done > 0) {
+      r = pt_group_render(group, &finfo.camera, done, todo);
+    } else {
+      r = pt_group_render_bands(group, &finfo.camera, 0, todo); // fewer samples than GPUs: split the frame
+    }
+    if (r != PT_OK || pt_group_sync(group) != PT_OK) rc = 1;
+  } else if (!rc) {
+    pt_ctx_set_max_iterations(ctx, n_spp);
+    // pt_render clips at max_iterations: a resumed context only renders what is missing
+    if (pt_render(ctx, &finfo.camera, n_spp) != PT_OK || pt_sync(ctx) != PT_OK) rc = 1;
+  }
   sw.end_stage("Path Tracing");
   if (!rc && checkpoint && pt_ctx_save_state(ctx, checkpoint->c_str()) != PT_OK) rc = 1;
   if (!rc && filter_size > 0) {
@@ -279,20 +336,17 @@ static int cli_main(int argc, char** argv)
   }
   std::vector<unsigned char> rgba((size_t)finfo.width * finfo.height * 4);
   if (!rc && pt_resolve_rgba8(ctx, PT_BUF_FINAL, rgba.data(), 0) != PT_OK) rc = 1;
-  if (!rc) {
-    const std::filesystem::path op(*output);
-    if (op.extension() == ".png") {
-      if (pt_write_png_rgba8(output->c_str(), rgba.data(), (uint32_t)finfo.width, (uint32_t)finfo.height) != PT_OK)
-        std::fprintf(stderr, "%s\n", pt_last_error());
-    } else {
-      std::fprintf(stderr, "%s has an unrecognized extension\n", output->c_str());
-    }
-  }
+  // a run that wrote no image is a failed run (write_image_file panics, image.cpp:19-21)
+  if (!rc && pt_write_png_rgba8(output->c_str(), rgba.data(), (uint32_t)finfo.width, (uint32_t)finfo.height) != PT_OK)
+    rc = 1;
   sw.end_stage("Write image file");
   if (rc) std::fprintf(stderr, "Panic: %s\n", pt_last_error());
 
   pt_stats st{};
-  pt_get_stats(ctx, &st);
+  if (group)
+    pt_group_get_stats(group, &st);
+  else
+    pt_get_stats(ctx, &st);
   if (!rc) {
     std::printf("Done path tracing %s!\n\n", filename->c_str());
     sw.report();
@@ -303,23 +357,25 @@ static int cli_main(int argc, char** argv)
       for (auto& e : sw.entries)
         if (e.first == "Path Tracing") render_s = e.second;
       pt_scene_info si{};
-      pt_scene_get_info(scene, &si);
+      if (group)
+        pt_group_scene_info(group, &si);
+      else
+        pt_scene_get_info(scene, &si);
       std::fprintf(f,
                    "{\"scene\": \"%s\", \"width\": %d, \"height\": %d, \"spp\": %d, \"max_depth\": %d, "
                    "\"rays\": %llu, \"render_s\": %.6f, \"mrays_per_s\": %.3f, \"triangles\": %llu, "
-                   "\"bvh_nodes\": %llu, \"bvh_build_ms\": %.3f, \"launches\": %llu",
+                   "\"bvh_nodes\": %llu, \"bvh_build_ms\": %.3f, \"launches\": %llu, \"gpus\": %d",
                    filename->c_str(), finfo.width, finfo.height, n_spp, max_depth,
                    (unsigned long long)st.rays, render_s,
                    render_s > 0 ? (double)st.rays / render_s * 1e-6 : 0.0,
                    (unsigned long long)si.n_world_triangles, (unsigned long long)si.n_bvh_nodes,
-                   si.build_ms, (unsigned long long)st.kernel_launches);
+                   si.build_ms, (unsigned long long)st.kernel_launches, group ? gpus : 1);
       for (auto& e : sw.entries) std::fprintf(f, ", \"%s_s\": %.6f", e.first.c_str(), e.second);
       std::fprintf(f, "}\n");
       std::fclose(f);
     }
   }
-  pt_ctx_destroy(ctx);
-  pt_scene_destroy(scene);
+  cleanup();
   return rc;
 }
 

@@ -177,10 +177,16 @@ void pt_denoise_params_default(pt_denoise_params* p)
 }
 
 // ------------------------------------------------------------------- scene
-static int pt_scene_create_impl(const pt_scene_desc* desc, int device, pt_scene** out)
+// Scene creation in two halves so that a multi-GPU group builds the tree once and uploads it to
+// every device: scene_prepare (host only: validation, sphere/material tables, instance bake + SAH
+// build unless the device builder is asked for) and scene_upload (one device).
+} // extern "C"
+
+namespace pt {
+
+int scene_prepare(const pt_scene_desc* desc, bool host_build, SceneBuild& sb)
 {
-  if (!desc || !out) return fail(PT_ERR_INVALID, "pt_scene_create: null argument");
-  *out = nullptr;
+  if (!desc) return fail(PT_ERR_INVALID, "pt_scene_create: null argument");
   if (desc->n_indices % 3 != 0) return fail(PT_ERR_INVALID, "index count is not a multiple of 3");
   if (desc->n_objects && !desc->objects) return fail(PT_ERR_INVALID, "objects is null");
   if (desc->n_materials == 0 || !desc->materials)
@@ -196,11 +202,8 @@ static int pt_scene_create_impl(const pt_scene_desc* desc, int device, pt_scene*
       return fail(PT_ERR_INVALID, "unknown material type");
 
   const double t0 = now_ms();
-  const uint64_t n_tri = desc->n_indices / 3;
-
-  // ---- objects -> spheres (reference order quirks kept) + baked mesh instances
-  std::vector<DevSphere> sph_before, sph_after;
-  std::vector<uint32_t> mesh_objects;
+  // ---- objects -> spheres (reference order quirks kept) + mesh instances
+  std::vector<DevSphere> sph_after;
   bool seen_mesh = false;
   for (uint32_t i = 0; i < desc->n_objects; ++i) {
     const pt_object& ob = desc->objects[i];
@@ -220,82 +223,58 @@ static int pt_scene_create_impl(const pt_scene_desc* desc, int device, pt_scene*
       d.material = ob.material;
       d.object = (int32_t)i;
       sphere_world_bound(ob.m, s, d);
-      (seen_mesh ? sph_after : sph_before).push_back(d);
+      (seen_mesh ? sph_after : sb.spheres).push_back(d);
     } else if (ob.type == PT_OBJ_MESH) {
       seen_mesh = true;
-      mesh_objects.push_back(i);
+      sb.mesh_objects.push_back(i);
+      uint64_t first, count;
+      if (!mesh_range(desc, ob, first, count))
+        return fail(PT_ERR_INVALID, "mesh object refers to a mesh that does not exist");
     } else {
       return fail(PT_ERR_INVALID, "unknown object type");
     }
   }
+  sb.n_spheres_before = (uint32_t)sb.spheres.size();
+  sb.spheres.insert(sb.spheres.end(), sph_after.begin(), sph_after.end());
 
-  // every argument check is done: only now is the device touched
-  int dev_count = 0;
-  PT_CUDA(cudaGetDeviceCount(&dev_count));
-  if (device < 0 || device >= dev_count) return fail(PT_ERR_INVALID, "no such CUDA device");
-  PT_CUDA(cudaSetDevice(device));
-
-  // PT_BVH=8 additionally derives the compressed 8-wide tree and traverses it (opt-in: on B200
-  // it trades the binary walk's L1 wavefront bound for an ALU-pipe bound and measures 10-30 %
-  // slower, profiles/README.md); the default is the binary tree alone.
-  const char* bvh_env = getenv("PT_BVH");
-  const bool wide = bvh_env && atoi(bvh_env) == 8;
-  // PT_BUILD=lbvh (cuda_pt --fast-build): bake the instances and build the tree on the device
-  // (lbvh.cu) instead of the host bake + SAH builder — tens of milliseconds at 10 M triangles, a
-  // lower-quality tree.  The device builder may decline (tiny scene, tree deeper than the
-  // traversal stack): the host path below then runs as usual.
-  const char* build_env = getenv("PT_BUILD");
-  FlatBVH bvh;
-  DeviceLBVH dl;
-  uint64_t n_world = 0;
-  if (build_env && !strcmp(build_env, "lbvh") && !wide && !mesh_objects.empty()) {
-    std::vector<MeshInstance> inst(mesh_objects.size());
-    for (size_t k = 0; k < mesh_objects.size(); ++k) {
-      const pt_object& ob = desc->objects[mesh_objects[k]];
-      MeshInstance& mi = inst[k];
-      std::memcpy(mi.m, ob.m, sizeof(mi.m));
-      if (!mesh_range(desc, ob, mi.first_tri, mi.n_tri))
-        return fail(PT_ERR_INVALID, "mesh object refers to a mesh that does not exist");
-      mi.out_at = n_world;
-      mi.object = mesh_objects[k];
-      mi.material = ob.material;
-      n_world += mi.n_tri;
-    }
-    const int ce = build_lbvh_device_mesh_c(desc->positions, desc->n_vertices, desc->indices, desc->n_indices,
-                                            inst.data(), (uint32_t)inst.size(), n_world, dl);
-    if (ce != 0) return cuda_fail((cudaError_t)ce, "device LBVH build");
-  }
-  BuildTris tris;
-  if (!dl.built) {
-    const int rc = bake_triangles(desc, mesh_objects, tris);
-    if (rc != PT_OK) return rc;
-    n_world = tris.size();
-  }
-  if (dl.built) {
-    bvh.n_nodes = dl.n_nodes;
-    bvh.n_tris = dl.n_tris;
-    bvh.depth = dl.depth;
-    for (int a = 0; a < 3; ++a) bvh.root_lo[a] = dl.root_lo[a], bvh.root_hi[a] = dl.root_hi[a];
-  } else {
-    build_bvh(tris, bvh, wide);
-  }
-  const double t1 = now_ms();
-
-  std::vector<DevMaterial> mats(desc->n_materials);
+  sb.mats.resize(desc->n_materials);
   for (uint32_t i = 0; i < desc->n_materials; ++i) {
     const pt_material& m = desc->materials[i];
     DevMaterial d{};
     d.type = m.type;
     d.r = m.albedo[0], d.g = m.albedo[1], d.b = m.albedo[2];
     d.param = m.type == PT_MAT_METAL ? m.fuzz : (m.type == PT_MAT_DIELECTRIC ? m.refraction_index : 0.f);
-    mats[i] = d;
+    sb.mats[i] = d;
   }
+  // PT_BVH=8 additionally derives the compressed 8-wide tree and traverses it (opt-in: on B200
+  // it trades the binary walk's L1 wavefront bound for an ALU-pipe bound and measures 10-30 %
+  // slower, profiles/README.md); the default is the binary tree alone.
+  const char* bvh_env = getenv("PT_BVH");
+  sb.wide = bvh_env && atoi(bvh_env) == 8;
+  if (host_build) {
+    BuildTris tris;
+    const int rc = bake_triangles(desc, sb.mesh_objects, tris);
+    if (rc != PT_OK) return rc;
+    sb.n_world = tris.size();
+    build_bvh(tris, sb.bvh, sb.wide);
+    sb.host_built = true;
+  }
+  sb.build_ms = now_ms() - t0;
+  return PT_OK;
+}
 
+int scene_upload(const pt_scene_desc* desc, const SceneBuild& sb, DeviceLBVH* dl, int device, pt_scene** out)
+{
+  *out = nullptr;
+  int dev_count = 0;
+  PT_CUDA(cudaGetDeviceCount(&dev_count));
+  if (device < 0 || device >= dev_count) return fail(PT_ERR_INVALID, "no such CUDA device");
+  PT_CUDA(cudaSetDevice(device));
+  const double t1 = now_ms();
+  const FlatBVH& bvh = sb.bvh;
+  const bool from_device = dl && dl->built;
   pt_scene* sc = new pt_scene();
   sc->device = device;
-  std::vector<DevSphere> spheres = sph_before;
-  spheres.insert(spheres.end(), sph_after.begin(), sph_after.end());
-
   auto upload = [&](const void* src, size_t bytes, void** dst) -> cudaError_t {
     *dst = nullptr;
     if (bytes == 0) return cudaSuccess;
@@ -305,54 +284,118 @@ static int pt_scene_create_impl(const pt_scene_desc* desc, int device, pt_scene*
     return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
   };
   cudaError_t e = cudaSuccess;
-  if (dl.built) {
-    sc->d_nodes = dl.nodes;
-    sc->d_tris = dl.tris;
-    sc->info.device_bytes += ((size_t)dl.n_nodes * 16 + (size_t)dl.n_tris * 12) * 4;
+  if (from_device) {
+    // ownership of the device-built arrays moves to the scene at once: any failure below frees them
+    sc->d_nodes = dl->nodes;
+    sc->d_tris = dl->tris;
+    dl->nodes = nullptr;
+    dl->tris = nullptr;
+    sc->info.device_bytes += ((size_t)dl->n_nodes * 16 + (size_t)dl->n_tris * 12) * 4;
     sc->info.device_build = 1;
   } else {
     if (e == cudaSuccess) e = upload(bvh.nodes.data(), bvh.nodes.size() * 4, &sc->d_nodes);
     if (e == cudaSuccess) e = upload(bvh.tris.data(), bvh.tris.size() * 4, &sc->d_tris);
   }
   if (e == cudaSuccess) e = upload(bvh.nodes8.data(), bvh.nodes8.size() * 4, &sc->d_nodes8);
-  if (e == cudaSuccess) e = upload(spheres.data(), spheres.size() * sizeof(DevSphere), &sc->d_spheres);
-  if (e == cudaSuccess) e = upload(mats.data(), mats.size() * sizeof(DevMaterial), &sc->d_materials);
+  if (e == cudaSuccess) e = upload(sb.spheres.data(), sb.spheres.size() * sizeof(DevSphere), &sc->d_spheres);
+  if (e == cudaSuccess) e = upload(sb.mats.data(), sb.mats.size() * sizeof(DevMaterial), &sc->d_materials);
   if (e != cudaSuccess) {
     pt_scene_destroy(sc);
     return cuda_fail(e, "scene upload");
   }
   const double t2 = now_ms();
 
+  const uint32_t n_nodes = from_device ? dl->n_nodes : bvh.n_nodes;
+  const uint32_t n_tris = from_device ? dl->n_tris : bvh.n_tris;
   sc->dev.nodes = (const float4*)sc->d_nodes;
   sc->dev.tris = (const float4*)sc->d_tris;
   sc->dev.spheres = (const DevSphere*)sc->d_spheres;
   sc->dev.materials = (const DevMaterial*)sc->d_materials;
-  sc->dev.n_spheres = (uint32_t)spheres.size();
-  sc->dev.n_spheres_before = (uint32_t)sph_before.size();
-  sc->dev.n_nodes = bvh.n_nodes;
+  sc->dev.n_spheres = (uint32_t)sb.spheres.size();
+  sc->dev.n_spheres_before = sb.n_spheres_before;
+  sc->dev.n_nodes = n_nodes;
   // the wide traversal keeps a PT_STACK8-entry stack: one node group per level at most
-  const bool use_wide = bvh.n_nodes8 != 0 && bvh.depth8 <= PT_STACK8;
+  const bool use_wide = !from_device && bvh.n_nodes8 != 0 && bvh.depth8 <= PT_STACK8;
   sc->dev.nodes8 = use_wide ? (const uint4*)sc->d_nodes8 : nullptr;
   sc->dev.n_nodes8 = use_wide ? bvh.n_nodes8 : 0u;
   sc->info.n_bvh8_nodes = bvh.n_nodes8;
   sc->info.bvh8_depth = bvh.depth8;
-  sc->dev.n_tris = bvh.n_tris;
+  sc->dev.n_tris = n_tris;
   for (int a = 0; a < 3; ++a) {
-    sc->dev.root_lo[a] = bvh.root_lo[a];
-    sc->dev.root_hi[a] = bvh.root_hi[a];
+    sc->dev.root_lo[a] = from_device ? dl->root_lo[a] : bvh.root_lo[a];
+    sc->dev.root_hi[a] = from_device ? dl->root_hi[a] : bvh.root_hi[a];
   }
-  sc->info.n_triangles = n_tri;
-  sc->info.n_world_triangles = n_world;
-  sc->info.n_bvh_nodes = bvh.n_nodes;
-  sc->info.n_bvh_triangles = bvh.n_tris;
-  sc->info.bvh_depth = bvh.depth;
+  sc->info.n_triangles = desc->n_indices / 3;
+  sc->info.n_world_triangles = sb.n_world;
+  sc->info.n_bvh_nodes = n_nodes;
+  sc->info.n_bvh_triangles = n_tris;
+  sc->info.bvh_depth = from_device ? dl->depth : bvh.depth;
   sc->info.n_objects = desc->n_objects;
-  sc->info.n_spheres = (uint32_t)spheres.size();
+  sc->info.n_spheres = (uint32_t)sb.spheres.size();
   sc->info.n_materials = desc->n_materials;
-  sc->info.build_ms = t1 - t0;
+  sc->info.build_ms = sb.build_ms;
   sc->info.upload_ms = t2 - t1;
   *out = sc;
   return PT_OK;
+}
+
+} // namespace pt
+
+extern "C" {
+
+static int pt_scene_create_impl(const pt_scene_desc* desc, int device, pt_scene** out)
+{
+  if (!desc || !out) return fail(PT_ERR_INVALID, "pt_scene_create: null argument");
+  *out = nullptr;
+  // PT_BUILD=lbvh (cuda_pt --fast-build): bake the instances and build the tree on the device
+  // (lbvh.cu) instead of the host bake + SAH builder — tens of milliseconds at 10 M triangles, a
+  // lower-quality tree.  The device builder may decline (tiny scene, tree deeper than the
+  // traversal stack): the host path then runs as usual.
+  const char* build_env = getenv("PT_BUILD");
+  const char* bvh_env = getenv("PT_BVH");
+  const bool want_lbvh = build_env && !strcmp(build_env, "lbvh") && !(bvh_env && atoi(bvh_env) == 8);
+  SceneBuild sb;
+  int rc = scene_prepare(desc, !want_lbvh, sb); // every argument check happens before the device is touched
+  if (rc != PT_OK) return rc;
+  DeviceLBVH dl;
+  if (want_lbvh) {
+    int dev_count = 0;
+    PT_CUDA(cudaGetDeviceCount(&dev_count));
+    if (device < 0 || device >= dev_count) return fail(PT_ERR_INVALID, "no such CUDA device");
+    PT_CUDA(cudaSetDevice(device));
+    const double t0 = now_ms();
+    if (!sb.mesh_objects.empty()) {
+      std::vector<MeshInstance> inst(sb.mesh_objects.size());
+      uint64_t n_world = 0;
+      for (size_t k = 0; k < sb.mesh_objects.size(); ++k) {
+        const pt_object& ob = desc->objects[sb.mesh_objects[k]];
+        MeshInstance& mi = inst[k];
+        std::memcpy(mi.m, ob.m, sizeof(mi.m));
+        mesh_range(desc, ob, mi.first_tri, mi.n_tri);
+        mi.out_at = n_world;
+        mi.object = sb.mesh_objects[k];
+        mi.material = ob.material;
+        n_world += mi.n_tri;
+      }
+      const int ce = build_lbvh_device_mesh_c(desc->positions, desc->n_vertices, desc->indices, desc->n_indices,
+                                              inst.data(), (uint32_t)inst.size(), n_world, dl);
+      if (ce != 0) return cuda_fail((cudaError_t)ce, "device LBVH build");
+      if (dl.built) sb.n_world = n_world;
+    }
+    if (!dl.built) { // declined: host bake + SAH build
+      BuildTris tris;
+      rc = bake_triangles(desc, sb.mesh_objects, tris);
+      if (rc != PT_OK) return rc;
+      sb.n_world = tris.size();
+      build_bvh(tris, sb.bvh, false);
+      sb.host_built = true;
+    }
+    sb.build_ms += now_ms() - t0;
+  }
+  rc = scene_upload(desc, sb, &dl, device, out);
+  if (dl.nodes) cudaFree(dl.nodes); // not taken over by a scene (upload failed early)
+  if (dl.tris) cudaFree(dl.tris);
+  return rc;
 }
 
 int pt_scene_create(const pt_scene_desc* desc, int device, pt_scene** out)

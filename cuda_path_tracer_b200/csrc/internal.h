@@ -1,6 +1,7 @@
 // internal.h — host-side structures behind the opaque C-ABI handles.
 #pragma once
 #include "../../include/b200pt.h"
+#include "bvh_build.h"
 #include "kernels.h"
 
 #include <exception>
@@ -47,6 +48,20 @@ Mat4 mat4_inverse(const Mat4& a);
 bool mat4_decompose_trs(const Mat4& a, float pos[3], float quat_wxyz[4]);
 void mat4_from_camera(const pt_camera& cam, float out12[12]);
 DevCamera make_dev_camera(const pt_camera& cam, uint32_t w, uint32_t h);
+
+// host half of scene creation (context.cpp): built once, uploaded to one or several devices
+struct SceneBuild {
+  std::vector<DevSphere> spheres; // spheres preceding the first mesh object first
+  uint32_t n_spheres_before = 0;
+  std::vector<uint32_t> mesh_objects;
+  std::vector<DevMaterial> mats;
+  FlatBVH bvh;
+  uint64_t n_world = 0;
+  double build_ms = 0.0;
+  bool wide = false, host_built = false;
+};
+int scene_prepare(const pt_scene_desc* desc, bool host_build, SceneBuild& sb);
+int scene_upload(const pt_scene_desc* desc, const SceneBuild& sb, DeviceLBVH* dl, int device, pt_scene** out);
 
 // parsed scene file (scene_io.cpp)
 struct SceneFile {

@@ -87,6 +87,8 @@ struct Hit {
 // re-normalised while t_min/t_max stay world-space; the reported t is the
 // world-space distance; the normal is transformed by the inverse transpose and
 // not re-normalised.
+// PRE = false: the caller knows the sphere is hit (resolve_hit rebuilding an accepted hit).
+template <bool PRE = true>
 PT_D bool sphere_test(const DevSphere* __restrict__ sp, f3 o, f3 d, float tmin, float tmax,
                       Hit& h)
 {
@@ -98,7 +100,7 @@ PT_D bool sphere_test(const DevSphere* __restrict__ sp, f3 o, f3 d, float tmin, 
   // widened by 2e-6 of the coordinate magnitudes for the error of the world->object transform),
   // or (b) the origin lies outside by the same margin and the ray points away, so both roots are
   // negative and fail t >= t_min > 0.  NaN/inf operands fail both comparisons and fall through.
-  if (sp->pre_ok) {
+  if (PRE && sp->pre_ok) {
     const f3 ocw = o - mk3(sp->wx, sp->wy, sp->wz);
     const float dd2 = dot3(d, d), bq = dot3(ocw, d), oc2 = dot3(ocw, ocw);
     const float re = fmaf(fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + sp->wl1, 2e-6f, sp->wr);
@@ -306,7 +308,7 @@ PT_D bool resolve_hit(const DevScene& sc, f3 o, f3 d, float tmin, float t_aux, u
     hit = true;
   } else if (code & AUX_VALUE) {
     // same root as when it was accepted: any t_max >= the accepted t selects it again
-    hit = sphere_test(sc.spheres + ((code & AUX_VALUE) - 1u), o, d, tmin, FLT_MAX, h);
+    hit = sphere_test<false>(sc.spheres + ((code & AUX_VALUE) - 1u), o, d, tmin, FLT_MAX, h);
   }
   if (code & (AUX_TRI | AUX_PENDING)) {
     for (uint32_t i = sc.n_spheres_before; i < sc.n_spheres; ++i) {
@@ -557,7 +559,7 @@ PT_D void stage_prefix(void* smem_dst, const void* gsrc, uint32_t bytes, unsigne
 #define EXT_REFILL 16
 #define EXT_INNER_MIN 8
 #ifndef PT_DEFAULT_ORDER
-#define PT_DEFAULT_ORDER 0
+#define PT_DEFAULT_ORDER 2 // measured: bunny +0.5 %, bunny_1m +1.5 %, terrain +5.5 % over order 0
 #endif
 
 enum { SRC_QUEUE = 1, SRC_BATCH = 2 };
@@ -1225,7 +1227,7 @@ static const Tunables& tunables()
     t.tri_min = env_int("PT_TRI_MIN", 4);
     t.chain_grid = env_int("PT_CHAIN_GRID", 6);
     t.chain_grid0 = env_int("PT_CHAIN_GRID0", 24);
-    t.trav_minb = EXT_MIN_BLOCKS;
+    t.trav_minb = 0; // 0 = choose by scene size (launch_t2)
     t.trav_l256 = 0;
     if (const char* v = getenv("PT_TRAV")) sscanf(v, "%d,%d", &t.trav_minb, &t.trav_l256);
     t.order = env_int("PT_ORDER", PT_DEFAULT_ORDER);
@@ -1303,8 +1305,18 @@ static void launch_t2(const LaunchEnv& env, const DevScene& sc, const PathState&
                       HitRecord* out, uint32_t max_grid)
 {
   const Tunables& t = tunables();
+  int minb = t.trav_minb, l256 = t.trav_l256;
+  if (minb == 0) {
+    // Measured (profiles/README.md, round 2): a tree that lives in L1/L2 is bound by L1 data-pipe
+    // wavefronts and likes the 256-bit node fetch (bunny: traverse -3 %); a scene far beyond the
+    // 126 MB L2 is bound by DRAM latency and likes 12 CTAs per SM at 40 registers (10 M-triangle
+    // terrain: -5 %); in between (2.6 M triangles) both lose 2 %.
+    const size_t node_bytes = (size_t)sc.n_nodes * 64, scene_bytes = node_bytes + (size_t)sc.n_tris * 48;
+    minb = scene_bytes > (512ull << 20) ? 12 : EXT_MIN_BLOCKS;
+    l256 = node_bytes <= (2ull << 20) ? 1 : 0;
+  }
 #define PT_T2_CASE(B, L)                                                                           \
-  if (t.trav_minb == B && t.trav_l256 == L)                                                        \
+  if (minb == B && l256 == L)                                                                      \
     return launch_t2v<SRC, B, L != 0>(env, sc, ps, tq, n_ptr, n_host, work, rays, out, max_grid);
   PT_T2_CASE(8, 0)
   PT_T2_CASE(8, 1)

@@ -373,6 +373,34 @@ def bunny_scene(mesh: Mesh | None = None, width=1920, height=1080, spp=10) -> Sc
     return s
 
 
+def many_materials_scene(width=1920, height=1080, spp=16, subdiv=4) -> SceneDescription:
+    """Material-divergence stress for the ray-binning experiment (reference hint: the commented-out
+    sort by material_id, path_tracer.cu:439-446): a 5 x 3 grid of instances of one mesh, neighbours
+    alternating between lambertian, metal and dielectric, over the ground sphere and under three
+    free-standing spheres of the three types."""
+    s = SceneDescription()
+    s.filename = "synthetic/many_materials.json"
+    s.add_material("ground", Material.lambertian((0.8, 0.8, 0.8)))
+    palette = [Material.lambertian((0.8, 0.3, 0.3)), Material.metal((0.8, 0.8, 0.8), 0.05), Material.dielectric(1.5),
+               Material.lambertian((0.3, 0.8, 0.3)), Material.metal((0.8, 0.6, 0.2), 0.4), Material.dielectric(1.3)]
+    for i, m in enumerate(palette):
+        s.add_material(f"m{i}", m)
+    s.add_mesh("models/bunny.obj", bunny_like(subdiv))
+    s.add_sphere(100.0, translate((0.0, -100.5, -1.0)), "ground")
+    k = 0
+    for row in range(3):
+        for col in range(5):
+            x, z = (col - 2) * 0.9, -1.6 - row * 0.9
+            s.add_mesh_object("models/bunny.obj", compose(scale(0.6), translate((x, -0.5, z))), f"m{k % len(palette)}")
+            k += 1
+    for i, x in enumerate((-1.2, 0.0, 1.2)):
+        s.add_sphere(0.25, translate((x, 0.55, -1.2)), f"m{(i * 2 + 1) % len(palette)}")
+    s.camera = Camera((0.0, 0.4, 1.0), (1.0, 0.0, 0.0, 0.0), math.radians(60.0))
+    s.resolution = (width, height)
+    s.spp = spp
+    return s
+
+
 def terrain_scene(n: int = 2236, width=3840, height=2160, spp=16, seed=0) -> SceneDescription:
     """BASELINE.json configs[3]: one procedural ~2*n^2-triangle mesh, diffuse albedo 0.7."""
     s = SceneDescription()

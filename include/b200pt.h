@@ -132,7 +132,9 @@ typedef struct pt_params {
   int32_t max_iterations; /* PathTracer::max_iterations; <=0 means unlimited */
   int32_t samples_per_pass; /* 0 = auto: batch several iterations into one wavefront */
   int32_t profile;        /* 1 = time every kernel with CUDA events (pt_get_stats) */
-  int32_t sort_rays;      /* reserved */
+  int32_t sort_rays;      /* 1 = bin the traversed rays by what they hit (miss / material type)
+                             before shading: the reference's commented-out sort by material_id
+                             (path_tracer.cu:439-446).  Off by default: measured slower. */
   int32_t reserved[2];
 } pt_params;
 
@@ -323,6 +325,40 @@ PT_API int pt_ctx_load_state(pt_ctx* ctx, const char* path);
 
 PT_API int pt_get_stats(pt_ctx* ctx, pt_stats* stats);
 PT_API int pt_reset_stats(pt_ctx* ctx);
+
+/* --- multi-GPU group: one process, N devices ---------------------------------------------
+ * The reference renders on device 0 only (cuda::init_CUDA / cudaSetDevice(0), src/cli/cli.cpp:71).
+ * A group holds one scene replica and one integrator context per device (the BVH is built once
+ * on the host and uploaded to each), drives them from one host thread per device and combines
+ * their frames over NVLink with NCCL (bound at run time; a one-device group never loads it).
+ *   devices == NULL: devices 0 .. n_devices-1;  n_devices <= 0: every visible device.
+ * After a render the frame lives in the ROOT context, pt_group_ctx(g, 0): denoise, resolve,
+ * download and save it through the ordinary pt_* calls on that context. */
+typedef struct pt_group pt_group;
+PT_API int pt_group_create(const pt_scene_desc* desc, const int* devices, int n_devices, uint32_t width,
+                           uint32_t height, const pt_params* params, pt_group** out);
+PT_API int pt_group_destroy(pt_group* group);
+PT_API int pt_group_size(const pt_group* group);
+PT_API pt_ctx* pt_group_ctx(pt_group* group, int i);
+PT_API int pt_group_device(const pt_group* group, int i);
+PT_API int pt_group_scene_info(const pt_group* group, pt_scene_info* info);
+/* PathTracer::restart for every member; also leaves band mode. */
+PT_API int pt_group_restart(pt_group* group);
+/* Samples per pixel the root's frame holds == PathTracer::iteration(). */
+PT_API int pt_group_iteration(const pt_group* group);
+/* Sample-range sharding (progressive / high spp): iterations [first, first+n) are split into
+ * one contiguous range per device, rendered with the seeds a single GPU would use, and summed
+ * into the root's running sums with ONE ncclReduce of 32 B/pixel.  Equal to pt_render_range on
+ * one device up to float re-association of the sums.  Asynchronous like pt_render. */
+PT_API int pt_group_render(pt_group* group, const pt_camera* camera, int first_iteration, int n_iterations);
+/* Row-band sharding of ONE frame (the 1-spp interactive path): device i renders rows
+ * [r_i, r_i+1) (multiples of 4 rows) of every iteration in the range; the bands are gathered in
+ * place into the root's frame with ncclSend/ncclRecv.  Identical to the single-device frame. */
+PT_API int pt_group_render_bands(pt_group* group, const pt_camera* camera, int first_iteration,
+                                 int n_iterations);
+PT_API int pt_group_sync(pt_group* group);
+/* Sums over the members (rays, launches, kernel times). */
+PT_API int pt_group_get_stats(pt_group* group, pt_stats* stats);
 
 /* --- parity hook: closest hit of a ray batch == ray_scene_intersection_test
  *     (path_tracer.cu:110-128).  rays8 = n x {ox,oy,oz,t_min,dx,dy,dz,t_max}

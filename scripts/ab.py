@@ -13,7 +13,7 @@ for setting in args:
         k, v = kv.split("=", 1); env[k] = v
     try:
       r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", wl, "--steps", steps, "--warmup", "3",
-                        "--no-cpu-baseline"], env=env, capture_output=True, text=True, timeout=150)
+                        "--no-cpu-baseline", "--no-secondary"], env=env, capture_output=True, text=True, timeout=150)
     except subprocess.TimeoutExpired:
       print(wl, setting, "TIMEOUT", flush=True); continue
     try:

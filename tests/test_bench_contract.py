@@ -31,3 +31,29 @@ def test_reference_arm_does_no_work_on_other_ranks():
                         "--workload", "three_balls", "--steps", "1", "--warmup", "0"], env=env, capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_strong_scaling_shares_partition_the_sample_range(monkeypatch):
+    """bench.py --gpus N splits the frame's spp into N disjoint sample ranges that cover it."""
+    sys.path.insert(0, ROOT)
+    import bench
+    for spp in (1, 16, 64, 1024):
+        for world in (1, 2, 3, 4, 8):
+            seen = []
+            for rank in range(world):
+                monkeypatch.setenv("WORLD_SIZE", str(world))
+                monkeypatch.setenv("RANK", str(rank))
+                first, n = bench.Dist().share(spp)
+                seen.extend(range(first, first + n))
+            assert seen == list(range(spp)), (spp, world)
+
+
+def test_both_arms_describe_the_workload_with_the_same_config_keys():
+    sys.path.insert(0, ROOT)
+    import bench
+    for name in bench.WORKLOADS:
+        c = bench.config_of(name)
+        assert c["workload"] == name and "l2" in c and {"w", "h", "spp", "depth"} <= set(c)
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    # one function builds `config` for both arms; neither arm adds keys to it afterwards
+    assert src.count('"config": config_of(') >= 3 and 'line["config"][' not in src

@@ -58,6 +58,12 @@ def test_cli_grammar_messages_and_exit_codes(tmp_path, tmp_path_factory):
     assert r.returncode == 1 and "Usage: cuda_pt [options] <filename>" in r.stderr
     r = _run(["-h"], cwd)
     assert r.returncode == 0 and "A Path Tracer written in CUDA" in r.stdout and "--spp" in r.stdout
+    assert "--gpus" in r.stdout
+    r = _run(["--gpus", "-2", "-o", "x.png", "scenes/bunny.json"], cwd)
+    assert r.returncode == 1 and "gpus" in r.stderr
+    # an output the writer cannot produce is refused BEFORE anything is rendered, exit code 1
+    r = _run(["-o", "x.jpeg", "scenes/bunny.json"], cwd)
+    assert r.returncode == 1 and "unrecognized extension" in r.stderr and "Start path tracing" not in r.stdout
     r = _run(["--no-such-flag", "scenes/bunny.json"], cwd)
     assert r.returncode == 1 and "does not exist" in r.stderr
     r = _run(["--spp"], cwd)
