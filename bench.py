@@ -225,7 +225,8 @@ def bench_render(name, steps, warmup, D: Dist, with_clocks=True):
     scene = pt.Scene.from_description(sd, device=D.local_rank)
     stream = torch.cuda.Stream()
     tracer = pt.PathTracer(max_depth=depth, profile=True, stream=stream.cuda_stream,
-                           samples_per_pass=int(os.environ.get("PT_SPP_PASS", "0")))
+                           samples_per_pass=int(os.environ.get("PT_SPP_PASS", "0")),
+                           sort_rays=os.environ.get("PT_SORT_RAYS", "0") == "1")
     tracer.max_iterations = 1 << 30
     tracer.create_buffers((W, H), scene)
     sums = torch.zeros(W * H * 8, dtype=torch.float32, device="cuda")

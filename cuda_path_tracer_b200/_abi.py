@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb200pt.so")
+# B200PT_LIB selects another build of the same library (the bounds-checked debug build)
+LIB_PATH = os.environ.get("B200PT_LIB") or os.path.join(HERE, "libb200pt.so")
 
 PT_OK = 0
 MAT_DIFFUSE, MAT_METAL, MAT_DIELECTRIC = 0, 1, 2

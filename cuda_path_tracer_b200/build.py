@@ -13,6 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200pt.so")
+LIB_DEBUG = os.path.join(HERE, "libb200pt_debug.so")
 EXE = os.path.join(HERE, "cuda_pt")
 
 SOURCES = ["wavefront.cu", "image_kernels.cu", "context.cpp", "bvh_build.cpp", "lbvh_host.cpp", "lbvh.cu", "hostmath.cpp", "scene_io.cpp",
@@ -41,6 +42,18 @@ def _stale(target: str, deps: list[str]) -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
+def build_debug(verbose: bool = False) -> str:
+    """libb200pt_debug.so: the same sources with -DPT_BOUNDS_CHECK (device-side index checks that
+    trap; common.cuh).  Select it with B200PT_LIB=<path> and run the GPU parity suite against it:
+    scripts/run_bounds_check.sh.  Not built by default."""
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [_nvcc(), *NVCC_FLAGS, "-DPT_BOUNDS_CHECK", "-shared", "-o", LIB_DEBUG, *srcs, "-lz", "-lgomp"]
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.run(cmd, check=True, cwd=CSRC)
+    return LIB_DEBUG
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
     deps = srcs + [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
@@ -60,4 +73,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--debug" in sys.argv:
+        print(build_debug(verbose="-v" in sys.argv))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

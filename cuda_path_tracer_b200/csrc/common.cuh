@@ -15,6 +15,25 @@
 #define PT_HD __host__ __device__ __forceinline__
 #define PT_D __device__ __forceinline__
 
+// Debug build (python -m cuda_path_tracer_b200.build --debug -> libb200pt_debug.so, selected with
+// B200PT_LIB): every index into the traversal stack, the tree, the triangle array, the parked-state
+// buffers and the bin lists is checked on the device; a violation prints what and where and traps
+// (the launch fails, the parity suite turns red).  compute-sanitizer is not available on the GPU
+// pool, this is its stand-in.  The release build compiles the checks away.
+#ifdef PT_BOUNDS_CHECK
+#include <stdio.h>
+#define PT_CHECK(cond, what)                                                                       \
+  do {                                                                                             \
+    if (!(cond)) {                                                                                 \
+      printf("b200pt bounds violation: %s (%s:%d, block %d thread %d)\n", what, __FILE__, __LINE__, \
+             (int)blockIdx.x, (int)threadIdx.x);                                                   \
+      __trap();                                                                                    \
+    }                                                                                              \
+  } while (0)
+#else
+#define PT_CHECK(cond, what) ((void)0)
+#endif
+
 namespace pt {
 
 // ---------------------------------------------------------------- float3 math
@@ -210,6 +229,18 @@ struct ParkBuf {
   uint32_t* pid;
 };
 
+// Ray binning (pt_params.sort_rays; the reference's commented-out sort by material_id,
+// path_tracer.cu:439-446): traverse_kernel appends the slot of every ray it finishes to the list
+// of its bin — 0 = no triangle hit (sky or a sphere), 1 + material type of the triangle hit
+// otherwise — and the following chain launch walks the lists bin after bin, so that the lanes of
+// a warp shade the same kind of surface.  list[b * cap + k], count[b]; null list = off.
+#define PT_BINS 4
+struct BinLists {
+  uint32_t* list;
+  uint32_t* count; // PT_BINS counters of this iteration
+  uint32_t cap;
+};
+
 // Exact unsigned division by a run-time constant (Granlund & Montgomery 1994, round-up method):
 // the bounce-0 index map divides three times per primary sample, ~20 instructions each as a
 // plain `/`.  q = (t + ((n - t) >> sh1)) >> sh2 with t = umulhi(m, n).
@@ -246,6 +277,7 @@ struct PassParams {
   uint32_t sbx;     // 8x8-tile super-blocks per row (order 2)
   uint32_t order;   // bounce-0 item order: 0 sample-major, 1 tile-major, 2 tile-major in 8x8-tile blocks
   uint32_t samples;
+  uint32_t capacity; // path slots per buffer (bounds checks)
   uint32_t first_iteration;
   uint32_t rng_mode;
   uint32_t stream_state; // path-state streams use the evict-first cache policy (PT_STREAM_STATE)

@@ -55,6 +55,26 @@ static void rows3x4(const float* colmajor, float* out12)
     for (int c = 0; c < 4; ++c) out12[r * 4 + c] = colmajor[c * 4 + r];
 }
 
+// FNV-1a fingerprint of a scene description: the tables in full, the mesh arrays sampled (every
+// 257th vertex and index) together with their sizes.  Stored in progressive-state files so that a
+// render is never resumed against a different scene.
+static uint64_t description_hash(const pt_scene_desc* d)
+{
+  uint64_t h = 1469598103934665603ull;
+  auto mix = [&](const void* p, size_t n) {
+    const unsigned char* b = (const unsigned char*)p;
+    for (size_t i = 0; i < n; ++i) h = (h ^ b[i]) * 1099511628211ull;
+  };
+  mix(&d->n_vertices, 8), mix(&d->n_indices, 8), mix(&d->n_objects, 4), mix(&d->n_spheres, 4);
+  mix(&d->n_materials, 4), mix(&d->n_meshes, 4);
+  for (uint32_t i = 0; i < d->n_objects; ++i) mix(&d->objects[i], sizeof(pt_object));
+  for (uint32_t i = 0; i < d->n_spheres; ++i) mix(&d->spheres[i], sizeof(pt_sphere));
+  for (uint32_t i = 0; i < d->n_materials; ++i) mix(&d->materials[i], sizeof(pt_material));
+  for (uint64_t i = 0; i < d->n_vertices; i += 257) mix(d->positions + 3 * i, 12);
+  for (uint64_t i = 0; i < d->n_indices; i += 257) mix(d->indices + i, 4);
+  return h;
+}
+
 // World-space bounding sphere for sphere_test's conservative pre-reject.  Only for similarity
 // transforms (rotation x uniform scale + translation, columns orthogonal and of equal length to
 // 1e-5): there the object-space test's rounding noise has the same relative size in world space,
@@ -236,6 +256,7 @@ int scene_prepare(const pt_scene_desc* desc, bool host_build, SceneBuild& sb)
   }
   sb.n_spheres_before = (uint32_t)sb.spheres.size();
   sb.spheres.insert(sb.spheres.end(), sph_after.begin(), sph_after.end());
+  sb.content_hash = description_hash(desc);
 
   sb.mats.resize(desc->n_materials);
   for (uint32_t i = 0; i < desc->n_materials; ++i) {
@@ -335,6 +356,7 @@ int scene_upload(const pt_scene_desc* desc, const SceneBuild& sb, DeviceLBVH* dl
   sc->info.n_materials = desc->n_materials;
   sc->info.build_ms = sb.build_ms;
   sc->info.upload_ms = t2 - t1;
+  sc->content_hash = sb.content_hash;
   *out = sc;
   return PT_OK;
 }
@@ -601,6 +623,8 @@ static void free_image_buffers(pt_ctx* c)
   c->pb.tq = nullptr;
   cudaFree(c->pb.flags);
   cudaFree(c->pb.block_sums);
+  cudaFree(c->pb.bin_list);
+  c->pb.bin_list = nullptr;
   if (c->own_sums) cudaFree(c->d_sums);
   c->own_sums = true;
   for (auto& p : c->d_dn) {
@@ -647,7 +671,9 @@ static int alloc_image_buffers(pt_ctx* c, uint32_t width, uint32_t height)
     spp_pass = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(64, target / c->pixels));
   }
   c->samples_per_pass = spp_pass;
-  const size_t cap = (size_t)c->pixels * spp_pass;
+  // rounded up to whole 256-record tiles: the chain kernel stages the parked state tile by tile
+  // with bulk copies of fixed size (and every plane stays 16-byte aligned)
+  const size_t cap = (((size_t)c->pixels * spp_pass) + 255) & ~(size_t)255;
   if (cap > (1ull << 30)) return fail(PT_ERR_INVALID, "wavefront too large");
   c->pb.capacity = (uint32_t)cap;
   if (c->params.rng_mode == PT_RNG_SLOT_RESEED) {
@@ -682,6 +708,7 @@ static int alloc_image_buffers(pt_ctx* c, uint32_t width, uint32_t height)
     uint32_t* ids = (uint32_t*)p;
     c->pb.park[0].pid = ids;
     c->pb.park[1].pid = ids + cap;
+    if (c->params.sort_rays) PT_CUDA(cudaMalloc((void**)&c->pb.bin_list, cap * PT_BINS * sizeof(uint32_t)));
   }
   PT_CUDA(cudaMalloc((void**)&c->d_sums, (size_t)c->pixels * sizeof(float4) * 2));
   PT_CUDA(cudaMemsetAsync(c->d_sums, 0, (size_t)c->pixels * sizeof(float4) * 2, c->stream));
@@ -728,13 +755,14 @@ static int pt_ctx_create_impl(const pt_scene* scene, uint32_t width, uint32_t he
     c->own_stream = true;
   }
   const size_t n_ctr = (size_t)p.max_depth + 2;
-  c->counters_bytes = n_ctr * 3 * sizeof(uint32_t);
+  c->counters_bytes = n_ctr * (3 + PT_BINS) * sizeof(uint32_t); // + per-iteration bin counters (sort_rays)
   int rc = PT_OK;
   do {
     if ((e = cudaMalloc(&c->d_counters, c->counters_bytes + 24)) != cudaSuccess) break;
     c->pb.counters = (uint32_t*)c->d_counters;
     c->pb.work = c->pb.counters + n_ctr;
     c->pb.tcounters = c->pb.counters + 2 * n_ctr;
+    c->pb.bin_counts = c->pb.counters + 3 * n_ctr;
     c->pb.total_rays = (unsigned long long*)((char*)c->d_counters + ((c->counters_bytes + 7) & ~7ull));
     if ((e = cudaMemset(c->d_counters, 0, c->counters_bytes + 24)) != cudaSuccess) break;
     if ((e = cudaHostAlloc((void**)&c->h_counts, n_ctr * sizeof(uint32_t), cudaHostAllocDefault)) !=
@@ -783,11 +811,32 @@ int pt_ctx_destroy(pt_ctx* c)
 int pt_ctx_resize(pt_ctx* c, uint32_t width, uint32_t height)
 {
   if (!c) return fail(PT_ERR_INVALID, "pt_ctx_resize: null context");
+  // validate BEFORE anything is freed: a refused size leaves the context as it was
+  if (width == 0 || height == 0 || (uint64_t)width * height > (1ull << 27))
+    return fail(PT_ERR_INVALID, "unsupported resolution");
   PT_CUDA(cudaSetDevice(c->scene->device));
   PT_CUDA(cudaStreamSynchronize(c->stream));
   free_image_buffers(c);
-  return alloc_image_buffers(c, width, height);
+  const int rc = alloc_image_buffers(c, width, height);
+  if (rc != PT_OK) {
+    // allocation failed half way: release what was allocated and refuse every later call on the
+    // frame until a resize succeeds (no kernel is ever launched on a null buffer)
+    const std::string why = pt_last_error();
+    free_image_buffers(c);
+    c->width = c->height = c->pixels = 0;
+    c->row_begin = c->row_end = 0;
+    c->usable = false;
+    return fail(rc, why);
+  }
+  c->usable = true;
+  return PT_OK;
 }
+
+// every entry point that touches the frame buffers starts here
+#define PT_NEED_FRAME(c, what)                                                                     \
+  do {                                                                                             \
+    if (!(c)->usable) return fail(PT_ERR_INVALID, what ": the context has no frame buffers (a resize failed)"); \
+  } while (0)
 
 int pt_ctx_set_rows(pt_ctx* c, uint32_t row_begin, uint32_t row_end)
 {
@@ -817,10 +866,14 @@ int pt_denoise_halo_rows(const pt_denoise_params* dp, uint32_t* rows)
 int pt_ctx_restart(pt_ctx* c)
 {
   if (!c) return fail(PT_ERR_INVALID, "pt_ctx_restart: null context");
+  PT_NEED_FRAME(c, "pt_ctx_restart");
   // PathTracer::restart only zeroes the counter (final_gather overwrites at
   // iteration 0); with running sums the buffers are cleared instead.
   PT_CUDA(cudaMemsetAsync(c->d_sums, 0, (size_t)c->pixels * sizeof(float4) * 2, c->stream));
   c->iteration = 0;
+  c->range_first = 0;
+  c->range_contiguous = true;
+  c->camera_locked = false;
   c->final_rgb = nullptr;
   return PT_OK;
 }
@@ -914,6 +967,7 @@ static int render_pass(pt_ctx* c, const pt_camera& cam, uint32_t first_iteration
   pp.fd_tiles_x = make_fastdiv(pp.tiles_x);
   pp.fd_width = make_fastdiv(c->width);
   pp.samples = samples;
+  pp.capacity = c->pb.capacity;
   pp.first_iteration = first_iteration;
   pp.rng_mode = (uint32_t)c->params.rng_mode;
   pp.stream_state = tunable_stream_state() ? 1u : 0u;
@@ -1019,9 +1073,21 @@ int pt_render_range(pt_ctx* c, const pt_camera* cam, int first_iteration, int n_
 {
   if (!c || !cam) return fail(PT_ERR_INVALID, "pt_render_range: null argument");
   if (first_iteration < 0 || n_iterations < 0) return fail(PT_ERR_INVALID, "negative iteration range");
+  PT_NEED_FRAME(c, "pt_render_range");
+  if (c->camera_locked && c->iteration > 0 && std::memcmp(cam, &c->last_camera, sizeof(pt_camera)) != 0)
+    return fail(PT_ERR_INVALID, "pt_render: the camera differs from the camera of the loaded progressive state "
+                                "(pt_ctx_restart first)");
   PT_CUDA(cudaSetDevice(c->scene->device));
   c->last_camera = *cam;
   c->have_camera = true;
+  if (n_iterations > 0) {
+    if (c->iteration == 0) {
+      c->range_first = first_iteration;
+      c->range_contiguous = true;
+    } else if (first_iteration != c->range_first + c->iteration) {
+      c->range_contiguous = false;
+    }
+  }
   int done = 0;
   while (done < n_iterations) {
     const uint32_t s = (uint32_t)std::min<int>(n_iterations - done, (int)c->samples_per_pass);
@@ -1039,7 +1105,12 @@ int pt_render(pt_ctx* c, const pt_camera* cam, int n_iterations)
   if (!c) return fail(PT_ERR_INVALID, "pt_render: null context");
   int n = n_iterations;
   if (c->params.max_iterations > 0) n = std::min(n, std::max(0, c->params.max_iterations - c->iteration));
-  return pt_render_range(c, cam, c->iteration, n);
+  if (!c->range_contiguous)
+    return fail(PT_ERR_INVALID, "pt_render: the sums hold a non-contiguous set of iterations; continue with "
+                                "pt_render_range or pt_ctx_restart");
+  // continues after the iterations the sums already hold (a shard that started at iteration K,
+  // or a resumed state of one, goes on at K + iteration(), never re-using seeds)
+  return pt_render_range(c, cam, c->range_first + c->iteration, n);
 }
 
 int pt_path_trace(pt_ctx* c, const pt_camera* cam) { return pt_render(c, cam, 1); }
@@ -1060,6 +1131,7 @@ int pt_denoise(pt_ctx* c, const pt_denoise_params* dp_in)
   else
     pt_denoise_params_default(&dp);
   if (dp.filter_size < 1) return fail(PT_ERR_INVALID, "filter_size must be >= 1");
+  PT_NEED_FRAME(c, "pt_denoise");
   if (!c->have_camera) return fail(PT_ERR_INVALID, "pt_denoise before any path_trace / upload_frame");
   PT_CUDA(cudaSetDevice(c->scene->device));
   for (auto& p : c->d_dn)
@@ -1103,6 +1175,7 @@ int pt_resolve_rgba8(pt_ctx* c, int kind, void* dst, int dst_is_device)
   if (!c || !dst) return fail(PT_ERR_INVALID, "pt_resolve_rgba8: null argument");
   if (kind < 0 || kind > 4) return fail(PT_ERR_INVALID, "unknown buffer kind");
   if (kind == PT_BUF_DENOISED && !c->final_rgb) return fail(PT_ERR_INVALID, "no denoised buffer");
+  PT_NEED_FRAME(c, "pt_resolve_rgba8");
   PT_CUDA(cudaSetDevice(c->scene->device));
   const LaunchEnv env{c->stream, c->sms};
   uchar4* target = dst_is_device ? (uchar4*)dst : c->d_rgba;
@@ -1126,6 +1199,7 @@ int pt_download_f32(pt_ctx* c, int kind, float* dst)
   if (!c || !dst) return fail(PT_ERR_INVALID, "pt_download_f32: null argument");
   if (kind < 0 || kind > 4) return fail(PT_ERR_INVALID, "unknown buffer kind");
   if (kind == PT_BUF_DENOISED && !c->final_rgb) return fail(PT_ERR_INVALID, "no denoised buffer");
+  PT_NEED_FRAME(c, "pt_download_f32");
   PT_CUDA(cudaSetDevice(c->scene->device));
   const LaunchEnv env{c->stream, c->sms};
   launch_export_f32(env, kind, c->d_sums, c->d_sums + c->pixels, c->final_rgb,
@@ -1174,18 +1248,28 @@ int pt_ctx_set_sample_count(pt_ctx* c, int n)
 // ---- progressive state on disk: the running sums are associative, so a 1024-spp render can be
 // stopped and resumed (or merged from shards) without changing the result.
 namespace {
+// version 2 (128 bytes).  Version 1 files (64-byte header: magic, version, width, height,
+// iteration, n_floats) are still read, without the fingerprint checks.
 struct StateHeader {
   char magic[8]; // "B200PTST"
-  uint32_t version, width, height, iteration;
+  uint32_t version, width, height, iteration; // iteration = number of iterations in the sums
   uint64_t n_floats;
-  uint32_t reserved[8];
+  // ---- version 2
+  uint32_t range_first;      // the sums hold iterations [range_first, range_first + iteration)
+  uint32_t range_contiguous; // 0: an arbitrary set (merged shards); pt_render will not continue it
+  uint64_t scene_hash;       // description_hash of the scene the sums were rendered from
+  int32_t max_depth, rng_mode;
+  uint32_t have_camera;
+  pt_camera camera;
+  uint32_t reserved[9];
 };
-static_assert(sizeof(StateHeader) == 64, "state header is 64 bytes");
+static_assert(sizeof(StateHeader) == 128, "state header is 128 bytes");
 } // namespace
 
 static int pt_ctx_save_state_impl(pt_ctx* c, const char* path)
 {
   if (!c || !path) return fail(PT_ERR_INVALID, "pt_ctx_save_state: null argument");
+  PT_NEED_FRAME(c, "pt_ctx_save_state");
   PT_CUDA(cudaSetDevice(c->scene->device));
   PT_CUDA(cudaStreamSynchronize(c->stream));
   const size_t n = (size_t)c->pixels * 8;
@@ -1193,11 +1277,18 @@ static int pt_ctx_save_state_impl(pt_ctx* c, const char* path)
   PT_CUDA(cudaMemcpy(host.data(), c->d_sums, n * sizeof(float), cudaMemcpyDeviceToHost));
   StateHeader h{};
   std::memcpy(h.magic, "B200PTST", 8);
-  h.version = 1;
+  h.version = 2;
   h.width = c->width;
   h.height = c->height;
   h.iteration = (uint32_t)c->iteration;
   h.n_floats = n;
+  h.range_first = (uint32_t)c->range_first;
+  h.range_contiguous = c->range_contiguous ? 1u : 0u;
+  h.scene_hash = c->scene->content_hash;
+  h.max_depth = c->params.max_depth;
+  h.rng_mode = c->params.rng_mode;
+  h.have_camera = c->have_camera ? 1u : 0u;
+  h.camera = c->last_camera;
   FILE* f = std::fopen(path, "wb");
   if (!f) return fail(PT_ERR_IO, std::string("cannot write ") + path);
   const bool ok = std::fwrite(&h, sizeof(h), 1, f) == 1 && std::fwrite(host.data(), sizeof(float), n, f) == n;
@@ -1214,19 +1305,31 @@ int pt_ctx_save_state(pt_ctx* c, const char* path)
 static int pt_ctx_load_state_impl(pt_ctx* c, const char* path)
 {
   if (!c || !path) return fail(PT_ERR_INVALID, "pt_ctx_load_state: null argument");
+  PT_NEED_FRAME(c, "pt_ctx_load_state");
   FILE* f = std::fopen(path, "rb");
   if (!f) return fail(PT_ERR_IO, std::string("cannot open ") + path);
   StateHeader h{};
   const size_t n = (size_t)c->pixels * 8;
   std::vector<float> host(n);
-  bool ok = std::fread(&h, sizeof(h), 1, f) == 1;
-  if (ok && (std::memcmp(h.magic, "B200PTST", 8) != 0 || h.version != 1)) {
+  bool ok = std::fread(&h, 64, 1, f) == 1; // the version-1 header is the first 64 bytes
+  if (ok && (std::memcmp(h.magic, "B200PTST", 8) != 0 || (h.version != 1 && h.version != 2))) {
     std::fclose(f);
     return fail(PT_ERR_PARSE, std::string(path) + " is not a progressive-state file");
   }
+  if (ok && h.version == 2) ok = std::fread((char*)&h + 64, sizeof(h) - 64, 1, f) == 1;
   if (ok && (h.width != c->width || h.height != c->height || h.n_floats != n)) {
     std::fclose(f);
     return fail(PT_ERR_INVALID, "progressive state has a different resolution");
+  }
+  if (ok && h.version == 2) {
+    const char* why = nullptr;
+    if (h.scene_hash != c->scene->content_hash) why = "progressive state was rendered from a different scene";
+    else if (h.max_depth != c->params.max_depth) why = "progressive state was rendered with a different max_depth";
+    else if (h.rng_mode != c->params.rng_mode) why = "progressive state was rendered with a different rng_mode";
+    if (why) {
+      std::fclose(f);
+      return fail(PT_ERR_INVALID, why);
+    }
   }
   ok = ok && std::fread(host.data(), sizeof(float), n, f) == n;
   std::fclose(f);
@@ -1235,6 +1338,14 @@ static int pt_ctx_load_state_impl(pt_ctx* c, const char* path)
   PT_CUDA(cudaStreamSynchronize(c->stream));
   PT_CUDA(cudaMemcpy(c->d_sums, host.data(), n * sizeof(float), cudaMemcpyHostToDevice));
   c->iteration = (int)h.iteration;
+  c->range_first = h.version == 2 ? (int)h.range_first : 0;
+  c->range_contiguous = h.version == 2 ? h.range_contiguous != 0 : true;
+  if (h.version == 2 && h.have_camera) {
+    // rendering on with another camera would blend two different images
+    c->last_camera = h.camera;
+    c->have_camera = true;
+    c->camera_locked = true;
+  }
   c->final_rgb = nullptr;
   return PT_OK;
 }
@@ -1249,6 +1360,7 @@ int pt_ctx_upload_frame(pt_ctx* c, const float* color3, const float* normal3, co
 {
   if (!c || !color3 || !normal3 || !depth1 || !cam)
     return fail(PT_ERR_INVALID, "pt_ctx_upload_frame: null argument");
+  PT_NEED_FRAME(c, "pt_ctx_upload_frame");
   PT_CUDA(cudaSetDevice(c->scene->device));
   float* tmp = nullptr;
   const size_t n = c->pixels;

@@ -271,6 +271,9 @@ int pt_group_render(pt_group* g, const pt_camera* cam, int first_iteration, int 
     if (i != 0) {
       const int r = pt_ctx_restart(c);
       if (r != PT_OK) return r;
+    } else {
+      c->range_contiguous = true; // its own share is one more piece of the group's range (set below)
+      if (c->iteration == 0) c->range_first = first_iteration;
     }
     const int share = base + (i < extra ? 1 : 0);
     const int first = first_iteration + i * base + std::min(i, extra);
@@ -288,9 +291,17 @@ int pt_group_render(pt_group* g, const pt_camera* cam, int first_iteration, int 
     return (int)PT_OK;
   });
   if (rc != PT_OK) return rc;
+  // the reduced sums hold the WHOLE range, whatever share the root rendered itself
+  pt_ctx* root = g->ctxs[0];
+  if (g->samples == 0) {
+    root->range_first = first_iteration;
+    root->range_contiguous = true;
+  } else if (first_iteration != root->range_first + g->samples) {
+    root->range_contiguous = false;
+  }
   g->samples += n_iterations;
-  pt_ctx_set_sample_count(g->ctxs[0], g->samples);
-  g->ctxs[0]->final_rgb = nullptr;
+  pt_ctx_set_sample_count(root, g->samples);
+  root->final_rgb = nullptr;
   g->last_host_ms = now_ms() - t0;
   return PT_OK;
 }

@@ -59,6 +59,7 @@ struct SceneBuild {
   uint64_t n_world = 0;
   double build_ms = 0.0;
   bool wide = false, host_built = false;
+  uint64_t content_hash = 0; // fingerprint of the description (progressive-state files)
 };
 int scene_prepare(const pt_scene_desc* desc, bool host_build, SceneBuild& sb);
 int scene_upload(const pt_scene_desc* desc, const SceneBuild& sb, DeviceLBVH* dl, int device, pt_scene** out);
@@ -92,6 +93,7 @@ struct pt_scene {
   void* d_spheres = nullptr;
   void* d_materials = nullptr;
   pt_scene_info info{};
+  uint64_t content_hash = 0;
 };
 
 struct pt_ctx {
@@ -102,6 +104,12 @@ struct pt_ctx {
   bool own_stream = false;
   int sms = 148;
   int iteration = 0;
+  bool usable = true; // false after a failed resize: no frame buffers
+  // which iterations the running sums hold: [range_first, range_first + iteration) while
+  // range_contiguous (progressive-state files record it; pt_render continues after it)
+  int range_first = 0;
+  bool range_contiguous = true;
+  bool camera_locked = false; // sums came from a state file: rendering on needs the same camera
   uint32_t samples_per_pass = 1;
   uint32_t row_begin = 0, row_end = 0; // rendered / denoised band (row-band sharding); whole frame by default
 

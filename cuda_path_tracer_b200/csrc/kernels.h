@@ -18,6 +18,8 @@ struct PassBuffers {
   uint32_t* counters;  // [0 .. max_depth]   live paths entering bounce b
   uint32_t* tcounters; // [0 .. max_depth]   length of the traverse queue of bounce b
   uint32_t* work;      // [0 .. max_depth]   persistent-kernel work-fetch cursors
+  uint32_t* bin_list;  // PT_BINS x capacity slots (sort_rays only, else null)
+  uint32_t* bin_counts; // [0 .. max_depth] x PT_BINS
   uint8_t* flags;      // stable-compaction alive flags (PT_RNG_SLOT_RESEED only)
   uint32_t* block_sums; // stable-compaction block counts / offsets
   unsigned long long* total_rays; // device-side ray counter

@@ -264,9 +264,19 @@ static cudaError_t build_lbvh_device(const TriSource& src, uint32_t n_u, DeviceL
   const int n = (int)n_u;
   const int kLeafMax = leaf_max_setting();
   if (n <= 4 || n_u >= (1u << 28)) return cudaSuccess;
-  cudaEvent_t e0, e1;
-  LB_TRY(cudaEventCreate(&e0));
-  LB_TRY(cudaEventCreate(&e1));
+  // timing events released on every return path (early LB_TRY exits, the too-deep decline)
+  struct Events {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ~Events()
+    {
+      if (e0) cudaEventDestroy(e0);
+      if (e1) cudaEventDestroy(e1);
+    }
+  } ev;
+  LB_TRY(cudaEventCreate(&ev.e0));
+  LB_TRY(cudaEventCreate(&ev.e1));
+  cudaEvent_t& e0 = ev.e0;
+  cudaEvent_t& e1 = ev.e1;
   Scratch sc;
   BuildTri* d_tris;
   Box6 *pbox, *nbox;
@@ -360,8 +370,6 @@ static cudaError_t build_lbvh_device(const TriSource& src, uint32_t n_u, DeviceL
   }
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e0, e1);
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   out.built = true;
   out.nodes = nodes;
   out.tris = tris_out;

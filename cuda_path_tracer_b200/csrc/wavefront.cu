@@ -32,6 +32,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <mutex>
+
 namespace pt {
 
 // =================================================================== helpers
@@ -292,6 +294,7 @@ PT_D bool resolve_hit(const DevScene& sc, f3 o, f3 d, float tmin, float t_aux, u
   bool hit = false;
   float tbest = t_aux;
   if (code & AUX_TRI) {
+    PT_CHECK((code & AUX_VALUE) < sc.n_tris, "hit record names a triangle outside the array");
     const float4* tp = sc.tris + (size_t)(code & AUX_VALUE) * 3;
     const float4 t0 = ldg4(tp + 0);
     const float4 t1 = ldg4(tp + 1);
@@ -307,6 +310,7 @@ PT_D bool resolve_hit(const DevScene& sc, f3 o, f3 d, float tmin, float t_aux, u
     h.material = (uint32_t)__float_as_int(t2.w);
     hit = true;
   } else if (code & AUX_VALUE) {
+    PT_CHECK((code & AUX_VALUE) - 1u < sc.n_spheres, "hit record names a sphere outside the table");
     // same root as when it was accepted: any t_max >= the accepted t selects it again
     hit = sphere_test<false>(sc.spheres + ((code & AUX_VALUE) - 1u), o, d, tmin, FLT_MAX, h);
   }
@@ -362,6 +366,7 @@ template <bool L256>
 PT_D void trav_inner(const DevScene& sc, Trav& T, int* stack)
 {
   float4 n0, n1, n2, n3;
+  PT_CHECK((uint32_t)T.node < sc.n_nodes, "inner node index outside the tree");
   load_node<L256>(sc.nodes + (size_t)T.node * 4, n0, n1, n2, n3);
   const float c0lox = n0.x * T.idx - T.odx, c0hix = n0.y * T.idx - T.odx;
   const float c0loy = n0.z * T.idy - T.ody, c0hiy = n0.w * T.idy - T.ody;
@@ -383,11 +388,15 @@ PT_D void trav_inner(const DevScene& sc, Trav& T, int* stack)
   const int c0 = __float_as_int(n3.x);
   const int c1 = __float_as_int(n3.y);
   if (!trav0 && !trav1) {
+    PT_CHECK(T.sp > 0, "traversal stack underflow");
     T.node = stack[--T.sp];
   } else {
     const bool swap = trav1 && (!trav0 || c1min < c0min);
     T.node = swap ? c1 : c0;
-    if (trav0 && trav1) stack[T.sp++] = swap ? c0 : c1;
+    if (trav0 && trav1) {
+      PT_CHECK(T.sp < PT_STACK, "traversal stack overflow");
+      stack[T.sp++] = swap ? c0 : c1;
+    }
   }
 }
 
@@ -400,6 +409,7 @@ PT_D void trav_leaf(const DevScene& sc, Trav& T, int* stack)
   const uint32_t code = (uint32_t)(~T.node);
   const uint32_t first = code >> 3;
   const uint32_t count = (code & 7u) + 1u;
+  PT_CHECK(first + count <= sc.n_tris, "leaf outside the triangle array");
   for (uint32_t k = 0; k < count; ++k) {
     const float4* tp = sc.tris + (size_t)(first + k) * 3;
     const float4 t0 = ldg4(tp + 0);
@@ -421,6 +431,7 @@ PT_D void trav_leaf(const DevScene& sc, Trav& T, int* stack)
       T.best = (int)(first + k);
     }
   }
+  PT_CHECK(T.sp > 0, "traversal stack underflow");
   T.node = stack[--T.sp];
 }
 
@@ -577,7 +588,7 @@ __global__ void __launch_bounds__(EXT_THREADS, MINB)
 traverse_kernel(const DevScene sc, const PathState ps, const uint32_t* __restrict__ tq,
                 const uint32_t* __restrict__ n_ptr, uint32_t n_host, uint32_t* __restrict__ work,
                 const float4* __restrict__ batch_rays, HitRecord* __restrict__ batch_out,
-                int refill_min, int inner_min, int stream_state)
+                int refill_min, int inner_min, int stream_state, const BinLists bins)
 {
   const uint32_t n = SRC == SRC_QUEUE ? *n_ptr : n_host;
   const uint32_t lane = threadIdx.x & 31u;
@@ -644,6 +655,27 @@ traverse_kernel(const DevScene sc, const PathState ps, const uint32_t* __restric
       if (has && T.node < 0) trav_leaf(sc, T, stack);
     }
     // ---- retire finished lanes
+    if (SRC == SRC_QUEUE && bins.list != nullptr) {
+      // ray binning: one atomic per (warp, bin) for the lanes that retire now
+      const bool retiring = has && T.node == PT_SENTINEL;
+      uint32_t bin = PT_BINS; // not retiring
+      if (retiring) {
+        bin = 0u;
+        if (T.best >= 0) {
+          const uint32_t mat = (uint32_t)__float_as_int(ldg4(sc.tris + (size_t)T.best * 3 + 2).w);
+          bin = 1u + (uint32_t)sc.materials[mat].type;
+        }
+      }
+      const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+      if (retiring) {
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if ((int)lane == leader) base = atomicAdd(bins.count + bin, (uint32_t)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        PT_CHECK(base + (uint32_t)__popc(peers & lt_mask) < bins.cap && pid < bins.cap, "bin list slot out of range");
+        bins.list[(size_t)bin * bins.cap + base + (uint32_t)__popc(peers & lt_mask)] = pid;
+      }
+    }
     if (has && T.node == PT_SENTINEL) {
       if (SRC == SRC_QUEUE) {
         if (T.best >= 0)
@@ -1111,22 +1143,144 @@ PT_D uint32_t warp_slot(bool push, uint32_t* __restrict__ count, uint32_t lane)
   return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
 }
 
-template <bool FIRST>
+// TMA (re-entry launches only, opt-in PT_CHAIN_TMA=1|2): the parked state a launch consumes is
+// four contiguous streams, so it can be staged into shared memory with cp.async.bulk completing on
+// an mbarrier, double-buffered, while the previous tile is shaded.  Two granularities were built
+// and measured (profiles/README.md, round 2): 1 = one 256-record tile (17 KB) per CTA and stage,
+// with a CTA barrier before a stage is refilled; 2 = one 32-record tile (2 176 B) per WARP and
+// stage, no CTA barrier.  Both take the stream reads off the long-scoreboard list (4.0 -> 2.4
+// stalled warps per issue) and both are SLOWER than plain loads (chain<false> +3..+10 %): the
+// kernel's time is in the dependent scene fetches after the state arrives, and the staging adds a
+// synchronisation per tile.  Default off.
+#define CHAIN_TILE FULL_THREADS
+#define CHAIN_STAGE_BYTES (CHAIN_TILE * 68u)
+#define CHAIN_WSTAGE_BYTES (32u * 68u)
+template <uint32_t RECORDS>
+PT_D void chain_stage_issue(const ParkBuf& in, size_t first, unsigned char* stage, unsigned long long* bar)
+{
+  const uint32_t b = smem_u32(bar);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic reads of this stage are done
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(RECORDS * 68u) : "memory");
+  const uint32_t dst = smem_u32(stage);
+#define PT_BULK(off, src, bytes)                                                                   \
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"( \
+                   dst + (off)),                                                                   \
+               "l"(src), "r"(bytes), "r"(b)                                                        \
+               : "memory")
+  PT_BULK(0u, in.ray + 2 * first, RECORDS * 32u);
+  PT_BULK(RECORDS * 32u, in.thr + first, RECORDS * 16u);
+  PT_BULK(RECORDS * 48u, in.aux + first, RECORDS * 16u);
+  PT_BULK(RECORDS * 64u, in.pid + first, RECORDS * 4u);
+#undef PT_BULK
+}
+PT_D void mbar_wait(unsigned long long* bar, uint32_t parity)
+{
+  const uint32_t b = smem_u32(bar);
+  uint32_t ready = 0;
+  while (!ready) {
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+        : "=r"(ready)
+        : "r"(b), "r"(parity)
+        : "memory");
+  }
+}
+
+template <bool FIRST, int TMA>
 __global__ void __launch_bounds__(FULL_THREADS)
 chain_kernel(const DevScene sc, const PathState ps, const PassParams pp, const ParkBuf in,
              const uint32_t* __restrict__ n_ptr, uint32_t n_first, const ParkBuf out,
              uint32_t* __restrict__ out_count, uint32_t max_depth,
-             unsigned long long* __restrict__ total_rays)
+             unsigned long long* __restrict__ total_rays, const BinLists bins)
 {
   const uint32_t n = FIRST ? n_first : *n_ptr;
+  // ray binning: the items are the bins' lists back to back (their counts sum to n)
+  uint32_t bin_end[PT_BINS] = {0u, 0u, 0u, 0u};
+  if (!FIRST && bins.list != nullptr) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int b = 0; b < PT_BINS; ++b) {
+      acc += bins.count[b];
+      bin_end[b] = acc;
+    }
+  }
   const uint32_t n_round = (n + 31u) & ~31u;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t stride = gridDim.x * blockDim.x;
   const uint32_t cs = pp.stream_state;
   uint32_t rays_local = 0;
-  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_round; idx += stride) {
+  extern __shared__ __align__(128) unsigned char s_stage[]; // TMA: 2 stages per CTA, or per warp
+  __shared__ __align__(8) unsigned long long s_full[2 * (FULL_THREADS / 32)];
+  const uint32_t n_tiles = n_round == 0u ? 0u : (n_round + CHAIN_TILE - 1u) / CHAIN_TILE;
+  const uint32_t warp = threadIdx.x >> 5;
+  if (TMA == 1) {
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_full[0])));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_full[1])));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (blockIdx.x < n_tiles)
+        chain_stage_issue<CHAIN_TILE>(in, (size_t)blockIdx.x * CHAIN_TILE, s_stage, &s_full[0]);
+      if (blockIdx.x + gridDim.x < n_tiles)
+        chain_stage_issue<CHAIN_TILE>(in, (size_t)(blockIdx.x + gridDim.x) * CHAIN_TILE, s_stage + CHAIN_STAGE_BYTES,
+                                      &s_full[1]);
+    }
+  } else if (TMA == 2) {
+    if (lane == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_full[2 * warp])));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_full[2 * warp + 1])));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      const uint32_t first = blockIdx.x * blockDim.x + warp * 32u;
+      unsigned char* ws = s_stage + warp * 2u * CHAIN_WSTAGE_BYTES;
+      if (first < n_round) chain_stage_issue<32u>(in, first, ws, &s_full[2 * warp]);
+      if (first + stride < n_round)
+        chain_stage_issue<32u>(in, (size_t)first + stride, ws + CHAIN_WSTAGE_BYTES, &s_full[2 * warp + 1]);
+    }
+    __syncwarp();
+  }
+  // TMA 1: whole CTAs iterate together (the barrier below), padding lanes are simply not valid
+  const uint32_t n_loop = TMA == 1 ? n_tiles * CHAIN_TILE : n_round;
+  uint32_t k_iter = 0;
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_loop; idx += stride, ++k_iter) {
     uint32_t pid = 0, pixel, s, px, py;
     bool valid = idx < n;
+    float4 t_ro, t_rd, t_th;
+    uint4 t_ax;
+    uint32_t t_pid = 0;
+    if (TMA == 1) {
+      const uint32_t st = k_iter & 1u;
+      mbar_wait(&s_full[st], (k_iter >> 1) & 1u);
+      const unsigned char* base = s_stage + st * CHAIN_STAGE_BYTES;
+      const float4* sr = reinterpret_cast<const float4*>(base);
+      t_ro = sr[2 * threadIdx.x];
+      t_rd = sr[2 * threadIdx.x + 1];
+      t_th = reinterpret_cast<const float4*>(base + CHAIN_TILE * 32u)[threadIdx.x];
+      t_ax = reinterpret_cast<const uint4*>(base + CHAIN_TILE * 48u)[threadIdx.x];
+      t_pid = reinterpret_cast<const uint32_t*>(base + CHAIN_TILE * 64u)[threadIdx.x];
+      __syncthreads(); // the stage has been read by everyone: refill it with the tile after next
+      if (threadIdx.x == 0) {
+        const uint32_t next = blockIdx.x + (k_iter + 2u) * gridDim.x;
+        if (next < n_tiles)
+          chain_stage_issue<CHAIN_TILE>(in, (size_t)next * CHAIN_TILE, s_stage + st * CHAIN_STAGE_BYTES, &s_full[st]);
+      }
+    } else if (TMA == 2) {
+      const uint32_t st = k_iter & 1u;
+      mbar_wait(&s_full[2 * warp + st], (k_iter >> 1) & 1u);
+      unsigned char* base = s_stage + (warp * 2u + st) * CHAIN_WSTAGE_BYTES;
+      const float4* sr = reinterpret_cast<const float4*>(base);
+      t_ro = sr[2 * lane];
+      t_rd = sr[2 * lane + 1];
+      t_th = reinterpret_cast<const float4*>(base + 32u * 32u)[lane];
+      t_ax = reinterpret_cast<const uint4*>(base + 32u * 48u)[lane];
+      t_pid = reinterpret_cast<const uint32_t*>(base + 32u * 64u)[lane];
+      __syncwarp(); // the warp's stage has been read: refill it with its tile after next
+      if (lane == 0) {
+        const size_t next = (size_t)idx + 2u * (size_t)stride; // lane 0's idx = the warp's first item
+        if (next < n_round) chain_stage_issue<32u>(in, next, base, &s_full[2 * warp + st]);
+      }
+    }
     if (FIRST && valid) valid = first_item(pp, idx, pid, pixel, s, px, py);
     bool park = false; // the path leaves this kernel with a ray that needs the BVH
     f3 o = mk3(0.f, 0.f, 0.f), d = o, color = o;
@@ -1149,11 +1303,19 @@ chain_kernel(const DevScene sc, const PathState ps, const PassParams pp, const P
         need_traversal = classify(sc, o, d, tmin, FLT_MAX, tbest, code, start, h);
         have_hit = true;
       } else {
-        const float4 ro = ld_state(in.ray + 2 * (size_t)idx, cs);
-        const float4 rd = ld_state(in.ray + 2 * (size_t)idx + 1, cs);
-        const float4 th = ld_state(in.thr + idx, cs);
-        const uint4 ax = ld_state(in.aux + idx, cs);
-        pid = ld_state(in.pid + idx, cs);
+        uint32_t slot = idx;
+        if (TMA == 0 && bins.list != nullptr) {
+          int b = 0;
+#pragma unroll
+          for (int k = 0; k < PT_BINS - 1; ++k) b += idx >= bin_end[k] ? 1 : 0;
+          slot = bins.list[(size_t)b * bins.cap + (idx - (b ? bin_end[b - 1] : 0u))];
+          PT_CHECK(slot < bins.cap, "bin list entry out of range");
+        }
+        const float4 ro = TMA ? t_ro : ld_state(in.ray + 2 * (size_t)slot, cs);
+        const float4 rd = TMA ? t_rd : ld_state(in.ray + 2 * (size_t)slot + 1, cs);
+        const float4 th = TMA ? t_th : ld_state(in.thr + slot, cs);
+        const uint4 ax = TMA ? t_ax : ld_state(in.aux + slot, cs);
+        pid = TMA ? t_pid : ld_state(in.pid + slot, cs);
         o = xyz(ro), d = xyz(rd);
         tmin = ro.w;
         color = xyz(th);
@@ -1190,6 +1352,7 @@ chain_kernel(const DevScene sc, const PathState ps, const PassParams pp, const P
     }
     const uint32_t slot = warp_slot(park, out_count, lane);
     if (park) {
+      PT_CHECK(slot < pp.capacity && pid < pp.capacity, "parked-state slot out of range");
       st_state(out.ray + 2 * (size_t)slot, mk4(o, tmin), cs);
       st_state(out.ray + 2 * (size_t)slot + 1, mk4(d, FLT_MAX), cs);
       st_state(out.thr + slot, mk4(color, __uint_as_float(rng)), cs);
@@ -1210,6 +1373,7 @@ struct Tunables {
   int refill, inner_min, stream_state, node_min, tri_min, chain_grid, chain_grid0;
   int trav_minb, trav_l256; // traverse_kernel instantiation (PT_TRAV="minb,l256")
   int order;                // bounce-0 item order (PT_ORDER)
+  int chain_tma;            // TMA-staged parked state in the re-entry chain launches (PT_CHAIN_TMA)
 };
 static int env_int(const char* name, int dflt)
 {
@@ -1231,6 +1395,7 @@ static const Tunables& tunables()
     t.trav_l256 = 0;
     if (const char* v = getenv("PT_TRAV")) sscanf(v, "%d,%d", &t.trav_minb, &t.trav_l256);
     t.order = env_int("PT_ORDER", PT_DEFAULT_ORDER);
+    t.chain_tma = env_int("PT_CHAIN_TMA", 0);
     return t;
   }();
   return t;
@@ -1270,6 +1435,9 @@ template <typename K>
 static uint32_t persistent_grid(K kern, const LaunchEnv& env, int threads, size_t smem, int* cache_nb,
                                 size_t* cache_smem)
 {
+  // (one lock for all kernels: contexts of a multi-GPU group launch from one host thread each)
+  static std::mutex lock;
+  std::lock_guard<std::mutex> guard(lock);
   int dev = 0;
   cudaGetDevice(&dev);
   dev &= 63;
@@ -1288,7 +1456,7 @@ static uint32_t persistent_grid(K kern, const LaunchEnv& env, int threads, size_
 template <int SRC, int MINB, bool L256>
 static void launch_t2v(const LaunchEnv& env, const DevScene& sc, const PathState& ps, const uint32_t* tq,
                        const uint32_t* n_ptr, uint32_t n_host, uint32_t* work, const float4* rays,
-                       HitRecord* out, uint32_t max_grid)
+                       HitRecord* out, uint32_t max_grid, const BinLists& bins)
 {
   auto kern = traverse_kernel<SRC, MINB, L256>;
   static int nb[64] = {0};
@@ -1296,13 +1464,13 @@ static void launch_t2v(const LaunchEnv& env, const DevScene& sc, const PathState
   const Tunables& t = tunables();
   const uint32_t grid = min(persistent_grid(kern, env, EXT_THREADS, 0, nb, sm), max_grid);
   kern<<<grid, EXT_THREADS, 0, env.stream>>>(sc, ps, tq, n_ptr, n_host, work, rays, out, t.refill,
-                                             t.inner_min, t.stream_state);
+                                             t.inner_min, t.stream_state, bins);
 }
 
 template <int SRC>
 static void launch_t2(const LaunchEnv& env, const DevScene& sc, const PathState& ps, const uint32_t* tq,
                       const uint32_t* n_ptr, uint32_t n_host, uint32_t* work, const float4* rays,
-                      HitRecord* out, uint32_t max_grid)
+                      HitRecord* out, uint32_t max_grid, const BinLists& bins)
 {
   const Tunables& t = tunables();
   int minb = t.trav_minb, l256 = t.trav_l256;
@@ -1317,7 +1485,7 @@ static void launch_t2(const LaunchEnv& env, const DevScene& sc, const PathState&
   }
 #define PT_T2_CASE(B, L)                                                                           \
   if (minb == B && l256 == L)                                                                      \
-    return launch_t2v<SRC, B, L != 0>(env, sc, ps, tq, n_ptr, n_host, work, rays, out, max_grid);
+    return launch_t2v<SRC, B, L != 0>(env, sc, ps, tq, n_ptr, n_host, work, rays, out, max_grid, bins);
   PT_T2_CASE(8, 0)
   PT_T2_CASE(8, 1)
   PT_T2_CASE(10, 0)
@@ -1325,7 +1493,7 @@ static void launch_t2(const LaunchEnv& env, const DevScene& sc, const PathState&
   PT_T2_CASE(12, 0)
   PT_T2_CASE(12, 1)
 #undef PT_T2_CASE
-  launch_t2v<SRC, EXT_MIN_BLOCKS, false>(env, sc, ps, tq, n_ptr, n_host, work, rays, out, max_grid);
+  launch_t2v<SRC, EXT_MIN_BLOCKS, false>(env, sc, ps, tq, n_ptr, n_host, work, rays, out, max_grid, bins);
 }
 
 template <int SRC, int THREADS, int BLOCKS>
@@ -1347,11 +1515,12 @@ static void launch_t8(const LaunchEnv& env, const DevScene& sc, const PathState&
 template <int SRC>
 static void launch_traverse_shape(const LaunchEnv& env, const DevScene& sc, const PathState& ps,
                                   const uint32_t* tq, const uint32_t* n_ptr, uint32_t n_host,
-                                  uint32_t* work, const float4* rays, HitRecord* out, bool batch)
+                                  uint32_t* work, const float4* rays, HitRecord* out, bool batch,
+                                  const BinLists& bins = BinLists{nullptr, nullptr, 0u})
 {
   if (sc.n_nodes8 == 0u) {
     launch_t2<SRC>(env, sc, ps, tq, n_ptr, n_host, work, rays, out,
-                   batch ? cdiv(n_host, (uint32_t)EXT_THREADS) : 0xffffffffu);
+                   batch ? cdiv(n_host, (uint32_t)EXT_THREADS) : 0xffffffffu, bins);
     return;
   }
   const TShape sh = t8_shape();
@@ -1376,6 +1545,13 @@ void launch_traverse(const LaunchEnv& env, const DevScene& sc, const PassBuffers
                                    nullptr, nullptr, false);
 }
 
+// the bin lists traverse iteration `iter` fills and chain iteration `iter + 1` consumes
+static BinLists bins_of(const PassBuffers& pb, uint32_t iter)
+{
+  if (!pb.bin_list) return BinLists{nullptr, nullptr, 0u};
+  return BinLists{pb.bin_list, pb.bin_counts + (size_t)iter * PT_BINS, pb.capacity};
+}
+
 void launch_traverse_parked(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb, uint32_t iter)
 {
   // the compacted state of iteration `iter` is its own work list
@@ -1383,7 +1559,7 @@ void launch_traverse_parked(const LaunchEnv& env, const DevScene& sc, const Pass
   view.ray = pb.park[iter & 1].ray;
   view.aux = pb.park[iter & 1].aux;
   launch_traverse_shape<SRC_QUEUE>(env, sc, view, nullptr, pb.tcounters + iter, 0u, pb.work + iter,
-                                   nullptr, nullptr, false);
+                                   nullptr, nullptr, false, bins_of(pb, iter));
 }
 
 void launch_chain(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb,
@@ -1396,14 +1572,27 @@ void launch_chain(const LaunchEnv& env, const DevScene& sc, const PassBuffers& p
   const uint32_t grid = (uint32_t)env.sms * (uint32_t)tunables().chain_grid;
   const uint32_t grid_first = (uint32_t)env.sms * (uint32_t)tunables().chain_grid0;
   if (iter == 0) {
-    chain_kernel<true><<<min(grid_first, cdiv(n_items_first, FULL_THREADS)), FULL_THREADS, 0, env.stream>>>(
+    chain_kernel<true, 0><<<min(grid_first, cdiv(n_items_first, FULL_THREADS)), FULL_THREADS, 0, env.stream>>>(
         sc, pb.ps, pp, ParkBuf{}, nullptr, n_items_first, pb.park[0], pb.tcounters + 0, max_depth,
-        pb.total_rays);
+        pb.total_rays, BinLists{nullptr, nullptr, 0u});
   } else {
     // consumes the traversed state of iteration iter-1, parks into the buffer of iteration iter
-    chain_kernel<false><<<grid, FULL_THREADS, 0, env.stream>>>(
-        sc, pb.ps, pp, pb.park[(iter - 1) & 1], pb.tcounters + (iter - 1), 0u, pb.park[iter & 1],
-        pb.tcounters + iter, max_depth, pb.total_rays);
+    const BinLists bins = bins_of(pb, iter - 1);
+    const int tma = bins.list == nullptr ? tunables().chain_tma : 0;
+    if (tma == 1) {
+      // (34 KB of dynamic shared memory: below the 48 KB that needs no opt-in)
+      chain_kernel<false, 1><<<grid, FULL_THREADS, 2 * CHAIN_STAGE_BYTES, env.stream>>>(
+          sc, pb.ps, pp, pb.park[(iter - 1) & 1], pb.tcounters + (iter - 1), 0u, pb.park[iter & 1],
+          pb.tcounters + iter, max_depth, pb.total_rays, bins);
+    } else if (tma == 2) {
+      chain_kernel<false, 2><<<grid, FULL_THREADS, 2 * CHAIN_STAGE_BYTES, env.stream>>>(
+          sc, pb.ps, pp, pb.park[(iter - 1) & 1], pb.tcounters + (iter - 1), 0u, pb.park[iter & 1],
+          pb.tcounters + iter, max_depth, pb.total_rays, bins);
+    } else {
+      chain_kernel<false, 0><<<grid, FULL_THREADS, 0, env.stream>>>(
+          sc, pb.ps, pp, pb.park[(iter - 1) & 1], pb.tcounters + (iter - 1), 0u, pb.park[iter & 1],
+          pb.tcounters + iter, max_depth, pb.total_rays, bins);
+    }
   }
 }
 

@@ -318,8 +318,12 @@ PT_API int pt_ctx_upload_frame(pt_ctx* ctx, const float* color3, const float* no
                                const float* depth1, const pt_camera* camera);
 
 /* Progressive state on disk (checkpoint + resume of long progressive renders): the
- * running sums and the iteration counter.  load requires a context of the same resolution and
- * continues where the saved render stopped (same seeds, same result as an uninterrupted run). */
+ * running sums, WHICH iterations they hold ([first, first + count), so a shard that rendered
+ * pt_render_range(first = K, ...) resumes at K + count and never re-uses seeds) and a fingerprint
+ * of what they were rendered from (scene description, max_depth, rng_mode, camera).  load refuses
+ * a state of another resolution, scene or parameter set; afterwards pt_render continues where the
+ * saved render stopped (same result as an uninterrupted run) and refuses another camera until
+ * pt_ctx_restart. */
 PT_API int pt_ctx_save_state(pt_ctx* ctx, const char* path);
 PT_API int pt_ctx_load_state(pt_ctx* ctx, const char* path);
 

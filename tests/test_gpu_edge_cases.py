@@ -381,3 +381,85 @@ def test_device_lbvh_build_matches_host_restatement_and_oracle(oracle, scene_nam
 
     d = np.abs(image(dev) - image(sah)).max(axis=2)
     assert (d > 1e-5).mean() < 2e-3, (d > 1e-5).mean()
+
+
+def test_ray_binning_changes_the_order_not_the_image():
+    """pt_params.sort_rays (the reference's commented-out sort by material_id, path_tracer.cu:
+    439-446): traversed rays are shaded bin by bin (miss / lambertian / metal / dielectric hit).
+    Every path carries its own RNG stream, so the frame and the ray count are bit-identical."""
+    sd = pt.many_materials_scene(320, 180, 4, subdiv=3)
+    w, h = sd.resolution
+    frames = []
+    for sort in (False, True):
+        tr = pt.PathTracer(max_depth=8, sort_rays=sort)
+        tr.create_buffers((w, h), sd)
+        tr.render(sd.camera, 4)
+        tr.synchronize()
+        frames.append((tr.download(DB.color), tr.download(DB.normal), int(tr.stats().rays)))
+    assert frames[0][2] == frames[1][2]
+    assert np.array_equal(frames[0][0], frames[1][0]) and np.array_equal(frames[0][1], frames[1][1])
+    assert frames[0][0].std() > 0.05                          # a real image, three material types
+
+
+def test_progressive_state_records_what_it_holds(tmp_path):
+    """a state file names the iterations its sums hold and what they were rendered from.
+    A shard that rendered [10, 14) resumes at 14 (never re-using seeds); a different scene,
+    max_depth or camera is refused instead of being blended in silently."""
+    sd = pt.bunny_scene(pt.bunny_like(2), 96, 54)
+    w, h = sd.resolution
+    path = str(tmp_path / "shard.state")
+    a = pt.PathTracer(max_depth=6)
+    a.create_buffers((w, h), sd)
+    a.render_range(sd.camera, 10, 4)
+    a.save_state(path)
+    b = pt.PathTracer(max_depth=6)
+    b.max_iterations = 1 << 20
+    b.create_buffers((w, h), sd)
+    b.load_state(path)
+    assert b.iteration() == 4
+    b.render(sd.camera, 2)                                   # continues with iterations 14, 15
+    whole = pt.PathTracer(max_depth=6)
+    whole.create_buffers((w, h), sd)
+    whole.render_range(sd.camera, 10, 6)
+    assert np.abs(b.download(DB.color) - whole.download(DB.color)).max() < 1e-6
+    # another camera would blend two images: refused until restart
+    cam2 = pt.Camera((0.0, 0.2, 0.0), (1.0, 0.0, 0.0, 0.0), sd.camera.vfov)
+    with pytest.raises(pt.PTError, match="camera"):
+        b.render(cam2, 1)
+    b.restart()
+    b.render(cam2, 1)
+    # another scene / another depth
+    other = pt.PathTracer(max_depth=6)
+    other.create_buffers((w, h), pt.bunny_scene(pt.bunny_like(3), 96, 54))
+    with pytest.raises(pt.PTError, match="different scene"):
+        other.load_state(path)
+    deeper = pt.PathTracer(max_depth=7)
+    deeper.create_buffers((w, h), sd)
+    with pytest.raises(pt.PTError, match="max_depth"):
+        deeper.load_state(path)
+    # a merged, non-contiguous set of iterations is not continued by pt_render
+    c = pt.PathTracer(max_depth=6)
+    c.max_iterations = 1 << 20
+    c.create_buffers((w, h), sd)
+    c.render_range(sd.camera, 0, 2)
+    c.render_range(sd.camera, 7, 2)
+    with pytest.raises(pt.PTError, match="non-contiguous"):
+        c.render(sd.camera, 1)
+
+
+def test_failed_resize_leaves_a_context_that_refuses_work():
+    """a refused size changes nothing; nothing is ever launched on freed buffers."""
+    sd = pt.three_balls(64, 64)
+    tr = pt.PathTracer(max_depth=4)
+    tr.create_buffers((64, 64), sd)
+    tr.render(sd.camera, 1)
+    before = tr.download(DB.color)
+    with pytest.raises(pt.PTError, match="resolution"):
+        tr.resize_image((0, 64))
+    with pytest.raises(pt.PTError, match="resolution"):
+        tr.resize_image((1 << 14, 1 << 14))
+    assert np.array_equal(tr.download(DB.color), before)        # untouched
+    tr.resize_image((32, 48))
+    tr.max_iterations = 4
+    tr.render(sd.camera, 1)
+    assert tr.download(DB.color).shape == (48, 32, 3)
