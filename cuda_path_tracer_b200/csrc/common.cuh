@@ -199,7 +199,16 @@ struct DevScene {
   uint32_t n_nodes8; // 0 = traverse the binary tree
   uint32_t n_tris;
   float root_lo[3], root_hi[3]; // padded bounds of the whole mesh BVH (classification)
+  // Sphere acceleration (scenes with many spheres; the reference scans its objects linearly,
+  // path_tracer.cu:118): a binary tree in the mesh BVH's node format over the world bounds of each
+  // sphere GROUP (the spheres before / after the first mesh object), leaves of <= 4 spheres
+  // (~(first << 3 | count - 1), `first` indexing `spheres`).  Built only for groups of more than
+  // PT_SPHERE_BVH_MIN rigidly placed spheres (there the closest hit does not depend on the test
+  // order); root < 0 = test the group linearly.
+  const float4* sph_nodes;
+  int32_t sph_root_before, sph_root_after;
 };
+#define PT_SPHERE_BVH_MIN 32
 
 // Path state, all indexed by path id = sample_in_pass * pixels + pixel (64 B/path):
 //   ray[2*id]   = (origin.xyz, t_min)  ray[2*id+1] = (direction.xyz, t_max)

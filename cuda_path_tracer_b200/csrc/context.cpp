@@ -111,6 +111,85 @@ static void sphere_world_bound(const float* m, const pt_sphere& s, DevSphere& d)
   d.pre_ok = ok && !disabled ? 1u : 0u;
 }
 
+// Tree over one sphere group (DevScene::sph_nodes): median split of the centroids along the
+// widest axis, <= 4 spheres per leaf, the group's spheres reordered into leaf order.  Returns the
+// child reference of the range [a, b) and its bounds.
+struct SphereTreeBuilder {
+  std::vector<DevSphere>& sph;
+  std::vector<float>& nodes;
+  uint32_t offset; // index of the group's first sphere in the scene's sphere array
+  struct B {
+    float lo[3], hi[3];
+  };
+  static B box_of(const DevSphere& s)
+  {
+    B b;
+    const float c[3] = {s.wx, s.wy, s.wz};
+    for (int a = 0; a < 3; ++a) {
+      const float lo = c[a] - s.wr, hi = c[a] + s.wr;
+      b.lo[a] = lo - (std::fabs(lo) * 4e-7f + 1e-30f); // outwards: the node test is exact otherwise
+      b.hi[a] = hi + (std::fabs(hi) * 4e-7f + 1e-30f);
+    }
+    return b;
+  }
+  int build(uint32_t a, uint32_t b, B& out)
+  {
+    out = box_of(sph[a]);
+    for (uint32_t i = a + 1; i < b; ++i) {
+      const B bi = box_of(sph[i]);
+      for (int k = 0; k < 3; ++k) out.lo[k] = std::min(out.lo[k], bi.lo[k]), out.hi[k] = std::max(out.hi[k], bi.hi[k]);
+    }
+    if (b - a <= 4) return ~(int)(((offset + a) << 3) | (b - a - 1));
+    float clo[3] = {sph[a].wx, sph[a].wy, sph[a].wz}, chi[3] = {sph[a].wx, sph[a].wy, sph[a].wz};
+    for (uint32_t i = a + 1; i < b; ++i) {
+      const float c[3] = {sph[i].wx, sph[i].wy, sph[i].wz};
+      for (int k = 0; k < 3; ++k) clo[k] = std::min(clo[k], c[k]), chi[k] = std::max(chi[k], c[k]);
+    }
+    int axis = 0;
+    for (int k = 1; k < 3; ++k)
+      if (chi[k] - clo[k] > chi[axis] - clo[axis]) axis = k;
+    const uint32_t mid = a + (b - a) / 2;
+    std::nth_element(sph.begin() + a, sph.begin() + mid, sph.begin() + b, [axis](const DevSphere& x, const DevSphere& y) {
+      const float cx[3] = {x.wx, x.wy, x.wz}, cy[3] = {y.wx, y.wy, y.wz};
+      return cx[axis] < cy[axis];
+    });
+    const int me = (int)(nodes.size() / 16);
+    nodes.resize(nodes.size() + 16, 0.f);
+    B b0, b1;
+    const int c0 = build(a, mid, b0), c1 = build(mid, b, b1);
+    float* n = nodes.data() + (size_t)me * 16; // (after the recursion: the vector may have grown)
+    n[0] = b0.lo[0], n[1] = b0.hi[0], n[2] = b0.lo[1], n[3] = b0.hi[1];
+    n[4] = b1.lo[0], n[5] = b1.hi[0], n[6] = b1.lo[1], n[7] = b1.hi[1];
+    n[8] = b0.lo[2], n[9] = b0.hi[2], n[10] = b1.lo[2], n[11] = b1.hi[2];
+    std::memcpy(n + 12, &c0, 4);
+    std::memcpy(n + 13, &c1, 4);
+    return me;
+  }
+};
+
+// Groups of more than PT_SPHERE_BVH_MIN spheres, all placed rigidly (unit scale: the sphere test
+// then reports the same distance whatever else was hit first, so the order of the tests does not
+// matter), get a tree; anything else keeps the reference's linear scan.
+static void build_sphere_trees(SceneBuild& sb, const std::vector<uint8_t>& rigid)
+{
+  static const bool disabled = getenv("PT_SPHERE_BVH") && atoi(getenv("PT_SPHERE_BVH")) == 0;
+  if (disabled) return;
+  auto group = [&](uint32_t a, uint32_t b) -> int {
+    if (b - a <= PT_SPHERE_BVH_MIN) return -1;
+    for (uint32_t i = a; i < b; ++i)
+      if (!rigid[i]) return -1;
+    // the builder reorders a copy of the group into leaf order; `a` offsets its leaf references
+    std::vector<DevSphere> part(sb.spheres.begin() + a, sb.spheres.begin() + b);
+    SphereTreeBuilder builder{part, sb.sph_nodes, a};
+    SphereTreeBuilder::B box;
+    const int root = builder.build(0, (uint32_t)part.size(), box);
+    std::copy(part.begin(), part.end(), sb.spheres.begin() + a);
+    return root;
+  };
+  sb.sph_root_before = group(0, sb.n_spheres_before);
+  sb.sph_root_after = group(sb.n_spheres_before, (uint32_t)sb.spheres.size());
+}
+
 } // namespace pt
 
 using namespace pt;
@@ -224,6 +303,7 @@ int scene_prepare(const pt_scene_desc* desc, bool host_build, SceneBuild& sb)
   const double t0 = now_ms();
   // ---- objects -> spheres (reference order quirks kept) + mesh instances
   std::vector<DevSphere> sph_after;
+  std::vector<uint8_t> rigid_before, rigid_after;
   bool seen_mesh = false;
   for (uint32_t i = 0; i < desc->n_objects; ++i) {
     const pt_object& ob = desc->objects[i];
@@ -243,6 +323,9 @@ int scene_prepare(const pt_scene_desc* desc, bool host_build, SceneBuild& sb)
       d.material = ob.material;
       d.object = (int32_t)i;
       sphere_world_bound(ob.m, s, d);
+      // rigid = similarity (pre_ok) with unit scale
+      const double len2 = (double)ob.m[0] * ob.m[0] + (double)ob.m[1] * ob.m[1] + (double)ob.m[2] * ob.m[2];
+      (seen_mesh ? rigid_after : rigid_before).push_back(d.pre_ok && std::fabs(len2 - 1.0) < 1e-5 ? 1 : 0);
       (seen_mesh ? sph_after : sb.spheres).push_back(d);
     } else if (ob.type == PT_OBJ_MESH) {
       seen_mesh = true;
@@ -256,6 +339,8 @@ int scene_prepare(const pt_scene_desc* desc, bool host_build, SceneBuild& sb)
   }
   sb.n_spheres_before = (uint32_t)sb.spheres.size();
   sb.spheres.insert(sb.spheres.end(), sph_after.begin(), sph_after.end());
+  rigid_before.insert(rigid_before.end(), rigid_after.begin(), rigid_after.end());
+  build_sphere_trees(sb, rigid_before);
   sb.content_hash = description_hash(desc);
 
   sb.mats.resize(desc->n_materials);
@@ -319,6 +404,7 @@ int scene_upload(const pt_scene_desc* desc, const SceneBuild& sb, DeviceLBVH* dl
   }
   if (e == cudaSuccess) e = upload(bvh.nodes8.data(), bvh.nodes8.size() * 4, &sc->d_nodes8);
   if (e == cudaSuccess) e = upload(sb.spheres.data(), sb.spheres.size() * sizeof(DevSphere), &sc->d_spheres);
+  if (e == cudaSuccess) e = upload(sb.sph_nodes.data(), sb.sph_nodes.size() * 4, &sc->d_sph_nodes);
   if (e == cudaSuccess) e = upload(sb.mats.data(), sb.mats.size() * sizeof(DevMaterial), &sc->d_materials);
   if (e != cudaSuccess) {
     pt_scene_destroy(sc);
@@ -334,6 +420,9 @@ int scene_upload(const pt_scene_desc* desc, const SceneBuild& sb, DeviceLBVH* dl
   sc->dev.materials = (const DevMaterial*)sc->d_materials;
   sc->dev.n_spheres = (uint32_t)sb.spheres.size();
   sc->dev.n_spheres_before = sb.n_spheres_before;
+  sc->dev.sph_nodes = (const float4*)sc->d_sph_nodes;
+  sc->dev.sph_root_before = sb.sph_root_before;
+  sc->dev.sph_root_after = sb.sph_root_after;
   sc->dev.n_nodes = n_nodes;
   // the wide traversal keeps a PT_STACK8-entry stack: one node group per level at most
   const bool use_wide = !from_device && bvh.n_nodes8 != 0 && bvh.depth8 <= PT_STACK8;
@@ -508,6 +597,7 @@ int pt_scene_destroy(pt_scene* sc)
   cudaFree(sc->d_tris);
   cudaFree(sc->d_nodes8);
   cudaFree(sc->d_spheres);
+  cudaFree(sc->d_sph_nodes);
   cudaFree(sc->d_materials);
   delete sc;
   return PT_OK;

@@ -5,6 +5,9 @@
 //   atrous      denoising_kernel                             (denoising/...denoiser.cu:24-86)
 #include "kernels.h"
 
+#include <algorithm>
+#include <stdlib.h>
+
 #include <float.h>
 
 namespace pt {
@@ -255,33 +258,70 @@ denoise_prepare_kernel(const DevCamera cam, const float4* __restrict__ sum_color
 // pixel (0, v+1) while its position is still rebuilt from the ray through (W+0.5, v+0.5);
 // reads that would fall past the end of the buffer (undefined in the reference) use the last
 // row / last pixel instead.  clamp_fix selects the sane W-1/H-1 clamp.
-#ifndef ATR_R
-#define ATR_R 2
-#endif
-#ifndef ATR_JUNROLL
-#define ATR_JUNROLL 6
+// Taps clamped to u == W or v == H (clamp_fix = 0): u == W aliases pixel (0, v+1) while its
+// position is still rebuilt from the ray through (W+0.5, v+0.5); reads past the end of the buffer
+// (undefined in the reference) use the last row / last pixel.
+struct Tap9 {
+  f3 c, n, p;
+};
+__device__ __noinline__ Tap9 edge_tap(const DevCamera& cam, const float4* __restrict__ color_in,
+                                      const float4* __restrict__ normal_depth, int u, int v, int W, int H)
+{
+  Tap9 t;
+  int qi = u + v * W;
+  if (qi >= W * H) qi = min(u, W - 1) + (H - 1) * W;
+  const float4 c = ldg4(color_in + qi), n = ldg4(normal_depth + qi);
+  t.c = mk3(c.x, c.y, c.z);
+  t.n = mk3(n.x, n.y, n.z);
+  f3 o, d;
+  camera_ray(cam, (float)u + 0.5f, (float)v + 0.5f, o, d);
+  t.p = o + d * n.w;
+  return t;
+}
+
+// ATR_R (outputs per thread, `step` rows apart) is a template parameter: 2 for the edge strips,
+// PT_ATR_R (default below) for the interior.
+#ifndef ATR_R_DEFAULT
+#define ATR_R_DEFAULT 2
 #endif
 
-__global__ void __launch_bounds__(128)
-atrous_kernel(const DevCamera cam, const DenoiseParams dp, const float4* __restrict__ color_in,
-              const float4* __restrict__ normal_depth, const float4* __restrict__ position,
-              float4* __restrict__ color_out, int step, int n_groups, int row_lo, int row_hi)
+// One launch per iteration covers three regions of the output window, each a list of CTAs:
+//   region 0  the interior: outputs none of whose taps reaches the clamp values u == W or v == H
+//             (everything with clamp_fix).  EDGE = false: the edge path is compiled out of this
+//             body — a third of the instructions and no call in the unrolled loop;
+//   region 1/2 the right and bottom strips (2 * step wide / high), EDGE = true.
+// A CTA runs exactly one of the bodies, so the interior never fetches the edge code, and the strips
+// overlap with the interior instead of trailing it as two latency-bound launches (measured:
+// 13 us each per iteration).
+struct AtrousRegion {
+  int x_lo, x_hi, row_lo, row_hi, n_groups, grid_x, n_ctas;
+};
+struct AtrousRegions {
+  AtrousRegion r[3];
+};
+
+template <bool EDGE, int ATR_R>
+PT_D void atrous_body(const DevCamera& cam, const DenoiseParams& dp, const float4* __restrict__ color_in,
+                      const float4* __restrict__ normal_depth, const float4* __restrict__ position,
+                      float4* __restrict__ color_out, int step, const AtrousRegion& rg, int cta)
 {
+  const int n_groups = rg.n_groups, row_lo = rg.row_lo, row_hi = rg.row_hi, x_lo = rg.x_lo, x_hi = rg.x_hi;
+  const int bx = cta % rg.grid_x, by = cta / rg.grid_x;
   // rows [row_lo, row_hi) are written (the whole frame, or one GPU's band plus its halo); taps
   // are clamped at the FRAME edges either way, so a band computes what the full frame would
   const int W = (int)cam.width, H = (int)cam.height;
-  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int g = blockIdx.y * 4 + (threadIdx.x >> 5); // (phase, group of ATR_R dilated rows)
+  const int x = x_lo + bx * 32 + (threadIdx.x & 31);
+  const int g = by * 4 + (threadIdx.x >> 5); // (phase, group of ATR_R dilated rows)
   const int ph = g % step, k = g / step;
-  if (x >= W || k >= n_groups) return;
+  if (x >= x_hi || k >= n_groups) return;
   const int q0 = row_lo / step + k * ATR_R;
 
   const float log2e = 1.4426950408889634f;
   const float kc = log2e / dp.c_phi;
   const float kn = log2e / (dp.n_phi * (float)(step * step));
   const float kp = log2e / dp.p_phi;
-  const int umax = dp.clamp_fix ? W - 1 : W;
-  const int vmax = dp.clamp_fix ? H - 1 : H;
+  const int umax = !EDGE || dp.clamp_fix ? W - 1 : W;
+  const int vmax = !EDGE || dp.clamp_fix ? H - 1 : H;
 
   f3 cv[ATR_R], nv[ATR_R], pv[ATR_R], sum[ATR_R];
   float cum[ATR_R];
@@ -299,8 +339,8 @@ atrous_kernel(const DevCamera cam, const DenoiseParams dp, const float4* __restr
     cum[r] = 0.f;
   }
 
-  constexpr int kJUnroll = ATR_JUNROLL;
-#pragma unroll kJUnroll
+  // fully unrolled (ATR_R + 4 tap rows): dy = j - r below must be a compile-time constant
+#pragma unroll
   for (int j = -2; j < ATR_R + 2; ++j) {
     const int v = min(max((q0 + j) * step + ph, 0), vmax);
 #pragma unroll
@@ -308,19 +348,16 @@ atrous_kernel(const DevCamera cam, const DenoiseParams dp, const float4* __restr
       const int u = min(max(x + dx * step, 0), umax);
       int qi = u + v * W;
       f3 ct, nt, pt3;
-      if (u < W && v < H) {
+      if (!EDGE || (u < W && v < H)) {
         const float4 c = ldg4(color_in + qi), n = ldg4(normal_depth + qi), q = ldg4(position + qi);
         ct = mk3(c.x, c.y, c.z);
         nt = mk3(n.x, n.y, n.z);
         pt3 = mk3(q.x, q.y, q.z);
       } else {
-        if (qi >= W * H) qi = min(u, W - 1) + (H - 1) * W;
-        const float4 c = ldg4(color_in + qi), n = ldg4(normal_depth + qi);
-        ct = mk3(c.x, c.y, c.z);
-        nt = mk3(n.x, n.y, n.z);
-        f3 o, d;
-        camera_ray(cam, (float)u + 0.5f, (float)v + 0.5f, o, d);
-        pt3 = o + d * n.w;
+        // the reference's right/bottom edge quirks: rare, kept out of line so that the unrolled
+        // tap loop stays small (inlined 30 times it was most of an 11 000-instruction kernel)
+        const Tap9 t = edge_tap(cam, color_in, normal_depth, u, v, W, H);
+        ct = t.c, nt = t.n, pt3 = t.p;
       }
 #pragma unroll
       for (int r = 0; r < ATR_R; ++r) {
@@ -330,7 +367,9 @@ atrous_kernel(const DevCamera cam, const DenoiseParams dp, const float4* __restr
         const float kw = (adx < ady ? adx : ady) == 0 ? 3.f / 8.f : ((adx < ady ? adx : ady) == 1 ? 1.f / 4.f : 1.f / 16.f);
         const f3 dc = cv[r] - ct, dn = nv[r] - nt, dq = pv[r] - pt3;
         const float e = dot3(dc, dc) * kc + dot3(dn, dn) * kn + dot3(dq, dq) * kp;
-        const float w = exp2f(-e) * kw;
+        float ex;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-e)); // 2 ulp; no range fix-up code
+        const float w = ex * kw;
         sum[r] = sum[r] + ct * w;
         cum[r] += w;
       }
@@ -342,6 +381,26 @@ atrous_kernel(const DevCamera cam, const DenoiseParams dp, const float4* __restr
     const int y = (q0 + r) * step + ph;
     color_out[y * W + x] = make_float4(sum[r].x / cum[r], sum[r].y / cum[r], sum[r].z / cum[r], 0.f);
   }
+}
+
+template <int R_INTERIOR>
+__global__ void __launch_bounds__(128)
+atrous_kernel(const DevCamera cam, const DenoiseParams dp, const float4* __restrict__ color_in,
+              const float4* __restrict__ normal_depth, const float4* __restrict__ position,
+              float4* __restrict__ color_out, int step, const AtrousRegions regions)
+{
+  int cta = (int)blockIdx.x;
+  if (cta < regions.r[0].n_ctas) {
+    atrous_body<false, R_INTERIOR>(cam, dp, color_in, normal_depth, position, color_out, step, regions.r[0], cta);
+    return;
+  }
+  cta -= regions.r[0].n_ctas;
+  if (cta < regions.r[1].n_ctas) {
+    atrous_body<true, 2>(cam, dp, color_in, normal_depth, position, color_out, step, regions.r[1], cta);
+    return;
+  }
+  cta -= regions.r[1].n_ctas;
+  atrous_body<true, 2>(cam, dp, color_in, normal_depth, position, color_out, step, regions.r[2], cta);
 }
 
 // ================================================================ launchers
@@ -407,13 +466,44 @@ void launch_atrous(const LaunchEnv& env, const DevCamera& cam, const DenoisePara
 {
   // rows are grouped per phase (y mod step): ATR_R outputs of one thread are `step` apart;
   // dilated row index q = y / step runs over the window [row_lo, row_hi)
-  const uint32_t q_lo = row_lo / (uint32_t)step_width;
-  const uint32_t nq = cdiv(row_hi, (uint32_t)step_width) - q_lo;
-  const uint32_t n_groups = cdiv(nq, ATR_R);
-  dim3 grid(cdiv(cam.width, 32), cdiv(n_groups * (uint32_t)step_width, 4));
-  atrous_kernel<<<grid, 128, 0, env.stream>>>(cam, dp, color_in, normal_depth, position,
-                                              color_out, step_width, (int)n_groups, (int)row_lo,
-                                              (int)row_hi);
+  const int W = (int)cam.width, H = (int)cam.height, step = step_width;
+  static const int interior_r = [] {
+    const char* v = getenv("PT_ATR_R");
+    const int r = v ? atoi(v) : ATR_R_DEFAULT;
+    return r == 3 || r == 4 ? r : 2;
+  }();
+  auto region = [&](bool edge, int y0, int y1, int x0, int x1) {
+    AtrousRegion rg{};
+    if (y0 >= y1 || x0 >= x1) return rg; // empty: n_ctas = 0
+    const uint32_t R = edge ? 2u : (uint32_t)interior_r;
+    const uint32_t q_lo = (uint32_t)y0 / (uint32_t)step;
+    const uint32_t nq = cdiv((uint32_t)y1, (uint32_t)step) - q_lo;
+    const uint32_t n_groups = cdiv(nq, R);
+    rg.x_lo = x0, rg.x_hi = x1, rg.row_lo = y0, rg.row_hi = y1;
+    rg.n_groups = (int)n_groups;
+    rg.grid_x = (int)cdiv((uint32_t)(x1 - x0), 32);
+    rg.n_ctas = rg.grid_x * (int)cdiv(n_groups * (uint32_t)step, 4);
+    return rg;
+  };
+  // outputs whose taps stay inside [0, W-1] x [0, H-1]: x + 2 step <= W - 1, y + 2 step <= H - 1
+  const int xin = dp.clamp_fix ? W : std::max(0, W - 2 * step);
+  const int yin = dp.clamp_fix ? H : std::max(0, H - 2 * step);
+  const int r0 = (int)row_lo, r1 = (int)row_hi;
+  AtrousRegions rs;
+  rs.r[0] = region(false, r0, std::min(r1, yin), 0, xin);  // interior
+  rs.r[1] = region(true, r0, r1, xin, W);                  // right strip
+  rs.r[2] = region(true, std::max(r0, yin), r1, 0, xin);   // bottom strip
+  const int total = rs.r[0].n_ctas + rs.r[1].n_ctas + rs.r[2].n_ctas;
+  if (total == 0) return;
+#define PT_ATROUS(RR)                                                                              \
+  atrous_kernel<RR><<<total, 128, 0, env.stream>>>(cam, dp, color_in, normal_depth, position, color_out, step, rs)
+  if (interior_r == 4)
+    PT_ATROUS(4);
+  else if (interior_r == 3)
+    PT_ATROUS(3);
+  else
+    PT_ATROUS(2);
+#undef PT_ATROUS
 }
 
 } // namespace pt

@@ -60,6 +60,8 @@ struct SceneBuild {
   double build_ms = 0.0;
   bool wide = false, host_built = false;
   uint64_t content_hash = 0; // fingerprint of the description (progressive-state files)
+  std::vector<float> sph_nodes; // sphere-group trees (16 floats per node), see DevScene
+  int sph_root_before = -1, sph_root_after = -1;
 };
 int scene_prepare(const pt_scene_desc* desc, bool host_build, SceneBuild& sb);
 int scene_upload(const pt_scene_desc* desc, const SceneBuild& sb, DeviceLBVH* dl, int device, pt_scene** out);
@@ -91,6 +93,7 @@ struct pt_scene {
   void* d_tris = nullptr;
   void* d_nodes8 = nullptr;
   void* d_spheres = nullptr;
+  void* d_sph_nodes = nullptr;
   void* d_materials = nullptr;
   pt_scene_info info{};
   uint64_t content_hash = 0;

@@ -182,10 +182,10 @@ PT_D float safe_inv(float x)
 // together with the node the walk stopped at.
 // Slab tests of both children of an inner node against the segment [tmin, tbest]
 // (the same arithmetic as trav_inner).
-PT_D void node_test(const DevScene& sc, int node, f3 id, f3 od, float tmin, float tbest, bool& t0,
+PT_D void node_test(const float4* __restrict__ nodes, int node, f3 id, f3 od, float tmin, float tbest, bool& t0,
                     bool& t1, int& c0, int& c1, float& c0min, float& c1min)
 {
-  const float4* np = sc.nodes + (size_t)node * 4;
+  const float4* np = nodes + (size_t)node * 4;
   const float4 n0 = ldg4(np + 0);
   const float4 n1 = ldg4(np + 1);
   const float4 n2 = ldg4(np + 2);
@@ -229,6 +229,63 @@ PT_D void load_node(const float4* __restrict__ np, float4& n0, float4& n1, float
   }
 }
 
+// Closest sphere of one group (spheres[lo, hi)): linear scan like the reference's object loop,
+// or — root >= 0 — an ordered walk of the group's tree.  A subtree is skipped when the ray's line
+// misses its box or enters it farther than the closest accepted hit (entry parameter x |d| =
+// distance, the unit sphere_test reports; 1e-5 slack).  Equivalent to the scan for rigidly placed
+// spheres except for the winner of an exact tie.
+PT_D void spheres_closest(const DevScene& sc, int root, uint32_t lo, uint32_t hi, f3 o, f3 d, float tmin,
+                          float& tbest, uint32_t& code, Hit& hs)
+{
+  if (root < 0) {
+    for (uint32_t i = lo; i < hi; ++i) {
+      if (sphere_test(sc.spheres + i, o, d, tmin, tbest, hs)) {
+        code = i + 1u;
+        tbest = hs.t;
+      }
+    }
+    return;
+  }
+  const f3 id = mk3(safe_inv(d.x), safe_inv(d.y), safe_inv(d.z));
+  const f3 od = mk3(o.x * id.x, o.y * id.y, o.z * id.z);
+  const float len = length3(d);
+  int stack[24]; // median-split tree over <= 2^24 spheres, 4 per leaf: at most 22 levels
+  int sp = 0, node = root;
+  for (;;) {
+    if (node >= 0) {
+      bool t0, t1;
+      int c0, c1;
+      float m0, m1;
+      node_test(sc.sph_nodes, node, id, od, 0.0f, FLT_MAX, t0, t1, c0, c1, m0, m1);
+      const float far = tbest * 1.00001f;
+      t0 = t0 && m0 * len <= far;
+      t1 = t1 && m1 * len <= far;
+      if (t0 && t1) {
+        const bool swap = m1 < m0;
+        PT_CHECK(sp < 24, "sphere tree stack overflow");
+        stack[sp++] = swap ? c0 : c1;
+        node = swap ? c1 : c0;
+        continue;
+      }
+      if (t0 || t1) {
+        node = t0 ? c0 : c1;
+        continue;
+      }
+    } else {
+      const uint32_t leaf = (uint32_t)(~node);
+      const uint32_t first = leaf >> 3, count = (leaf & 7u) + 1u;
+      for (uint32_t k = 0; k < count; ++k) {
+        if (sphere_test(sc.spheres + first + k, o, d, tmin, tbest, hs)) {
+          code = first + k + 1u;
+          tbest = hs.t;
+        }
+      }
+    }
+    if (sp == 0) return;
+    node = stack[--sp];
+  }
+}
+
 #define PREFIX_MAX 6
 // `hs` receives the full Intersection of the sphere named by `code` (valid when the ray is simple
 // and code != 0): a caller that shades the ray at once (chain_kernel) need not rebuild it.
@@ -238,12 +295,7 @@ PT_D bool classify(const DevScene& sc, f3 o, f3 d, float tmin, float tmax, float
   tbest = tmax;
   code = 0u;
   start = 0;
-  for (uint32_t i = 0; i < sc.n_spheres_before; ++i) {
-    if (sphere_test(sc.spheres + i, o, d, tmin, tbest, hs)) {
-      code = i + 1u;
-      tbest = hs.t;
-    }
-  }
+  spheres_closest(sc, sc.sph_root_before, 0u, sc.n_spheres_before, o, d, tmin, tbest, code, hs);
   bool complex_ray = false;
   if (sc.n_tris != 0u) {
     // Walk the hot top of the tree while at most one child box is hit: such a prefix needs no
@@ -258,7 +310,7 @@ PT_D bool classify(const DevScene& sc, f3 o, f3 d, float tmin, float tmax, float
       bool t0, t1;
       int c0, c1;
       float m0, m1;
-      node_test(sc, node, id, od, tmin, tbest, t0, t1, c0, c1, m0, m1);
+      node_test(sc.nodes, node, id, od, tmin, tbest, t0, t1, c0, c1, m0, m1);
       if (!t0 && !t1) {
         complex_ray = false;
         break;
@@ -272,12 +324,7 @@ PT_D bool classify(const DevScene& sc, f3 o, f3 d, float tmin, float tmax, float
   if (complex_ray) {
     code |= AUX_PENDING;
   } else {
-    for (uint32_t i = sc.n_spheres_before; i < sc.n_spheres; ++i) {
-      if (sphere_test(sc.spheres + i, o, d, tmin, tbest, hs)) {
-        code = i + 1u;
-        tbest = hs.t;
-      }
-    }
+    spheres_closest(sc, sc.sph_root_after, sc.n_spheres_before, sc.n_spheres, o, d, tmin, tbest, code, hs);
   }
   return complex_ray;
 }
@@ -315,11 +362,12 @@ PT_D bool resolve_hit(const DevScene& sc, f3 o, f3 d, float tmin, float t_aux, u
     hit = sphere_test<false>(sc.spheres + ((code & AUX_VALUE) - 1u), o, d, tmin, FLT_MAX, h);
   }
   if (code & (AUX_TRI | AUX_PENDING)) {
-    for (uint32_t i = sc.n_spheres_before; i < sc.n_spheres; ++i) {
-      if (sphere_test(sc.spheres + i, o, d, tmin, tbest, h)) {
-        hit = true;
-        tbest = h.t;
-      }
+    uint32_t after = 0u;
+    spheres_closest(sc, sc.sph_root_after, sc.n_spheres_before, sc.n_spheres, o, d, tmin, tbest, after, h);
+    if (after != 0u) {
+      hit = true;
+      // h holds the LAST accepted sphere = the closest one; when the walk found none closer than
+      // the triangle, h was not touched
     }
   }
   return hit;
