@@ -50,6 +50,7 @@ WORKLOADS = {
     "terrain": dict(kind="terrain", n=2236, w=3840, h=2160, spp=16, depth=8),
     "terrain_small": dict(kind="terrain", n=700, w=3840, h=2160, spp=16, depth=8),
     "many_materials": dict(kind="materials", w=1920, h=1080, spp=16, depth=8),
+    "many_spheres": dict(kind="spheres", n=2000, w=1920, h=1080, spp=8, depth=8),
 }
 L2_NOTE = "no flush: the per-step path state (hundreds of MB to GB) exceeds the 126 MB L2"
 METRIC = "Mrays/s (all bounces)"
@@ -70,6 +71,8 @@ def make_scene(wl):
         return pt.three_balls(wl["w"], wl["h"], wl["spp"])
     if wl["kind"] == "materials":
         return pt.many_materials_scene(wl["w"], wl["h"], wl["spp"])
+    if wl["kind"] == "spheres":
+        return pt.many_spheres_scene(wl["n"], wl["w"], wl["h"], wl["spp"])
     return pt.terrain_scene(wl["n"], wl["w"], wl["h"], wl["spp"])
 
 

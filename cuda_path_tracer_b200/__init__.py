@@ -8,7 +8,7 @@ from ._abi import (BUF_COLOR, BUF_DENOISED, BUF_DEPTH, BUF_FINAL, BUF_NORMAL, LI
 from .api import (DisplayBufferType, EdgeAvoidingATrousDenoiser, GPUMethod, HIT_DTYPE, PathTracer,
                   PathTracerGroup, Scene, cli_main, write_image_file)
 from .scene_description import (Camera, Material, Mesh, SceneDescription, bunny_like, bunny_scene,
-                                compose, heightfield, many_materials_scene, rotate, scale, terrain_scene,
+                                compose, heightfield, many_materials_scene, many_spheres_scene, rotate, scale, terrain_scene,
                                 three_balls,
                                 translate, write_obj)
 

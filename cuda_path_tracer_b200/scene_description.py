@@ -401,6 +401,38 @@ def many_materials_scene(width=1920, height=1080, spp=16, subdiv=4) -> SceneDesc
     return s
 
 
+def many_spheres_scene(n: int = 400, width=800, height=800, spp=1, seed=0, with_mesh=True) -> SceneDescription:
+    """Sphere-count stress (the reference scans its objects linearly per ray, path_tracer.cu:118):
+    n small spheres of the three material types scattered over the ground sphere, half of them
+    listed before the mesh object and half after it."""
+    rng = np.random.default_rng(seed)
+    s = SceneDescription()
+    s.filename = f"synthetic/many_spheres_{n}.json"
+    s.add_material("ground", Material.lambertian((0.8, 0.8, 0.8)))
+    s.add_material("a", Material.lambertian((0.8, 0.3, 0.3)))
+    s.add_material("b", Material.metal((0.8, 0.8, 0.8), 0.1))
+    s.add_material("c", Material.dielectric(1.5))
+    if with_mesh:
+        s.add_mesh("models/bunny.obj", bunny_like(3))
+    s.add_sphere(100.0, translate((0.0, -100.5, -1.0)), "ground")
+
+    def scatter(count):
+        for _ in range(count):
+            x, z = rng.uniform(-4.0, 4.0), rng.uniform(-9.0, -1.0)
+            r = float(rng.uniform(0.05, 0.18))
+            y = -100.5 + math.sqrt(max(0.0, (100.0 + r) ** 2 - x * x - (z + 1.0) ** 2))   # resting on the ground
+            s.add_sphere(r, translate((float(x), float(y), float(z))), "abc"[int(rng.integers(0, 3))])
+
+    scatter(n // 2)
+    if with_mesh:
+        s.add_mesh_object("models/bunny.obj", translate((0.0, -0.5, -3.0)), "a")
+    scatter(n - n // 2)
+    s.camera = Camera((0.0, 0.6, 1.0), (1.0, 0.0, 0.0, 0.0), math.radians(60.0))
+    s.resolution = (width, height)
+    s.spp = spp
+    return s
+
+
 def terrain_scene(n: int = 2236, width=3840, height=2160, spp=16, seed=0) -> SceneDescription:
     """BASELINE.json configs[3]: one procedural ~2*n^2-triangle mesh, diffuse albedo 0.7."""
     s = SceneDescription()

@@ -463,3 +463,34 @@ def test_failed_resize_leaves_a_context_that_refuses_work():
     tr.max_iterations = 4
     tr.render(sd.camera, 1)
     assert tr.download(DB.color).shape == (48, 32, 3)
+
+
+def test_sphere_group_trees_match_the_linear_scan(oracle):
+    """Scenes with many spheres (the reference scans its objects linearly per ray):
+    groups of more than 32 rigidly placed spheres are walked through a small tree.  Closest hits
+    and the image equal the oracle's linear object loop; ties aside, the order of the tests does
+    not matter for rigid spheres."""
+    sd = pt.many_spheres_scene(300, 160, 120)
+    w, h = sd.resolution
+    scene = pt.Scene.from_description(sd)
+    osc = oracle.scene(sd)
+    prim, rng = _rays_for(oracle, sd, w, h, n_random=6000, seed=3)
+    ref = osc.trace_batch(prim, 0)
+    ours = scene.trace_batch(prim)
+    assert (ref["prim"][ref["t"] > 0] < 0).mean() > 0.5          # most hits are spheres
+    _check_hits(ours, ref, allow_frac=5e-4)
+    sec = _secondary(prim, ref, rng)
+    _check_hits(scene.trace_batch(sec), osc.trace_batch(sec, 0), allow_frac=1e-3)
+    tr = pt.PathTracer(max_depth=6)
+    tr.create_buffers((w, h), scene)
+    tr.render(sd.camera, 2)
+    c = tr.download(DB.color)
+    rc, _, _, rrays = osc.render(sd.camera, w, h, 2, 6)
+    diff = np.abs(c - rc).max(axis=2)
+    assert np.median(diff) < 1e-5 and (diff > 1e-3).mean() < 0.02, (np.median(diff), (diff > 1e-3).mean())
+    assert abs(int(tr.stats().rays) - rrays) <= 0.005 * rrays
+    # a sphere-only scene (no mesh at all) takes the same path
+    so = pt.many_spheres_scene(200, 96, 96, with_mesh=False)
+    s2, o2 = pt.Scene.from_description(so), oracle.scene(so)
+    p2, _ = _rays_for(oracle, so, 96, 96, n_random=3000, seed=4)
+    _check_hits(s2.trace_batch(p2), o2.trace_batch(p2, 0), allow_frac=5e-4)
