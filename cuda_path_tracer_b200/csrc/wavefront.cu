@@ -234,10 +234,15 @@ PT_D void load_node(const float4* __restrict__ np, float4& n0, float4& n1, float
 // misses its box or enters it farther than the closest accepted hit (entry parameter x |d| =
 // distance, the unit sphere_test reports; 1e-5 slack).  Equivalent to the scan for rigidly placed
 // spheres except for the winner of an exact tie.
+// ST is a template parameter of everything that tests spheres: the kernels of scenes without a
+// sphere tree (every bundled scene) are compiled without the walk (measured: with the walk
+// compiled in, the chain kernels of the headline scene went from 71-80 to 78-80 registers plus
+// 96 B of local stack and lost 2 %).
+template <bool ST>
 PT_D void spheres_closest(const DevScene& sc, int root, uint32_t lo, uint32_t hi, f3 o, f3 d, float tmin,
                           float& tbest, uint32_t& code, Hit& hs)
 {
-  if (root < 0) {
+  if (!ST || root < 0) {
     for (uint32_t i = lo; i < hi; ++i) {
       if (sphere_test(sc.spheres + i, o, d, tmin, tbest, hs)) {
         code = i + 1u;
@@ -289,13 +294,14 @@ PT_D void spheres_closest(const DevScene& sc, int root, uint32_t lo, uint32_t hi
 #define PREFIX_MAX 6
 // `hs` receives the full Intersection of the sphere named by `code` (valid when the ray is simple
 // and code != 0): a caller that shades the ray at once (chain_kernel) need not rebuild it.
+template <bool ST = false>
 PT_D bool classify(const DevScene& sc, f3 o, f3 d, float tmin, float tmax, float& tbest,
                    uint32_t& code, int& start, Hit& hs)
 {
   tbest = tmax;
   code = 0u;
   start = 0;
-  spheres_closest(sc, sc.sph_root_before, 0u, sc.n_spheres_before, o, d, tmin, tbest, code, hs);
+  spheres_closest<ST>(sc, sc.sph_root_before, 0u, sc.n_spheres_before, o, d, tmin, tbest, code, hs);
   bool complex_ray = false;
   if (sc.n_tris != 0u) {
     // Walk the hot top of the tree while at most one child box is hit: such a prefix needs no
@@ -324,18 +330,20 @@ PT_D bool classify(const DevScene& sc, f3 o, f3 d, float tmin, float tmax, float
   if (complex_ray) {
     code |= AUX_PENDING;
   } else {
-    spheres_closest(sc, sc.sph_root_after, sc.n_spheres_before, sc.n_spheres, o, d, tmin, tbest, code, hs);
+    spheres_closest<ST>(sc, sc.sph_root_after, sc.n_spheres_before, sc.n_spheres, o, d, tmin, tbest, code, hs);
   }
   return complex_ray;
 }
+template <bool ST = false>
 PT_D bool classify(const DevScene& sc, f3 o, f3 d, float tmin, float tmax, float& tbest,
                    uint32_t& code, int& start)
 {
   Hit hs;
-  return classify(sc, o, d, tmin, tmax, tbest, code, start, hs);
+  return classify<ST>(sc, o, d, tmin, tmax, tbest, code, start, hs);
 }
 
 // Rebuilds the Intersection (intersection.hpp:8-14) from the 8-byte aux word.
+template <bool ST = false>
 PT_D bool resolve_hit(const DevScene& sc, f3 o, f3 d, float tmin, float t_aux, uint32_t code, Hit& h)
 {
   bool hit = false;
@@ -363,7 +371,7 @@ PT_D bool resolve_hit(const DevScene& sc, f3 o, f3 d, float tmin, float t_aux, u
   }
   if (code & (AUX_TRI | AUX_PENDING)) {
     uint32_t after = 0u;
-    spheres_closest(sc, sc.sph_root_after, sc.n_spheres_before, sc.n_spheres, o, d, tmin, tbest, after, h);
+    spheres_closest<ST>(sc, sc.sph_root_after, sc.n_spheres_before, sc.n_spheres, o, d, tmin, tbest, after, h);
     if (after != 0u) {
       hit = true;
       // h holds the LAST accepted sphere = the closest one; when the walk found none closer than
@@ -631,7 +639,7 @@ enum { SRC_QUEUE = 1, SRC_BATCH = 2 };
 // MINB: resident CTAs per SM the register allocation is bounded for (8 -> 64 registers, 50 % of
 // the warp slots; 10 -> 48; 12 -> 40); L256: node fetch with two 256-bit loads.  Both are
 // run-time choices between instantiations (PT_TRAV="minb,l256"), measured in profiles/README.md.
-template <int SRC, int MINB, bool L256>
+template <int SRC, int MINB, bool L256, bool ST>
 __global__ void __launch_bounds__(EXT_THREADS, MINB)
 traverse_kernel(const DevScene sc, const PathState ps, const uint32_t* __restrict__ tq,
                 const uint32_t* __restrict__ n_ptr, uint32_t n_host, uint32_t* __restrict__ work,
@@ -672,7 +680,7 @@ traverse_kernel(const DevScene sc, const PathState ps, const uint32_t* __restric
             const float4 ro = batch_rays[2 * (size_t)idx], rd = batch_rays[2 * (size_t)idx + 1];
             float tbest;
             int start;
-            const bool complex_ray = classify(sc, xyz(ro), xyz(rd), ro.w, rd.w, tbest, code, start);
+            const bool complex_ray = classify<ST>(sc, xyz(ro), xyz(rd), ro.w, rd.w, tbest, code, start);
             trav_init(T, xyz(ro), xyz(rd), ro.w, tbest, start, stack);
             if (!complex_ray) T.node = PT_SENTINEL;
             has = true;
@@ -734,7 +742,7 @@ traverse_kernel(const DevScene sc, const PathState ps, const uint32_t* __restric
         if (T.best >= 0) code = AUX_TRI | (uint32_t)T.best;
         Hit h;
         HitRecord r;
-        if (resolve_hit(sc, T.o, T.d, T.tmin, T.tbest, code, h)) {
+        if (resolve_hit<ST>(sc, T.o, T.d, T.tmin, T.tbest, code, h)) {
           r.t = h.t;
           r.px = h.p.x, r.py = h.p.y, r.pz = h.p.z;
           r.nx = h.n.x, r.ny = h.n.y, r.nz = h.n.z;
@@ -1234,7 +1242,7 @@ PT_D void mbar_wait(unsigned long long* bar, uint32_t parity)
   }
 }
 
-template <bool FIRST, int TMA>
+template <bool FIRST, int TMA, bool ST>
 __global__ void __launch_bounds__(FULL_THREADS)
 chain_kernel(const DevScene sc, const PathState ps, const PassParams pp, const ParkBuf in,
              const uint32_t* __restrict__ n_ptr, uint32_t n_first, const ParkBuf out,
@@ -1348,7 +1356,7 @@ chain_kernel(const DevScene sc, const PathState ps, const PassParams pp, const P
         tmin = 1e-4f;
         color = mk3(1.0f, 1.0f, 1.0f);
         depth = 0;
-        need_traversal = classify(sc, o, d, tmin, FLT_MAX, tbest, code, start, h);
+        need_traversal = classify<ST>(sc, o, d, tmin, FLT_MAX, tbest, code, start, h);
         have_hit = true;
       } else {
         uint32_t slot = idx;
@@ -1381,7 +1389,7 @@ chain_kernel(const DevScene sc, const PathState ps, const PassParams pp, const P
         ++rays_local;
         // a simple ray's sphere hit comes straight from classification (same arithmetic, same
         // root as resolve_hit would pick); traversed rays rebuild theirs from the aux word
-        const bool hit = have_hit ? code != 0u : resolve_hit(sc, o, d, tmin, tbest, code, h);
+        const bool hit = have_hit ? code != 0u : resolve_hit<ST>(sc, o, d, tmin, tbest, code, h);
         if (depth == 0u) {
           st_state(ps.gbuf + pid,
                    hit ? make_float4(h.n.x, h.n.y, h.n.z, h.t) : make_float4(-d.x, -d.y, -d.z, 1e6f), cs);
@@ -1393,7 +1401,7 @@ chain_kernel(const DevScene sc, const PathState ps, const PassParams pp, const P
         const DevMaterial mat = sc.materials[h.material];
         scatter(mat, h, o, d, tmin, color, rng);
         if (++depth == max_depth) break; // survivors contribute their throughput (path_tracer.cu:252-265)
-        need_traversal = classify(sc, o, d, tmin, FLT_MAX, tbest, code, start, h);
+        need_traversal = classify<ST>(sc, o, d, tmin, FLT_MAX, tbest, code, start, h);
         have_hit = true;
       }
       if (!park) st_state(ps.thr + pid, mk4(color, __uint_as_float(rng)), cs); // the path's contribution
@@ -1506,7 +1514,7 @@ static void launch_t2v(const LaunchEnv& env, const DevScene& sc, const PathState
                        const uint32_t* n_ptr, uint32_t n_host, uint32_t* work, const float4* rays,
                        HitRecord* out, uint32_t max_grid, const BinLists& bins)
 {
-  auto kern = traverse_kernel<SRC, MINB, L256>;
+  auto kern = traverse_kernel<SRC, MINB, L256, false>;
   static int nb[64] = {0};
   static size_t sm[64] = {0};
   const Tunables& t = tunables();
@@ -1521,6 +1529,16 @@ static void launch_t2(const LaunchEnv& env, const DevScene& sc, const PathState&
                       HitRecord* out, uint32_t max_grid, const BinLists& bins)
 {
   const Tunables& t = tunables();
+  if (SRC == SRC_BATCH && (sc.sph_root_before >= 0 || sc.sph_root_after >= 0)) {
+    // the parity hook of a scene with sphere trees: classification + hit rebuild walk them
+    auto kern = traverse_kernel<SRC, EXT_MIN_BLOCKS, false, true>;
+    static int nb[64] = {0};
+    static size_t sm[64] = {0};
+    const uint32_t grid = min(persistent_grid(kern, env, EXT_THREADS, 0, nb, sm), max_grid);
+    kern<<<grid, EXT_THREADS, 0, env.stream>>>(sc, ps, tq, n_ptr, n_host, work, rays, out, t.refill, t.inner_min,
+                                               t.stream_state, bins);
+    return;
+  }
   int minb = t.trav_minb, l256 = t.trav_l256;
   if (minb == 0) {
     // Measured (profiles/README.md, round 2): a tree that lives in L1/L2 is bound by L1 data-pipe
@@ -1617,27 +1635,38 @@ void launch_chain(const LaunchEnv& env, const DevScene& sc, const PassBuffers& p
   // bunny frame: the primary launch likes a fine grid (its per-item cost varies with how many
   // in-register bounces follow: 6 -> 4.03 ms, 24 -> 3.73 ms), the re-entry launches do not
   // (6 -> 5.09 ms, 24 -> 5.17 ms).
+  const bool sphere_trees = sc.sph_root_before >= 0 || sc.sph_root_after >= 0;
   const uint32_t grid = (uint32_t)env.sms * (uint32_t)tunables().chain_grid;
   const uint32_t grid_first = (uint32_t)env.sms * (uint32_t)tunables().chain_grid0;
   if (iter == 0) {
-    chain_kernel<true, 0><<<min(grid_first, cdiv(n_items_first, FULL_THREADS)), FULL_THREADS, 0, env.stream>>>(
-        sc, pb.ps, pp, ParkBuf{}, nullptr, n_items_first, pb.park[0], pb.tcounters + 0, max_depth,
-        pb.total_rays, BinLists{nullptr, nullptr, 0u});
+    const uint32_t g0 = min(grid_first, cdiv(n_items_first, FULL_THREADS));
+    if (sphere_trees)
+      chain_kernel<true, 0, true><<<g0, FULL_THREADS, 0, env.stream>>>(sc, pb.ps, pp, ParkBuf{}, nullptr, n_items_first,
+                                                                     pb.park[0], pb.tcounters + 0, max_depth,
+                                                                     pb.total_rays, BinLists{nullptr, nullptr, 0u});
+    else
+      chain_kernel<true, 0, false><<<g0, FULL_THREADS, 0, env.stream>>>(sc, pb.ps, pp, ParkBuf{}, nullptr, n_items_first,
+                                                                      pb.park[0], pb.tcounters + 0, max_depth,
+                                                                      pb.total_rays, BinLists{nullptr, nullptr, 0u});
   } else {
     // consumes the traversed state of iteration iter-1, parks into the buffer of iteration iter
     const BinLists bins = bins_of(pb, iter - 1);
-    const int tma = bins.list == nullptr ? tunables().chain_tma : 0;
-    if (tma == 1) {
+    const int tma = bins.list == nullptr && !sphere_trees ? tunables().chain_tma : 0;
+    if (sphere_trees) {
+      chain_kernel<false, 0, true><<<grid, FULL_THREADS, 0, env.stream>>>(
+          sc, pb.ps, pp, pb.park[(iter - 1) & 1], pb.tcounters + (iter - 1), 0u, pb.park[iter & 1],
+          pb.tcounters + iter, max_depth, pb.total_rays, bins);
+    } else if (tma == 1) {
       // (34 KB of dynamic shared memory: below the 48 KB that needs no opt-in)
-      chain_kernel<false, 1><<<grid, FULL_THREADS, 2 * CHAIN_STAGE_BYTES, env.stream>>>(
+      chain_kernel<false, 1, false><<<grid, FULL_THREADS, 2 * CHAIN_STAGE_BYTES, env.stream>>>(
           sc, pb.ps, pp, pb.park[(iter - 1) & 1], pb.tcounters + (iter - 1), 0u, pb.park[iter & 1],
           pb.tcounters + iter, max_depth, pb.total_rays, bins);
     } else if (tma == 2) {
-      chain_kernel<false, 2><<<grid, FULL_THREADS, 2 * CHAIN_STAGE_BYTES, env.stream>>>(
+      chain_kernel<false, 2, false><<<grid, FULL_THREADS, 2 * CHAIN_STAGE_BYTES, env.stream>>>(
           sc, pb.ps, pp, pb.park[(iter - 1) & 1], pb.tcounters + (iter - 1), 0u, pb.park[iter & 1],
           pb.tcounters + iter, max_depth, pb.total_rays, bins);
     } else {
-      chain_kernel<false, 0><<<grid, FULL_THREADS, 0, env.stream>>>(
+      chain_kernel<false, 0, false><<<grid, FULL_THREADS, 0, env.stream>>>(
           sc, pb.ps, pp, pb.park[(iter - 1) & 1], pb.tcounters + (iter - 1), 0u, pb.park[iter & 1],
           pb.tcounters + iter, max_depth, pb.total_rays, bins);
     }

@@ -392,6 +392,7 @@ def test_ray_binning_changes_the_order_not_the_image():
     frames = []
     for sort in (False, True):
         tr = pt.PathTracer(max_depth=8, sort_rays=sort)
+        tr.max_iterations = 4
         tr.create_buffers((w, h), sd)
         tr.render(sd.camera, 4)
         tr.synchronize()
@@ -482,6 +483,7 @@ def test_sphere_group_trees_match_the_linear_scan(oracle):
     sec = _secondary(prim, ref, rng)
     _check_hits(scene.trace_batch(sec), osc.trace_batch(sec, 0), allow_frac=1e-3)
     tr = pt.PathTracer(max_depth=6)
+    tr.max_iterations = 2
     tr.create_buffers((w, h), scene)
     tr.render(sd.camera, 2)
     c = tr.download(DB.color)
