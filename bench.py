@@ -185,8 +185,6 @@ class Dist:
         torch.cuda.set_device(self.local_rank)
         if self.multi:
             import torch.distributed as dist
-            # 16 host threads per process x N processes oversubscribe the box: share them
-            os.environ.setdefault("OMP_NUM_THREADS", str(max(1, (os.cpu_count() or 8) // self.world)))
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
             self.dist = dist
 
@@ -428,7 +426,9 @@ def ref_library_for(sd, wl):
 
 def ref_render(sd, wl, spp, steps, warmup):
     lib, depth = ref_library_for(sd, wl)
-    rt = lib.tracer(sd, wl["w"], wl["h"], wl["depth"])
+    t0 = time.perf_counter()
+    rt = lib.tracer(sd, wl["w"], wl["h"], wl["depth"])   # build_scene(): bvh_from_mesh on one host thread + uploads
+    create_s = time.perf_counter() - t0
     times, rays = [], 0
     for i in range(warmup + steps):
         ms, r = rt.render_timed(sd.camera, spp)
@@ -438,7 +438,7 @@ def ref_render(sd, wl, spp, steps, warmup):
     rt.close()
     total = sum(times)
     return {"value": rays / (total * 1e-3) * 1e-6, "unit": "Mrays/s", "ms_per_step": total / len(times),
-            "spp_per_step": spp, "steps": steps, "best_step_mrays": max(0.0, rays / len(times) / (min(times) * 1e-3) * 1e-6),
+            "spp_per_step": spp, "steps": steps, "scene_create_s": round(create_s, 3), "best_step_mrays": max(0.0, rays / len(times) / (min(times) * 1e-3) * 1e-6),
             "build": {"library": os.path.basename(lib.path), "traversal_stack": lib.stack_size,
                       "reference_bvh_depth": depth, "flags": "-O3 -DNDEBUG -arch=sm_100 -rdc=true (the reference's)",
                       "patches": REF_PATCHES, "mode": "streaming (CLI default)"}}
@@ -538,9 +538,13 @@ def main():
         run_reference(args)
         return
 
+    D = Dist()
+    if D.multi:
+        # before the library (and its OpenMP runtime) loads: N processes share the host's threads
+        # instead of each starting one per core (scene build 5 -> 97 ms across ranks in round 1)
+        os.environ.setdefault("OMP_NUM_THREADS", str(max(1, (os.cpu_count() or 8) // D.world)))
     import cuda_path_tracer_b200 as pt
     pt.load_library()  # raises if the CUDA extension is missing: no fallback
-    D = Dist()
     D.init()
     wl = WORKLOADS[args.workload]
     head, sd = bench_render(args.workload, args.steps, args.warmup, D)

@@ -72,7 +72,7 @@ def test_terrain_4k_frame_matches_the_golden_frame():
     sd = pt.terrain_scene(N, W, H, SPP)
     tr = pt.PathTracer(max_depth=DEPTH)
     tr.create_buffers((W, H), sd)
-    tr.render(sd.camera, SPP)
+    tr.render_range(sd.camera, 0, SPP)
     tr.synchronize()
     a, n, d = tr.download(DB.color), tr.download(DB.normal), tr.download(DB.depth).reshape(H, W)
     rays = int(tr.stats().rays)
