@@ -281,6 +281,7 @@ struct PassParams {
   uint32_t tiles_x, tiles_y; // 8x4-pixel warp tiles (tiles_y = tile rows of the rendered band)
   uint32_t tile_y0;          // first tile row of the band (row-band sharding), else 0
   uint32_t pixel_begin, pixel_end; // pixel range of the band (accumulate)
+  uint32_t band_pixels;            // pixel_end - pixel_begin: path id = sample * band_pixels + (pixel - pixel_begin)
   FastDiv fd_per_sample, fd_tiles_x, fd_width; // divisors of the bounce-0 index map
   FastDiv fd_samples, fd_sbx;                  // (tile-major orders)
   uint32_t sbx;     // 8x8-tile super-blocks per row (order 2)

@@ -706,6 +706,11 @@ int pt_scene_load_file(const char* json_path, int device, pt_scene** out, pt_sce
 // ----------------------------------------------------------------- context
 static void free_image_buffers(pt_ctx* c)
 {
+  if (c->lane2) free_image_buffers(c->lane2);
+  if (c->is_lane) { // a lane shares the parent's frame buffers: only the path state is its own
+    c->d_sums = nullptr;
+    c->own_sums = false;
+  }
   cudaFree(c->d_state);
   cudaFree(c->pb.queue[0]);
   cudaFree(c->pb.queue[1]);
@@ -716,7 +721,7 @@ static void free_image_buffers(pt_ctx* c)
   cudaFree(c->pb.bin_list);
   c->pb.bin_list = nullptr;
   if (c->own_sums) cudaFree(c->d_sums);
-  c->own_sums = true;
+  c->own_sums = !c->is_lane;
   for (auto& p : c->d_dn) {
     cudaFree(p);
     p = nullptr;
@@ -761,9 +766,12 @@ static int alloc_image_buffers(pt_ctx* c, uint32_t width, uint32_t height)
     spp_pass = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(64, target / c->pixels));
   }
   c->samples_per_pass = spp_pass;
+  // two lanes: each holds path state for half the frame's tile rows (rounded up)
+  const uint32_t tile_rows = (height + 3) / 4;
+  c->rows_cap = (c->lane2 || c->is_lane) ? std::min(height, ((tile_rows + 1) / 2) * 4) : height;
   // rounded up to whole 256-record tiles: the chain kernel stages the parked state tile by tile
   // with bulk copies of fixed size (and every plane stays 16-byte aligned)
-  const size_t cap = (((size_t)c->pixels * spp_pass) + 255) & ~(size_t)255;
+  const size_t cap = (((size_t)width * c->rows_cap * spp_pass) + 255) & ~(size_t)255;
   if (cap > (1ull << 30)) return fail(PT_ERR_INVALID, "wavefront too large");
   c->pb.capacity = (uint32_t)cap;
   if (c->params.rng_mode == PT_RNG_SLOT_RESEED) {
@@ -800,17 +808,50 @@ static int alloc_image_buffers(pt_ctx* c, uint32_t width, uint32_t height)
     c->pb.park[1].pid = ids + cap;
     if (c->params.sort_rays) PT_CUDA(cudaMalloc((void**)&c->pb.bin_list, cap * PT_BINS * sizeof(uint32_t)));
   }
+  c->iteration = 0;
+  c->final_rgb = nullptr;
+  if (c->is_lane) return PT_OK; // frame buffers belong to the parent
   PT_CUDA(cudaMalloc((void**)&c->d_sums, (size_t)c->pixels * sizeof(float4) * 2));
   PT_CUDA(cudaMemsetAsync(c->d_sums, 0, (size_t)c->pixels * sizeof(float4) * 2, c->stream));
   PT_CUDA(cudaMalloc((void**)&c->d_rgba, (size_t)c->pixels * 4));
   PT_CUDA(cudaMalloc((void**)&c->d_export, (size_t)c->pixels * 3 * 4));
-  c->iteration = 0;
-  c->final_rgb = nullptr;
+  if (c->lane2) {
+    // same pass size as this context, half the rows, this context's sums
+    c->lane2->params.samples_per_pass = (int32_t)c->samples_per_pass;
+    const int rc = alloc_image_buffers(c->lane2, width, height);
+    if (rc != PT_OK) return rc;
+    c->lane2->d_sums = c->d_sums;
+    c->lane2->own_sums = false;
+  }
   return PT_OK;
 }
 
+// PT_LANES=1|2 (read once): 2 = every pixel-stream context renders its band as two half-bands on
+// two streams (internal.h, pt_ctx::lane2).
+#ifndef PT_DEFAULT_LANES
+#define PT_DEFAULT_LANES 1
+#endif
+static int lanes_setting()
+{
+  static const int n = [] {
+    const char* v = getenv("PT_LANES");
+    const int k = v ? atoi(v) : PT_DEFAULT_LANES;
+    return k == 2 ? 2 : 1;
+  }();
+  return n;
+}
+
+static int pt_ctx_create_core(const pt_scene* scene, uint32_t width, uint32_t height, const pt_params* params,
+                              void* stream, bool as_lane, pt_ctx** out);
+
 static int pt_ctx_create_impl(const pt_scene* scene, uint32_t width, uint32_t height, const pt_params* params,
                   void* stream, pt_ctx** out)
+{
+  return pt_ctx_create_core(scene, width, height, params, stream, false, out);
+}
+
+static int pt_ctx_create_core(const pt_scene* scene, uint32_t width, uint32_t height, const pt_params* params,
+                              void* stream, bool as_lane, pt_ctx** out)
 {
   if (!scene || !out) return fail(PT_ERR_INVALID, "pt_ctx_create: null argument");
   *out = nullptr;
@@ -826,6 +867,17 @@ static int pt_ctx_create_impl(const pt_scene* scene, uint32_t width, uint32_t he
   pt_ctx* c = new pt_ctx();
   c->scene = scene;
   c->params = p;
+  c->is_lane = as_lane;
+  if (!as_lane && lanes_setting() == 2 && p.rng_mode == PT_RNG_PIXEL_STREAM && height >= 16) {
+    // the second lane first: alloc_image_buffers below sizes both for half the rows
+    pt_ctx* lane = nullptr;
+    const int lrc = pt_ctx_create_core(scene, width, height, &p, nullptr, true, &lane);
+    if (lrc != PT_OK) {
+      delete c;
+      return lrc;
+    }
+    c->lane2 = lane;
+  }
   cudaDeviceProp prop;
   cudaError_t e = cudaGetDeviceProperties(&prop, scene->device);
   if (e != cudaSuccess) {
@@ -862,10 +914,14 @@ static int pt_ctx_create_impl(const pt_scene* scene, uint32_t width, uint32_t he
     for (auto& ev : c->bounce_events)
       if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) break;
   } while (0);
+  if (e == cudaSuccess && c->lane2) {
+    if ((e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming)) == cudaSuccess)
+      e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+  }
   if (e != cudaSuccess) {
     rc = cuda_fail(e, "context allocation");
-  } else {
-    rc = alloc_image_buffers(c, width, height);
+  } else if (!as_lane) {
+    rc = alloc_image_buffers(c, width, height); // also the lane's
   }
   if (rc != PT_OK) {
     pt_ctx_destroy(c);
@@ -886,7 +942,15 @@ int pt_ctx_destroy(pt_ctx* c)
   if (!c) return PT_OK;
   cudaSetDevice(c->scene->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  free_image_buffers(c);
+  if (c->lane2 && c->lane2->stream) cudaStreamSynchronize(c->lane2->stream);
+  free_image_buffers(c); // (the lane's too)
+  if (c->lane2) {
+    pt_ctx* lane = c->lane2;
+    c->lane2 = nullptr;
+    pt_ctx_destroy(lane);
+  }
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   cudaFree(c->d_counters);
   cudaFreeHost(c->h_counts);
   for (auto ev : c->bounce_events)
@@ -906,6 +970,7 @@ int pt_ctx_resize(pt_ctx* c, uint32_t width, uint32_t height)
     return fail(PT_ERR_INVALID, "unsupported resolution");
   PT_CUDA(cudaSetDevice(c->scene->device));
   PT_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->lane2) PT_CUDA(cudaStreamSynchronize(c->lane2->stream));
   free_image_buffers(c);
   const int rc = alloc_image_buffers(c, width, height);
   if (rc != PT_OK) {
@@ -1041,18 +1106,23 @@ static void prof_collect(pt_ctx* c)
   c->prof_tags.clear();
 }
 
-// One wavefront pass over `samples` consecutive iterations of every pixel.
-static int render_pass(pt_ctx* c, const pt_camera& cam, uint32_t first_iteration, uint32_t samples)
+// One wavefront pass over `samples` consecutive iterations of every pixel of rows
+// [row_begin, row_end), on c's own stream and path-state buffers.
+static int render_pass(pt_ctx* c, const pt_camera& cam, uint32_t first_iteration, uint32_t samples,
+                       uint32_t row_begin, uint32_t row_end)
 {
   const LaunchEnv env{c->stream, c->sms};
   PassParams pp{};
   pp.cam = make_dev_camera(cam, c->width, c->height);
   pp.pixels = c->pixels;
   pp.tiles_x = (c->width + 7) / 8;
-  pp.tiles_y = (c->row_end - c->row_begin + 3) / 4;
-  pp.tile_y0 = c->row_begin / 4;
-  pp.pixel_begin = c->row_begin * c->width;
-  pp.pixel_end = c->row_end * c->width;
+  pp.tiles_y = (row_end - row_begin + 3) / 4;
+  pp.tile_y0 = row_begin / 4;
+  pp.pixel_begin = row_begin * c->width;
+  pp.pixel_end = row_end * c->width;
+  pp.band_pixels = pp.pixel_end - pp.pixel_begin;
+  if ((uint64_t)samples * pp.band_pixels > c->pb.capacity)
+    return fail(PT_ERR_INVALID, "render_pass: the band does not fit the path-state buffers");
   pp.fd_per_sample = make_fastdiv(pp.tiles_x * pp.tiles_y * 32u);
   pp.fd_tiles_x = make_fastdiv(pp.tiles_x);
   pp.fd_width = make_fastdiv(c->width);
@@ -1073,7 +1143,7 @@ static int render_pass(pt_ctx* c, const pt_camera& cam, uint32_t first_iteration
   const uint32_t n0 = (uint32_t)n0_64;
   const uint32_t max_depth = (uint32_t)c->params.max_depth;
   const bool stable = c->params.rng_mode == PT_RNG_SLOT_RESEED;
-  if (stable && (c->row_begin != 0 || c->row_end != c->height))
+  if (stable && (row_begin != 0 || row_end != c->height))
     return fail(PT_ERR_INVALID, "row bands need PT_RNG_PIXEL_STREAM (slot re-seeding numbers the whole frame)");
   const uint32_t kLookBehind = 2;
 
@@ -1159,6 +1229,25 @@ static int render_pass(pt_ctx* c, const pt_camera& cam, uint32_t first_iteration
   return PT_OK;
 }
 
+// The pass of the context's band: one lane, or the band's two halves on two streams.  The second
+// lane starts after everything already queued on the main stream (a restart's memset of the sums,
+// a resolve still reading them) and the main stream continues after both halves have accumulated.
+static int render_pass_lanes(pt_ctx* c, const pt_camera& cam, uint32_t first_iteration, uint32_t samples)
+{
+  pt_ctx* lane = c->lane2;
+  const uint32_t t0 = c->row_begin / 4, t1 = (c->row_end + 3) / 4;
+  const uint32_t mid = std::min(c->row_end, (t0 + (t1 - t0 + 1) / 2) * 4);
+  if (!lane || mid >= c->row_end || mid <= c->row_begin)
+    return render_pass(c, cam, first_iteration, samples, c->row_begin, c->row_end);
+  PT_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+  PT_CUDA(cudaStreamWaitEvent(lane->stream, c->ev_fork, 0));
+  int rc = render_pass(c, cam, first_iteration, samples, c->row_begin, mid);
+  if (rc == PT_OK) rc = render_pass(lane, cam, first_iteration, samples, mid, c->row_end);
+  PT_CUDA(cudaEventRecord(c->ev_join, lane->stream));
+  PT_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+  return rc;
+}
+
 int pt_render_range(pt_ctx* c, const pt_camera* cam, int first_iteration, int n_iterations)
 {
   if (!c || !cam) return fail(PT_ERR_INVALID, "pt_render_range: null argument");
@@ -1181,7 +1270,7 @@ int pt_render_range(pt_ctx* c, const pt_camera* cam, int first_iteration, int n_
   int done = 0;
   while (done < n_iterations) {
     const uint32_t s = (uint32_t)std::min<int>(n_iterations - done, (int)c->samples_per_pass);
-    int rc = render_pass(c, *cam, (uint32_t)(first_iteration + done), s);
+    int rc = render_pass_lanes(c, *cam, (uint32_t)(first_iteration + done), s);
     if (rc != PT_OK) return rc;
     done += (int)s;
   }
@@ -1319,11 +1408,13 @@ int pt_ctx_bind_sums(pt_ctx* c, void* device_ptr)
     if (c->own_sums) cudaFree(c->d_sums);
     c->d_sums = (float4*)device_ptr;
     c->own_sums = false;
+    if (c->lane2) c->lane2->d_sums = c->d_sums;
   } else if (!c->own_sums) {
     c->d_sums = nullptr;
     PT_CUDA(cudaMalloc((void**)&c->d_sums, (size_t)c->pixels * sizeof(float4) * 2));
     c->own_sums = true;
     PT_CUDA(cudaMemsetAsync(c->d_sums, 0, (size_t)c->pixels * sizeof(float4) * 2, c->stream));
+    if (c->lane2) c->lane2->d_sums = c->d_sums;
   }
   return PT_OK;
 }
@@ -1473,18 +1564,44 @@ int pt_ctx_upload_frame(pt_ctx* c, const float* color3, const float* normal3, co
   return PT_OK;
 }
 
-int pt_get_stats(pt_ctx* c, pt_stats* out)
+// rays / launches / kernel times of one context (its own stream synchronised)
+static int collect_stats(pt_ctx* c)
 {
-  if (!c || !out) return fail(PT_ERR_INVALID, "pt_get_stats: null argument");
-  PT_CUDA(cudaSetDevice(c->scene->device));
   PT_CUDA(cudaStreamSynchronize(c->stream));
   prof_collect(c);
   unsigned long long rays[2] = {0, 0};
   PT_CUDA(cudaMemcpy(rays, c->pb.total_rays, sizeof(rays), cudaMemcpyDeviceToHost));
   c->stats.rays = rays[0];
   c->stats.rays_traversed = rays[1];
+  return PT_OK;
+}
+
+int pt_get_stats(pt_ctx* c, pt_stats* out)
+{
+  if (!c || !out) return fail(PT_ERR_INVALID, "pt_get_stats: null argument");
+  PT_CUDA(cudaSetDevice(c->scene->device));
+  int rc = collect_stats(c);
+  if (rc != PT_OK) return rc;
   c->stats.iterations = (uint32_t)c->iteration;
   *out = c->stats;
+  if (c->lane2) { // the second lane's share of every additive counter
+    rc = collect_stats(c->lane2);
+    if (rc != PT_OK) return rc;
+    const pt_stats& l = c->lane2->stats;
+    out->rays += l.rays;
+    out->rays_traversed += l.rays_traversed;
+    out->samples += l.samples;
+    out->passes += l.passes;
+    out->kernel_launches += l.kernel_launches;
+    out->ms_raygen_extend0 += l.ms_raygen_extend0;
+    out->ms_extend += l.ms_extend;
+    out->ms_shade += l.ms_shade;
+    out->ms_compact += l.ms_compact;
+    out->ms_accumulate += l.ms_accumulate;
+    out->n_extend_launches += l.n_extend_launches;
+    out->n_shade_launches += l.n_shade_launches;
+    out->max_bounce_reached = std::max(out->max_bounce_reached, l.max_bounce_reached);
+  }
   return PT_OK;
 }
 
@@ -1492,10 +1609,13 @@ int pt_reset_stats(pt_ctx* c)
 {
   if (!c) return fail(PT_ERR_INVALID, "null context");
   PT_CUDA(cudaSetDevice(c->scene->device));
-  PT_CUDA(cudaStreamSynchronize(c->stream));
-  PT_CUDA(cudaMemset(c->pb.total_rays, 0, 2 * sizeof(unsigned long long)));
-  prof_collect(c);
-  c->stats = pt_stats{};
+  for (pt_ctx* k : {c, c->lane2}) {
+    if (!k) continue;
+    PT_CUDA(cudaStreamSynchronize(k->stream));
+    PT_CUDA(cudaMemset(k->pb.total_rays, 0, 2 * sizeof(unsigned long long)));
+    prof_collect(k);
+    k->stats = pt_stats{};
+  }
   return PT_OK;
 }
 

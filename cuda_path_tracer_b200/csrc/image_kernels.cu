@@ -115,20 +115,21 @@ accumulate_kernel(const PathState ps, const PassParams pp, float4* __restrict__ 
     if (pp.rng_mode == 1u) {
       unsigned long long r = (unsigned long long)(pp.pixel_end - pp.pixel_begin) * pp.samples;
       for (uint32_t b = 1; b < max_depth; ++b) r += counters[b];
-      total_rays[0] += r;
+      atomicAdd(total_rays + 0, r);
     }
     // rays that entered the BVH traversal queue (tcounters follow counters and work cursors)
     const uint32_t* tc = counters + 2 * (max_depth + 2);
     unsigned long long tr = 0;
     for (uint32_t b = 0; b < max_depth; ++b) tr += tc[b];
-    total_rays[1] += tr;
+    atomicAdd(total_rays + 1, tr);
   }
   if (p >= pp.pixel_end) return;
   float4 c = sum_color[p];
   float4 g = sum_gbuf[p];
   for (uint32_t s = 0; s < pp.samples; ++s) {
-    const float4 t = ps.thr[(size_t)s * pp.pixels + p];
-    const float4 gb = ps.gbuf[(size_t)s * pp.pixels + p];
+    const size_t pid = (size_t)s * pp.band_pixels + (p - pp.pixel_begin);
+    const float4 t = ps.thr[pid];
+    const float4 gb = ps.gbuf[pid];
     c.x += t.x;
     c.y += t.y;
     c.z += t.z;

@@ -116,6 +116,15 @@ struct pt_ctx {
   uint32_t samples_per_pass = 1;
   uint32_t row_begin = 0, row_end = 0; // rendered / denoised band (row-band sharding); whole frame by default
 
+  // Second lane of the pass (PT_LANES=2, pixel-stream mode): an internal child context with its
+  // own stream and path-state buffers that renders the lower half of the band into the SAME sums
+  // while this context renders the upper half, so that the sparse tail launches of one half overlap
+  // the other half's work.  Each of the two holds buffers for half the frame's rows (rows_cap).
+  pt_ctx* lane2 = nullptr;
+  bool is_lane = false;
+  uint32_t rows_cap = 0; // rows the path-state buffers are sized for (0 = the whole frame)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+
   pt::PassBuffers pb{};
   void* d_state = nullptr;    // one slab for the six PathState planes
   void* d_counters = nullptr; // counters + work cursors (one memset per pass)

@@ -526,7 +526,7 @@ PT_D bool first_item(const PassParams& pp, uint32_t idx, uint32_t& pid, uint32_t
   x = tx * 8u + (lane & 7u);
   y = (ty + pp.tile_y0) * 4u + (lane >> 3);
   pixel = y * pp.cam.width + x;
-  pid = s * pp.pixels + pixel;
+  pid = s * pp.band_pixels + (pixel - pp.pixel_begin); // relative to the band: a lane's buffers hold its band only
   return x < pp.cam.width && y < pp.cam.height && s < pp.samples;
 }
 PT_D bool first_item(const PassParams& pp, uint32_t idx, uint32_t& pid, uint32_t& pixel, uint32_t& s)
