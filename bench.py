@@ -234,12 +234,16 @@ def bench_render(name, steps, warmup, D: Dist, with_clocks=True):
     tracer.bind_sums(sums.data_ptr())
     first, n_local = D.share(spp)
 
+    radiance = sums[: W * H * 4]   # colour sums + sample count (16 B/pixel); the G-buffer sums follow
+
     def step():
         sums.zero_()
         if n_local:
             tracer.render_range(sd.camera, first, n_local)
         if D.multi:
-            D.dist.reduce(sums, dst=0)
+            # the frame is tonemapped, not denoised: only the radiance plane is reduced (the
+            # G-buffer sums would ride along only for a denoiser, north_star / SURVEY 8e)
+            D.dist.reduce(radiance, dst=0)
 
     out = {}
     with torch.cuda.stream(stream):
@@ -261,6 +265,7 @@ def bench_render(name, steps, warmup, D: Dist, with_clocks=True):
         ms = e0.elapsed_time(e1)
         st = tracer.stats()
         rays = int(st.rays)
+        launches_timed = int(st.kernel_launches)
 
         # end to end through the public API: host camera in, host RGBA8 image out
         pinned = torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True).numpy()  # D2H target
@@ -276,6 +281,30 @@ def bench_render(name, steps, warmup, D: Dist, with_clocks=True):
         D.barrier()
         wall_ms = (time.perf_counter() - wall0) * 1e3
         rays_e2e = int(tracer.stats().rays)
+
+        # per-kernel times for the roofline: a one-lane pass, where every launch has the GPU to
+        # itself (in the timed region above two half-passes run concurrently, so the event time of
+        # one launch is not its own cost)
+        alone = pt.PathTracer(max_depth=depth, profile=True, stream=stream.cuda_stream, lanes=1,
+                              samples_per_pass=int(os.environ.get("PT_SPP_PASS", "0")))
+        alone.max_iterations = 1 << 30
+        tracer.close()
+        alone.create_buffers((W, H), scene)
+        k_steps = max(1, min(steps, 2))
+        for i in range(k_steps + 1):
+            if i == 1:
+                torch.cuda.synchronize()
+                alone.reset_stats()
+            if n_local:
+                alone.render_range(sd.camera, first, n_local)
+        torch.cuda.synchronize()
+        st = alone.stats()
+        alone.close()
+        tracer = pt.PathTracer(max_depth=depth, stream=stream.cuda_stream,
+                               samples_per_pass=int(os.environ.get("PT_SPP_PASS", "0")))
+        tracer.max_iterations = 1 << 30
+        tracer.create_buffers((W, H), scene)
+        tracer.bind_sums(sums.data_ptr())
 
         rmse = None
         if D.multi:
@@ -293,7 +322,9 @@ def bench_render(name, steps, warmup, D: Dist, with_clocks=True):
     (ms, wall_ms, _, _), (_, _, rays_all, rays_e2e_all) = D.max_sum([ms, wall_ms, float(rays), float(rays_e2e)])
     rays_all, rays_e2e_all = int(rays_all), int(rays_e2e_all)
     hbm, peak_src = peaks()
+    gpu_launches = launches_timed
     ext_ms = float(st.ms_extend)
+    ms_alone = ext_ms + float(st.ms_raygen_extend0) + float(st.ms_shade) + float(st.ms_accumulate)
     n_ext = max(1, int(st.n_extend_launches) - int(st.passes))
     achieved = (int(st.rays_traversed) * 48) / (ext_ms * 1e-3) * 1e-9 if ext_ms > 0 else None
     out.update(
@@ -302,21 +333,24 @@ def bench_render(name, steps, warmup, D: Dist, with_clocks=True):
         e2e={"value": rays_e2e_all / (wall_ms * 1e-3) * 1e-6, "unit": "Mrays/s",
              "h2d_bytes_per_step": C.sizeof(pt._abi.pt_camera), "d2h_bytes_per_step": W * H * 4,
              "ms_per_step": wall_ms / steps},
-        gpu_launches=int(st.kernel_launches),
+        gpu_launches=gpu_launches,
         roofline={"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                   "frac": (achieved / hbm) if achieved else None,
                   "traffic": ncu_traffic(name) if D.world == 1 else None,
                   "algorithmic_bytes_per_launch": int(st.rays_traversed) * 48 / n_ext,
                   "kernel": "traverse_kernel", "launches": n_ext,
-                  "rays_traversed_per_step": int(st.rays_traversed) // steps,
+                  "rays_traversed_per_step": int(st.rays_traversed) // k_steps,
                   "avg_launch_ms": ext_ms / n_ext,
-                  "extend_share_of_step": ext_ms / ms,
+                  "extend_share_of_step": ext_ms / ms_alone if ms_alone > 0 else None,
+                  "timed": "launches of %d one-lane step(s) after the timed region, events on the launching stream; "
+                           "the timed region itself runs two concurrent half-passes" % k_steps,
                   "wavefront_bytes_per_ray": 164,
                   "wavefront_frac": rays_all / D.world * 164 / (ms * 1e-3) * 1e-9 / hbm,
                   "peak_source": peak_src,
                   "per_rank": "rank 0's launches" if D.multi else None},
-        kernel_ms={"raygen_classify": st.ms_raygen_extend0, "traverse": st.ms_extend,
-                   "shade_classify_compact": st.ms_shade, "accumulate": st.ms_accumulate},
+        kernel_ms={"raygen_classify": st.ms_raygen_extend0 / k_steps, "traverse": st.ms_extend / k_steps,
+                   "shade_classify_compact": st.ms_shade / k_steps, "accumulate": st.ms_accumulate / k_steps,
+                   "note": "per step, one-lane pass (each launch alone on the GPU)"},
         scene={"triangles_world": int(scene.info.n_world_triangles), "bvh_nodes": int(scene.info.n_bvh_nodes),
                "scene_build_ms": round(float(scene.info.build_ms), 2),
                "scene_upload_ms": round(float(scene.info.upload_ms), 2),
@@ -552,8 +586,8 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": head.pop("ms_per_step"),
             "higher_is_better": True, "scaling": "strong" if D.multi else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config_of(args.workload),
-            "parallelism": f"sample ranges: {wl['spp']} spp split over {D.world} GPUs, one NCCL reduce of the sums"
-                           if D.multi else "single",
+            "parallelism": f"sample ranges: {wl['spp']} spp split over {D.world} GPUs, one NCCL reduce of the "
+                           f"radiance sums ({wl['w'] * wl['h'] * 16 / 1e6:.0f} MB) to rank 0" if D.multi else "single",
             **head}
     secondary = []
     if not args.no_secondary and args.workload == "bunny":

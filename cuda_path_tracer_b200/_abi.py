@@ -46,7 +46,7 @@ class pt_camera(C.Structure):
 class pt_params(C.Structure):
     _fields_ = [("max_depth", C.c_int32), ("rng_mode", C.c_int32), ("max_iterations", C.c_int32),
                 ("samples_per_pass", C.c_int32), ("profile", C.c_int32), ("sort_rays", C.c_int32),
-                ("reserved", C.c_int32 * 2)]
+                ("lanes", C.c_int32), ("reserved", C.c_int32 * 1)]
 
 
 class pt_denoise_params(C.Structure):

@@ -164,8 +164,9 @@ assert HIT_DTYPE.itemsize == C.sizeof(_abi.pt_hit)
 
 class PathTracer:
     def __init__(self, max_depth: int = 50, samples_per_pass: int = 0, profile: bool = False,
-                 stream: int | None = None, sort_rays: bool = False):
+                 stream: int | None = None, sort_rays: bool = False, lanes: int = 0):
         self.sort_rays = sort_rays
+        self.lanes = lanes
         self.max_iterations = 1
         self.current_gpu_method = GPUMethod.megakernel
         self.atrous_denoiser = EdgeAvoidingATrousDenoiser()
@@ -191,6 +192,7 @@ class PathTracer:
         p.samples_per_pass = self.samples_per_pass
         p.profile = 1 if self.profile else 0
         p.sort_rays = 1 if self.sort_rays else 0
+        p.lanes = int(self.lanes)
         h = C.c_void_p()
         w, hh = int(resolution[0]), int(resolution[1])
         check(lib.pt_ctx_create(scene._h, w, hh, C.byref(p), C.c_void_p(self._stream or 0), C.byref(h)))

@@ -828,8 +828,10 @@ static int alloc_image_buffers(pt_ctx* c, uint32_t width, uint32_t height)
 
 // PT_LANES=1|2 (read once): 2 = every pixel-stream context renders its band as two half-bands on
 // two streams (internal.h, pt_ctx::lane2).
+// measured (profiles/README.md, round 2): two lanes +3.9 % on the headline frame, +3.0 % at 2.6 M
+// triangles, +1.5 % on the 10 M-triangle terrain
 #ifndef PT_DEFAULT_LANES
-#define PT_DEFAULT_LANES 1
+#define PT_DEFAULT_LANES 2
 #endif
 static int lanes_setting()
 {
@@ -861,6 +863,7 @@ static int pt_ctx_create_core(const pt_scene* scene, uint32_t width, uint32_t he
   else
     pt_params_default(&p);
   if (p.max_depth <= 0 || p.max_depth > 4096) return fail(PT_ERR_INVALID, "max_depth out of range");
+  if (p.lanes < 0 || p.lanes > 2) return fail(PT_ERR_INVALID, "lanes must be 0 (default), 1 or 2");
   if (p.rng_mode != PT_RNG_PIXEL_STREAM && p.rng_mode != PT_RNG_SLOT_RESEED)
     return fail(PT_ERR_INVALID, "unknown rng_mode");
   PT_CUDA(cudaSetDevice(scene->device));
@@ -868,7 +871,8 @@ static int pt_ctx_create_core(const pt_scene* scene, uint32_t width, uint32_t he
   c->scene = scene;
   c->params = p;
   c->is_lane = as_lane;
-  if (!as_lane && lanes_setting() == 2 && p.rng_mode == PT_RNG_PIXEL_STREAM && height >= 16) {
+  const int want_lanes = p.lanes ? p.lanes : lanes_setting();
+  if (!as_lane && want_lanes == 2 && p.rng_mode == PT_RNG_PIXEL_STREAM && height >= 16 && !p.sort_rays) {
     // the second lane first: alloc_image_buffers below sizes both for half the rows
     pt_ctx* lane = nullptr;
     const int lrc = pt_ctx_create_core(scene, width, height, &p, nullptr, true, &lane);
@@ -881,7 +885,7 @@ static int pt_ctx_create_core(const pt_scene* scene, uint32_t width, uint32_t he
   cudaDeviceProp prop;
   cudaError_t e = cudaGetDeviceProperties(&prop, scene->device);
   if (e != cudaSuccess) {
-    delete c;
+    pt_ctx_destroy(c); // (also the lane)
     return cuda_fail(e, "cudaGetDeviceProperties");
   }
   c->sms = prop.multiProcessorCount;
@@ -891,7 +895,7 @@ static int pt_ctx_create_core(const pt_scene* scene, uint32_t width, uint32_t he
   } else {
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
-      delete c;
+      pt_ctx_destroy(c);
       return cuda_fail(e, "cudaStreamCreate");
     }
     c->own_stream = true;

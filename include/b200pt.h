@@ -135,7 +135,10 @@ typedef struct pt_params {
   int32_t sort_rays;      /* 1 = bin the traversed rays by what they hit (miss / material type)
                              before shading: the reference's commented-out sort by material_id
                              (path_tracer.cu:439-446).  Off by default: measured slower. */
-  int32_t reserved[2];
+  int32_t lanes;          /* 0 = default (2; PT_LANES overrides), 1 = one pass at a time, 2 = the band's
+                             two halves as two concurrent half-passes on two streams (the sparse tail
+                             launches of one half overlap the other half's work; same frame) */
+  int32_t reserved[1];
 } pt_params;
 
 /* EdgeAvoidingATrousDenoiser fields (denoising/edge_avoiding_a_trous_denoiser.hpp:9-12). */

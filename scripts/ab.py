@@ -19,7 +19,7 @@ for setting in args:
     try:
         j = json.loads(r.stdout.strip().splitlines()[-1])
         k = j["kernel_ms"]
-        print(f"{wl:10s} {setting:40s} {j['value']:9.1f} Mrays/s  step {j['ms_per_step']:8.2f} ms  traverse {k['traverse']/j['steps']:8.2f}  "
-              f"chain0 {k['raygen_classify']/j['steps']:6.2f}  chain {k['shade_classify_compact']/j['steps']:6.2f}  img {j.get('image_mean'):.4f}", flush=True)
+        print(f"{wl:10s} {setting:40s} {j['value']:9.1f} Mrays/s  step {j['ms_per_step']:8.2f} ms  traverse {k['traverse']:8.2f}  "
+              f"chain0 {k['raygen_classify']:6.2f}  chain {k['shade_classify_compact']:6.2f}  img {j.get('image_mean'):.4f}", flush=True)
     except Exception as e:
         print(wl, setting, "FAILED", r.stdout[-300:], r.stderr[-600:], flush=True)

@@ -81,14 +81,17 @@ def test_terrain_4k_frame_matches_the_golden_frame():
     box3 = lambda x: x.reshape(H // BOX, BOX, W // BOX, BOX, 3).mean(axis=(1, 3), dtype=np.float64)
     assert np.abs(box3(a) - g["color_box40"]).max() < 2e-4, np.abs(box3(a) - g["color_box40"]).max()
     assert np.abs(box3(n) - g["normal_box40"]).max() < 2e-3, np.abs(box3(n) - g["normal_box40"]).max()
-    # first-hit depth: a missed sample stores the reference's 1e6 sentinel, so one rounding-flipped
-    # silhouette sample moves a box mean by hundreds; compare the boxes that lie wholly on the mesh
+    # first-hit depth: a missed sample stores the reference's 1e6 sentinel, so ONE rounding-flipped
+    # sample (a ray through a shared triangle edge) moves a 40x40 box of 16-spp pixels by
+    # 1e6 / 16 / 1600 = 39 while scene depths are < 5: boxes agree to 2e-3 except for a handful,
+    # and those differ by whole sentinel samples
     dbox = d.reshape(H // BOX, BOX, W // BOX, BOX).mean(axis=(1, 3), dtype=np.float64)
     gd = g["depth_box40"].astype(np.float64)
-    on_mesh = (gd < 100.0) & (dbox < 100.0)
-    assert on_mesh.mean() > 0.3 and ((gd < 100.0) != (dbox < 100.0)).sum() <= 4
-    rel = np.abs(dbox - gd)[on_mesh] / gd[on_mesh]
-    assert rel.max() < 2e-3, rel.max()
+    rel = np.abs(dbox - gd) / np.maximum(gd, 1e-6)
+    off = rel > 2e-3
+    assert np.median(rel) < 1e-5 and off.mean() < 0.01, (np.median(rel), off.mean())
+    flips = (dbox - gd)[off] / (1e6 / SPP / (BOX * BOX))
+    assert np.abs(flips - np.round(flips)).max(initial=0.0) < 0.05, flips
     assert abs(rays - int(g["rays"])) <= 1e-5 * int(g["rays"]), (rays, int(g["rays"]))
 
 
