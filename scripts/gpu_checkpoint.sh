@@ -32,10 +32,11 @@ for s in j.get("secondary", []):
 PY
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/${TAG}_launches.csv \
   python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-secondary > $OUT/${TAG}_ncu_launches.log 2>&1
-timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum -k regex:traverse --clock-control none \
+# (PT_LANES=1 for the two kernel captures: every launch alone on the GPU, as the roofline's event times)
+PT_LANES=1 timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum -k regex:traverse --clock-control none \
   --csv --log-file $OUT/${TAG}_traffic_raw.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-secondary > $OUT/${TAG}_ncu_traffic.log 2>&1
 python scripts/traffic_json.py $OUT/${TAG}_traffic_raw.csv bunny $OUT/${TAG}_traverse_traffic
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:traverse_kernel -s 16 -c 4 \
+PT_LANES=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:traverse_kernel -s 8 -c 3 \
   -o $OUT/${TAG}_traverse -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-secondary > $OUT/${TAG}_ncu_full.log 2>&1
 if [ -f $OUT/${TAG}_traverse.ncu-rep ]; then
   ncu -i $OUT/${TAG}_traverse.ncu-rep --page raw --csv > $OUT/${TAG}_traverse_raw.csv 2>/dev/null

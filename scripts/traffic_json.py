@@ -24,7 +24,7 @@ with open(prefix + ".csv", "w") as f:
         f.write(f"{k},{p['dram__bytes_read.sum']:.0f},{p['dram__bytes_write.sum']:.0f},{p['gpu__time_duration.sum']:.0f}\n")
 total = sum(per[i]["dram__bytes_read.sum"] + per[i]["dram__bytes_write.sum"] for i in ids)
 json.dump({"workload": workload, "kernel": "traverse_kernel",
-           "command": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum -k regex:traverse "
+           "command": "PT_LANES=1 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum -k regex:traverse "
                       "--clock-control none python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-secondary",
            "launches": len(ids), "dram_bytes_total": total, "dram_bytes_per_launch": total / max(1, len(ids)),
            "ncu_time_ns_total": sum(per[i]["gpu__time_duration.sum"] for i in ids), "source": prefix + ".csv"},
