@@ -262,6 +262,48 @@ denoise_prepare_kernel(const DevCamera cam, const float4* __restrict__ sum_color
 // Taps clamped to u == W or v == H (clamp_fix = 0): u == W aliases pixel (0, v+1) while its
 // position is still rebuilt from the ray through (W+0.5, v+0.5); reads past the end of the buffer
 // (undefined in the reference) use the last row / last pixel.
+// sm_100 packed FP32 (FFMA2 / FADD2 / FMUL2): two independent lanes per instruction.  The filter is
+// bound by instruction issue (ncu: 69 % issue-active, FMA pipe 54 %), so the arithmetic of two
+// outputs that share a tap is issued as one packed stream.
+typedef unsigned long long f2x;
+PT_D f2x pk2(float a, float b)
+{
+  f2x r;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+PT_D void upk2(f2x v, float& a, float& b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+PT_D f2x sub2(f2x a, f2x b)
+{
+  f2x r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+PT_D f2x add2(f2x a, f2x b)
+{
+  f2x r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+PT_D f2x mul2(f2x a, f2x b)
+{
+  f2x r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+PT_D f2x fma2(f2x a, f2x b, f2x c)
+{
+  f2x r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+PT_D float kernel_weight(int dx, int dy)
+{
+  const int adx = dx < 0 ? -dx : dx, ady = dy < 0 ? -dy : dy;
+  const int m = adx < ady ? adx : ady;
+  return m == 0 ? 3.f / 8.f : (m == 1 ? 1.f / 4.f : 1.f / 16.f);
+}
+
 struct Tap9 {
   f3 c, n, p;
 };
@@ -282,6 +324,9 @@ __device__ __noinline__ Tap9 edge_tap(const DevCamera& cam, const float4* __rest
 
 // ATR_R (outputs per thread, `step` rows apart) is a template parameter: 2 for the edge strips,
 // PT_ATR_R (default below) for the interior.
+#ifndef ATR_PACK_DEFAULT
+#define ATR_PACK_DEFAULT 0
+#endif
 #ifndef ATR_R_DEFAULT
 #define ATR_R_DEFAULT 3 // measured (1080p, 5 iterations): 0.539 / 0.505 / 0.504 ms at 2 / 3 / 4
 #endif
@@ -301,7 +346,7 @@ struct AtrousRegions {
   AtrousRegion r[3];
 };
 
-template <bool EDGE, int ATR_R>
+template <bool EDGE, int ATR_R, bool PACK>
 PT_D void atrous_body(const DevCamera& cam, const DenoiseParams& dp, const float4* __restrict__ color_in,
                       const float4* __restrict__ normal_depth, const float4* __restrict__ position,
                       float4* __restrict__ color_out, int step, const AtrousRegion& rg, int cta)
@@ -360,19 +405,67 @@ PT_D void atrous_body(const DevCamera& cam, const DenoiseParams& dp, const float
         const Tap9 t = edge_tap(cam, color_in, normal_depth, u, v, W, H);
         ct = t.c, nt = t.n, pt3 = t.p;
       }
+      if (PACK) {
+        // outputs in aligned pairs (r, r+1): where this tap row serves both, one packed stream
+        const f2x tcx = pk2(ct.x, ct.x), tcy = pk2(ct.y, ct.y), tcz = pk2(ct.z, ct.z);
+        const f2x tnx = pk2(nt.x, nt.x), tny = pk2(nt.y, nt.y), tnz = pk2(nt.z, nt.z);
+        const f2x tpx = pk2(pt3.x, pt3.x), tpy = pk2(pt3.y, pt3.y), tpz = pk2(pt3.z, pt3.z);
 #pragma unroll
-      for (int r = 0; r < ATR_R; ++r) {
-        const int dy = j - r;
-        if (dy < -2 || dy > 2) continue; // compile-time after unrolling
-        const int adx = dx < 0 ? -dx : dx, ady = dy < 0 ? -dy : dy;
-        const float kw = (adx < ady ? adx : ady) == 0 ? 3.f / 8.f : ((adx < ady ? adx : ady) == 1 ? 1.f / 4.f : 1.f / 16.f);
-        const f3 dc = cv[r] - ct, dn = nv[r] - nt, dq = pv[r] - pt3;
-        const float e = dot3(dc, dc) * kc + dot3(dn, dn) * kn + dot3(dq, dq) * kp;
-        float ex;
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-e)); // 2 ulp; no range fix-up code
-        const float w = ex * kw;
-        sum[r] = sum[r] + ct * w;
-        cum[r] += w;
+        for (int r = 0; r < ATR_R; r += 2) {
+          const int dy0 = j - r, dy1 = j - (r + 1);
+          const bool v0 = dy0 >= -2 && dy0 <= 2;                    // compile-time after unrolling
+          const bool v1 = r + 1 < ATR_R && dy1 >= -2 && dy1 <= 2;
+          if (v0 && v1) {
+            const f2x dcx = sub2(pk2(cv[r].x, cv[r + 1].x), tcx), dcy = sub2(pk2(cv[r].y, cv[r + 1].y), tcy),
+                      dcz = sub2(pk2(cv[r].z, cv[r + 1].z), tcz);
+            const f2x dnx = sub2(pk2(nv[r].x, nv[r + 1].x), tnx), dny = sub2(pk2(nv[r].y, nv[r + 1].y), tny),
+                      dnz = sub2(pk2(nv[r].z, nv[r + 1].z), tnz);
+            const f2x dpx = sub2(pk2(pv[r].x, pv[r + 1].x), tpx), dpy = sub2(pk2(pv[r].y, pv[r + 1].y), tpy),
+                      dpz = sub2(pk2(pv[r].z, pv[r + 1].z), tpz);
+            const f2x cc = fma2(dcz, dcz, fma2(dcy, dcy, mul2(dcx, dcx)));
+            const f2x nn = fma2(dnz, dnz, fma2(dny, dny, mul2(dnx, dnx)));
+            const f2x pp2 = fma2(dpz, dpz, fma2(dpy, dpy, mul2(dpx, dpx)));
+            const f2x e2 = fma2(pp2, pk2(kp, kp), fma2(nn, pk2(kn, kn), mul2(cc, pk2(kc, kc))));
+            float e0, e1, x0, x1;
+            upk2(e2, e0, e1);
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(x0) : "f"(-e0));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(x1) : "f"(-e1));
+            const f2x w2 = mul2(pk2(x0, x1), pk2(kernel_weight(dx, dy0), kernel_weight(dx, dy1)));
+            f2x sx = pk2(sum[r].x, sum[r + 1].x), sy = pk2(sum[r].y, sum[r + 1].y), sz = pk2(sum[r].z, sum[r + 1].z);
+            sx = fma2(tcx, w2, sx);
+            sy = fma2(tcy, w2, sy);
+            sz = fma2(tcz, w2, sz);
+            const f2x cm = add2(pk2(cum[r], cum[r + 1]), w2);
+            upk2(sx, sum[r].x, sum[r + 1].x);
+            upk2(sy, sum[r].y, sum[r + 1].y);
+            upk2(sz, sum[r].z, sum[r + 1].z);
+            upk2(cm, cum[r], cum[r + 1]);
+          } else if (v0 || v1) {
+            const int rr = v0 ? r : r + 1, dy = v0 ? dy0 : dy1;
+            const float kw = kernel_weight(dx, dy);
+            const f3 dc = cv[rr] - ct, dn = nv[rr] - nt, dq = pv[rr] - pt3;
+            const float e = dot3(dc, dc) * kc + dot3(dn, dn) * kn + dot3(dq, dq) * kp;
+            float ex;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-e));
+            const float w = ex * kw;
+            sum[rr] = sum[rr] + ct * w;
+            cum[rr] += w;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < ATR_R; ++r) {
+          const int dy = j - r;
+          if (dy < -2 || dy > 2) continue; // compile-time after unrolling
+          const float kw = kernel_weight(dx, dy);
+          const f3 dc = cv[r] - ct, dn = nv[r] - nt, dq = pv[r] - pt3;
+          const float e = dot3(dc, dc) * kc + dot3(dn, dn) * kn + dot3(dq, dq) * kp;
+          float ex;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-e)); // 2 ulp; no range fix-up code
+          const float w = ex * kw;
+          sum[r] = sum[r] + ct * w;
+          cum[r] += w;
+        }
       }
     }
   }
@@ -384,7 +477,7 @@ PT_D void atrous_body(const DevCamera& cam, const DenoiseParams& dp, const float
   }
 }
 
-template <int R_INTERIOR>
+template <int R_INTERIOR, bool PACK>
 __global__ void __launch_bounds__(128)
 atrous_kernel(const DevCamera cam, const DenoiseParams dp, const float4* __restrict__ color_in,
               const float4* __restrict__ normal_depth, const float4* __restrict__ position,
@@ -392,16 +485,16 @@ atrous_kernel(const DevCamera cam, const DenoiseParams dp, const float4* __restr
 {
   int cta = (int)blockIdx.x;
   if (cta < regions.r[0].n_ctas) {
-    atrous_body<false, R_INTERIOR>(cam, dp, color_in, normal_depth, position, color_out, step, regions.r[0], cta);
+    atrous_body<false, R_INTERIOR, PACK>(cam, dp, color_in, normal_depth, position, color_out, step, regions.r[0], cta);
     return;
   }
   cta -= regions.r[0].n_ctas;
   if (cta < regions.r[1].n_ctas) {
-    atrous_body<true, 2>(cam, dp, color_in, normal_depth, position, color_out, step, regions.r[1], cta);
+    atrous_body<true, 2, false>(cam, dp, color_in, normal_depth, position, color_out, step, regions.r[1], cta);
     return;
   }
   cta -= regions.r[1].n_ctas;
-  atrous_body<true, 2>(cam, dp, color_in, normal_depth, position, color_out, step, regions.r[2], cta);
+  atrous_body<true, 2, false>(cam, dp, color_in, normal_depth, position, color_out, step, regions.r[2], cta);
 }
 
 // ================================================================ launchers
@@ -496,14 +589,19 @@ void launch_atrous(const LaunchEnv& env, const DevCamera& cam, const DenoisePara
   rs.r[2] = region(true, std::max(r0, yin), r1, 0, xin);   // bottom strip
   const int total = rs.r[0].n_ctas + rs.r[1].n_ctas + rs.r[2].n_ctas;
   if (total == 0) return;
-#define PT_ATROUS(RR)                                                                              \
-  atrous_kernel<RR><<<total, 128, 0, env.stream>>>(cam, dp, color_in, normal_depth, position, color_out, step, rs)
-  if (interior_r == 4)
-    PT_ATROUS(4);
-  else if (interior_r == 3)
-    PT_ATROUS(3);
-  else
-    PT_ATROUS(2);
+  static const bool pack = [] {
+    const char* v = getenv("PT_ATR_PACK");
+    return v ? atoi(v) != 0 : ATR_PACK_DEFAULT != 0;
+  }();
+#define PT_ATROUS(RR, P)                                                                           \
+  atrous_kernel<RR, P><<<total, 128, 0, env.stream>>>(cam, dp, color_in, normal_depth, position, color_out, step, rs)
+  if (interior_r == 4) {
+    if (pack) PT_ATROUS(4, true); else PT_ATROUS(4, false);
+  } else if (interior_r == 3) {
+    if (pack) PT_ATROUS(3, true); else PT_ATROUS(3, false);
+  } else {
+    if (pack) PT_ATROUS(2, true); else PT_ATROUS(2, false);
+  }
 #undef PT_ATROUS
 }
 

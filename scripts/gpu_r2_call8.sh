@@ -28,3 +28,7 @@ for n in (1, 2, 4, 8):
           "| terrain", round(t[0]["value"], 1) if t else None, "eff", round(t[0]["value"] / (n * base[1]), 3) if t and base[1] else None,
           "rmse", t[0].get("image_rmse_vs_single") if t else None, "| build ms", j["scene"]["scene_build_ms"], "kernel_ms", {k: round(v, 2) for k, v in j["kernel_ms"].items()})
 PY
+# DRAM traffic of every one-lane traverse launch (for roofline.traffic)
+PT_LANES=1 timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum -k regex:traverse --clock-control none \
+  --csv --log-file $OUT/r2c8_traffic_raw.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-secondary > $OUT/r2c8_ncu_traffic.log 2>&1
+python scripts/traffic_json.py $OUT/r2c8_traffic_raw.csv bunny $OUT/r2_traverse_traffic
