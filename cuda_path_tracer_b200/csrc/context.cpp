@@ -1162,8 +1162,18 @@ static int render_pass(pt_ctx* c, const pt_camera& cam, uint32_t first_iteration
     launch_chain(env, c->scene->dev, c->pb, pp, 0, n0, max_depth);
     prof_end(c);
     launched += 1;
+    const uint32_t finish_after = (uint32_t)tunable_finish_after((uint64_t)samples * pp.band_pixels);
     if (c->scene->dev.n_tris != 0) {
       for (uint32_t it = 0; it < max_depth; ++it) {
+        if (finish_after != 0 && it == finish_after && !c->pb.bin_list) {
+          // a small pass: the paths still parked are finished in one launch (finish_kernel)
+          prof_begin(c, TAG_EXT);
+          launch_finish(env, c->scene->dev, c->pb, it, max_depth);
+          prof_end(c);
+          launched += 1;
+          c->stats.max_bounce_reached = std::max(c->stats.max_bounce_reached, max_depth);
+          break;
+        }
         PT_CUDA(cudaMemcpyAsync(&c->h_counts[it], c->pb.tcounters + it, sizeof(uint32_t),
                                 cudaMemcpyDeviceToHost, c->stream));
         PT_CUDA(cudaEventRecord(c->bounce_events[it], c->stream));

@@ -29,6 +29,10 @@ struct PassBuffers {
 // experiment switches read once from the environment (wavefront.cu)
 int tunable_order();        // PT_ORDER: bounce-0 item order, see PassParams::order
 int tunable_stream_state(); // PT_STREAM_STATE
+// PT_FINISH: wavefront bounces after which a pass of `paths_in_pass` paths hands the paths still
+// parked to finish_kernel (0 = never: the pass is big, or the switch is off)
+int tunable_finish_after(uint64_t paths_in_pass);
+void launch_finish(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb, uint32_t iter, uint32_t max_depth);
 
 // bounce 0: raygen + classification of the primary rays (fills the traverse queue).
 void launch_raygen(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb,

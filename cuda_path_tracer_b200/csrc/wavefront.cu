@@ -625,6 +625,9 @@ PT_D void stage_prefix(void* smem_dst, const void* gsrc, uint32_t bytes, unsigne
 #endif
 #define EXT_REFILL 16
 #define EXT_INNER_MIN 8
+#ifndef PT_DEFAULT_FINISH
+#define PT_DEFAULT_FINISH 3 // measured: 1-spp 1080p frame 1.457 -> 1.262 ms (profiles/README.md)
+#endif
 #ifndef PT_DEFAULT_ORDER
 #define PT_DEFAULT_ORDER 2 // measured: bunny +0.5 %, bunny_1m +1.5 %, terrain +5.5 % over order 0
 #endif
@@ -1421,6 +1424,78 @@ chain_kernel(const DevScene sc, const PathState ps, const PassParams pp, const P
   if (lane == 0 && rays_local != 0u) atomicAdd(total_rays, (unsigned long long)rays_local);
 }
 
+// =================================================================== finish
+// The late bounces of a SMALL pass in one launch.  A pass is a chain of dependent launches
+// (traverse, chain per bounce); the late ones hold a few thousand rays and still cost ~50 us of
+// traversal + ~12 us of shading each, because one ray's dependent walk sets the floor (frame launch
+// list, profiles/README.md).  After `PT_FINISH` wavefront bounces, the paths still parked are
+// finished here: one lane per path, traversal inlined where the wavefront would park — the
+// chain loop of chain_kernel with trav_inner/trav_leaf in place of the hand-over.  Divergent, but
+// over few paths; results are bit-identical (every path carries its own RNG stream and the same
+// arithmetic runs in the same order per path).
+template <bool L256, bool ST>
+__global__ void __launch_bounds__(EXT_THREADS)
+finish_kernel(const DevScene sc, const PathState ps, const ParkBuf in, const uint32_t* __restrict__ n_ptr,
+              uint32_t max_depth, unsigned long long* __restrict__ total_rays)
+{
+  const uint32_t n = *n_ptr;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  uint32_t rays_local = 0, extra_traversed = 0;
+  int stack[PT_STACK];
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += stride) {
+    const float4 ro = in.ray[2 * (size_t)idx], rd = in.ray[2 * (size_t)idx + 1];
+    const float4 th = in.thr[idx];
+    const uint4 ax = in.aux[idx];
+    const uint32_t pid = in.pid[idx];
+    f3 o = xyz(ro), d = xyz(rd), color = xyz(th);
+    float tmin = ro.w, tbest = __uint_as_float(ax.x);
+    uint32_t rng = __float_as_uint(th.w), code = ax.y, depth = ax.w;
+    int start = (int)ax.z;
+    bool need_traversal = true, have_hit = false, first = true;
+    Hit h;
+    for (;;) {
+      if (need_traversal) {
+        Trav T;
+        trav_init(T, o, d, tmin, tbest, start, stack);
+        while (T.node != PT_SENTINEL) {
+          if (T.node >= 0)
+            trav_inner<L256>(sc, T, stack);
+          else
+            trav_leaf(sc, T, stack);
+        }
+        if (T.best >= 0) { // what traverse_kernel writes back into aux
+          tbest = T.tbest;
+          code = AUX_TRI | (uint32_t)T.best;
+        }
+        if (!first) ++extra_traversed; // (the first one is counted by the parked list's length)
+        first = false;
+        need_traversal = false;
+        have_hit = false;
+      }
+      ++rays_local;
+      const bool hit = have_hit ? code != 0u : resolve_hit<ST>(sc, o, d, tmin, tbest, code, h);
+      if (depth == 0u) ps.gbuf[pid] = hit ? make_float4(h.n.x, h.n.y, h.n.z, h.t) : make_float4(-d.x, -d.y, -d.z, 1e6f);
+      if (!hit) {
+        color = color * sky_color(d);
+        break;
+      }
+      const DevMaterial mat = sc.materials[h.material];
+      scatter(mat, h, o, d, tmin, color, rng);
+      if (++depth == max_depth) break;
+      need_traversal = classify<ST>(sc, o, d, tmin, FLT_MAX, tbest, code, start, h);
+      have_hit = true;
+    }
+    ps.thr[pid] = mk4(color, __uint_as_float(rng));
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    rays_local += __shfl_down_sync(0xffffffffu, rays_local, off);
+    extra_traversed += __shfl_down_sync(0xffffffffu, extra_traversed, off);
+  }
+  if (lane == 0 && rays_local != 0u) atomicAdd(total_rays, (unsigned long long)rays_local);
+  if (lane == 0 && extra_traversed != 0u) atomicAdd(total_rays + 1, (unsigned long long)extra_traversed);
+}
+
 // ================================================================ launchers
 static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
@@ -1430,6 +1505,8 @@ struct Tunables {
   int trav_minb, trav_l256; // traverse_kernel instantiation (PT_TRAV="minb,l256")
   int order;                // bounce-0 item order (PT_ORDER)
   int chain_tma;            // TMA-staged parked state in the re-entry chain launches (PT_CHAIN_TMA)
+  int finish_after;         // small passes: wavefront bounces before finish_kernel (PT_FINISH, 0 = never)
+  int finish_max_paths;     // "small" = at most this many paths in the pass (PT_FINISH_MAX)
 };
 static int env_int(const char* name, int dflt)
 {
@@ -1452,11 +1529,35 @@ static const Tunables& tunables()
     if (const char* v = getenv("PT_TRAV")) sscanf(v, "%d,%d", &t.trav_minb, &t.trav_l256);
     t.order = env_int("PT_ORDER", PT_DEFAULT_ORDER);
     t.chain_tma = env_int("PT_CHAIN_TMA", 0);
+    t.finish_after = env_int("PT_FINISH", PT_DEFAULT_FINISH);
+    t.finish_max_paths = env_int("PT_FINISH_MAX", 6 << 20);
     return t;
   }();
   return t;
 }
 int tunable_order() { return tunables().order; }
+int tunable_finish_after(uint64_t paths_in_pass)
+{
+  const Tunables& t = tunables();
+  return t.finish_after > 0 && paths_in_pass <= (uint64_t)t.finish_max_paths ? t.finish_after : 0;
+}
+
+void launch_finish(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb, uint32_t iter, uint32_t max_depth)
+{
+  // consumes the list chain iteration `iter` parked (not yet traversed)
+  const bool sphere_trees = sc.sph_root_before >= 0 || sc.sph_root_after >= 0;
+  const bool l256 = (size_t)sc.n_nodes * 64 <= (2ull << 20);
+  const uint32_t grid = (uint32_t)env.sms * 4u;
+#define PT_FIN(L, S)                                                                               \
+  finish_kernel<L, S><<<grid, EXT_THREADS, 0, env.stream>>>(sc, pb.ps, pb.park[iter & 1], pb.tcounters + iter, \
+                                                             max_depth, pb.total_rays)
+  if (sphere_trees) {
+    if (l256) PT_FIN(true, true); else PT_FIN(false, true);
+  } else {
+    if (l256) PT_FIN(true, false); else PT_FIN(false, false);
+  }
+#undef PT_FIN
+}
 int tunable_stream_state() { return tunables().stream_state; }
 
 void launch_raygen(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb,
