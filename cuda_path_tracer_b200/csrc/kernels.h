@@ -20,6 +20,7 @@ struct PassBuffers {
   uint32_t* work;      // [0 .. max_depth]   persistent-kernel work-fetch cursors
   uint32_t* bin_list;  // PT_BINS x capacity slots (sort_rays only, else null)
   uint32_t* bin_counts; // [0 .. max_depth] x PT_BINS
+  uint32_t* stop;       // 0, or the stamp of the finish_kernel attempt that took the pass over
   uint8_t* flags;      // stable-compaction alive flags (PT_RNG_SLOT_RESEED only)
   uint32_t* block_sums; // stable-compaction block counts / offsets
   unsigned long long* total_rays; // device-side ray counter
@@ -29,9 +30,9 @@ struct PassBuffers {
 // experiment switches read once from the environment (wavefront.cu)
 int tunable_order();        // PT_ORDER: bounce-0 item order, see PassParams::order
 int tunable_stream_state(); // PT_STREAM_STATE
-// PT_FINISH: wavefront bounces after which a pass of `paths_in_pass` paths hands the paths still
-// parked to finish_kernel (0 = never: the pass is big, or the switch is off)
-int tunable_finish_after(uint64_t paths_in_pass);
+// PT_FINISH: first wavefront bounce before which finish_kernel is offered the parked list (it takes
+// it over, on the device, once at most PT_FINISH_RAYS rays are left); 0 = never
+int tunable_finish_after();
 void launch_finish(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb, uint32_t iter, uint32_t max_depth);
 
 // bounce 0: raygen + classification of the primary rays (fills the traverse queue).

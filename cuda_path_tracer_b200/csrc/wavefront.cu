@@ -626,7 +626,10 @@ PT_D void stage_prefix(void* smem_dst, const void* gsrc, uint32_t bytes, unsigne
 #define EXT_REFILL 16
 #define EXT_INNER_MIN 8
 #ifndef PT_DEFAULT_FINISH
-#define PT_DEFAULT_FINISH 3 // measured: 1-spp 1080p frame 1.457 -> 1.262 ms (profiles/README.md)
+#define PT_DEFAULT_FINISH 2
+#endif
+#ifndef PT_DEFAULT_FINISH_RAYS
+#define PT_DEFAULT_FINISH_RAYS 131072
 #endif
 #ifndef PT_DEFAULT_ORDER
 #define PT_DEFAULT_ORDER 2 // measured: bunny +0.5 %, bunny_1m +1.5 %, terrain +5.5 % over order 0
@@ -647,8 +650,10 @@ __global__ void __launch_bounds__(EXT_THREADS, MINB)
 traverse_kernel(const DevScene sc, const PathState ps, const uint32_t* __restrict__ tq,
                 const uint32_t* __restrict__ n_ptr, uint32_t n_host, uint32_t* __restrict__ work,
                 const float4* __restrict__ batch_rays, HitRecord* __restrict__ batch_out,
-                int refill_min, int inner_min, int stream_state, const BinLists bins)
+                int refill_min, int inner_min, int stream_state, const BinLists bins,
+                const uint32_t* __restrict__ stop)
 {
+  if (SRC == SRC_QUEUE && stop != nullptr && *stop != 0u) return; // finish_kernel took the pass over
   const uint32_t n = SRC == SRC_QUEUE ? *n_ptr : n_host;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t lt_mask = (1u << lane) - 1u;
@@ -1250,8 +1255,9 @@ __global__ void __launch_bounds__(FULL_THREADS)
 chain_kernel(const DevScene sc, const PathState ps, const PassParams pp, const ParkBuf in,
              const uint32_t* __restrict__ n_ptr, uint32_t n_first, const ParkBuf out,
              uint32_t* __restrict__ out_count, uint32_t max_depth,
-             unsigned long long* __restrict__ total_rays, const BinLists bins)
+             unsigned long long* __restrict__ total_rays, const BinLists bins, const uint32_t* __restrict__ stop)
 {
+  if (!FIRST && stop != nullptr && *stop != 0u) return; // finish_kernel took the pass over
   const uint32_t n = FIRST ? n_first : *n_ptr;
   // ray binning: the items are the bins' lists back to back (their counts sum to n)
   uint32_t bin_end[PT_BINS] = {0u, 0u, 0u, 0u};
@@ -1433,12 +1439,22 @@ chain_kernel(const DevScene sc, const PathState ps, const PassParams pp, const P
 // chain loop of chain_kernel with trav_inner/trav_leaf in place of the hand-over.  Divergent, but
 // over few paths; results are bit-identical (every path carries its own RNG stream and the same
 // arithmetic runs in the same order per path).
+//
+// The decision is taken on the device, per attempt: an attempt before wavefront bounce `iter` takes
+// the parked list over only if it holds at most `max_rays` rays (one lane per ray is a good trade
+// for thousands of rays, a bad one for millions: measured -32 % on the terrain when forced), and
+// then stamps `stop` with iter + 1; every later traverse / chain launch and every later attempt of
+// the pass sees a foreign stamp and returns at once.
 template <bool L256, bool ST>
 __global__ void __launch_bounds__(EXT_THREADS)
 finish_kernel(const DevScene sc, const PathState ps, const ParkBuf in, const uint32_t* __restrict__ n_ptr,
-              uint32_t max_depth, unsigned long long* __restrict__ total_rays)
+              uint32_t max_depth, unsigned long long* __restrict__ total_rays, uint32_t max_rays,
+              uint32_t* __restrict__ stop, uint32_t stamp)
 {
   const uint32_t n = *n_ptr;
+  const uint32_t seen = *reinterpret_cast<volatile uint32_t*>(stop);
+  if (n == 0u || n > max_rays || (seen != 0u && seen != stamp)) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *stop = stamp; // (CTAs of THIS launch accept their own stamp)
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t stride = gridDim.x * blockDim.x;
   uint32_t rays_local = 0, extra_traversed = 0;
@@ -1505,8 +1521,8 @@ struct Tunables {
   int trav_minb, trav_l256; // traverse_kernel instantiation (PT_TRAV="minb,l256")
   int order;                // bounce-0 item order (PT_ORDER)
   int chain_tma;            // TMA-staged parked state in the re-entry chain launches (PT_CHAIN_TMA)
-  int finish_after;         // small passes: wavefront bounces before finish_kernel (PT_FINISH, 0 = never)
-  int finish_max_paths;     // "small" = at most this many paths in the pass (PT_FINISH_MAX)
+  int finish_after;         // first wavefront bounce before which finish_kernel may take over (PT_FINISH, 0 = never)
+  int finish_max_rays;      // ... if at most this many rays are still parked (PT_FINISH_RAYS)
 };
 static int env_int(const char* name, int dflt)
 {
@@ -1530,27 +1546,24 @@ static const Tunables& tunables()
     t.order = env_int("PT_ORDER", PT_DEFAULT_ORDER);
     t.chain_tma = env_int("PT_CHAIN_TMA", 0);
     t.finish_after = env_int("PT_FINISH", PT_DEFAULT_FINISH);
-    t.finish_max_paths = env_int("PT_FINISH_MAX", 6 << 20);
+    t.finish_max_rays = env_int("PT_FINISH_RAYS", PT_DEFAULT_FINISH_RAYS);
     return t;
   }();
   return t;
 }
 int tunable_order() { return tunables().order; }
-int tunable_finish_after(uint64_t paths_in_pass)
-{
-  const Tunables& t = tunables();
-  return t.finish_after > 0 && paths_in_pass <= (uint64_t)t.finish_max_paths ? t.finish_after : 0;
-}
+int tunable_finish_after() { return tunables().finish_after > 0 && tunables().finish_max_rays > 0 ? tunables().finish_after : 0; }
 
 void launch_finish(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb, uint32_t iter, uint32_t max_depth)
 {
   // consumes the list chain iteration `iter` parked (not yet traversed)
   const bool sphere_trees = sc.sph_root_before >= 0 || sc.sph_root_after >= 0;
   const bool l256 = (size_t)sc.n_nodes * 64 <= (2ull << 20);
-  const uint32_t grid = (uint32_t)env.sms * 4u;
+  const uint32_t max_rays = (uint32_t)tunables().finish_max_rays;
+  const uint32_t grid = min((uint32_t)env.sms * 4u, cdiv(max_rays, (uint32_t)EXT_THREADS));
 #define PT_FIN(L, S)                                                                               \
   finish_kernel<L, S><<<grid, EXT_THREADS, 0, env.stream>>>(sc, pb.ps, pb.park[iter & 1], pb.tcounters + iter, \
-                                                             max_depth, pb.total_rays)
+                                                             max_depth, pb.total_rays, max_rays, pb.stop, iter + 1u)
   if (sphere_trees) {
     if (l256) PT_FIN(true, true); else PT_FIN(false, true);
   } else {
@@ -1613,7 +1626,7 @@ static uint32_t persistent_grid(K kern, const LaunchEnv& env, int threads, size_
 template <int SRC, int MINB, bool L256>
 static void launch_t2v(const LaunchEnv& env, const DevScene& sc, const PathState& ps, const uint32_t* tq,
                        const uint32_t* n_ptr, uint32_t n_host, uint32_t* work, const float4* rays,
-                       HitRecord* out, uint32_t max_grid, const BinLists& bins)
+                       HitRecord* out, uint32_t max_grid, const BinLists& bins, const uint32_t* stop)
 {
   auto kern = traverse_kernel<SRC, MINB, L256, false>;
   static int nb[64] = {0};
@@ -1621,13 +1634,13 @@ static void launch_t2v(const LaunchEnv& env, const DevScene& sc, const PathState
   const Tunables& t = tunables();
   const uint32_t grid = min(persistent_grid(kern, env, EXT_THREADS, 0, nb, sm), max_grid);
   kern<<<grid, EXT_THREADS, 0, env.stream>>>(sc, ps, tq, n_ptr, n_host, work, rays, out, t.refill,
-                                             t.inner_min, t.stream_state, bins);
+                                             t.inner_min, t.stream_state, bins, stop);
 }
 
 template <int SRC>
 static void launch_t2(const LaunchEnv& env, const DevScene& sc, const PathState& ps, const uint32_t* tq,
                       const uint32_t* n_ptr, uint32_t n_host, uint32_t* work, const float4* rays,
-                      HitRecord* out, uint32_t max_grid, const BinLists& bins)
+                      HitRecord* out, uint32_t max_grid, const BinLists& bins, const uint32_t* stop)
 {
   const Tunables& t = tunables();
   if (SRC == SRC_BATCH && (sc.sph_root_before >= 0 || sc.sph_root_after >= 0)) {
@@ -1637,7 +1650,7 @@ static void launch_t2(const LaunchEnv& env, const DevScene& sc, const PathState&
     static size_t sm[64] = {0};
     const uint32_t grid = min(persistent_grid(kern, env, EXT_THREADS, 0, nb, sm), max_grid);
     kern<<<grid, EXT_THREADS, 0, env.stream>>>(sc, ps, tq, n_ptr, n_host, work, rays, out, t.refill, t.inner_min,
-                                               t.stream_state, bins);
+                                               t.stream_state, bins, stop);
     return;
   }
   int minb = t.trav_minb, l256 = t.trav_l256;
@@ -1652,7 +1665,7 @@ static void launch_t2(const LaunchEnv& env, const DevScene& sc, const PathState&
   }
 #define PT_T2_CASE(B, L)                                                                           \
   if (minb == B && l256 == L)                                                                      \
-    return launch_t2v<SRC, B, L != 0>(env, sc, ps, tq, n_ptr, n_host, work, rays, out, max_grid, bins);
+    return launch_t2v<SRC, B, L != 0>(env, sc, ps, tq, n_ptr, n_host, work, rays, out, max_grid, bins, stop);
   PT_T2_CASE(8, 0)
   PT_T2_CASE(8, 1)
   PT_T2_CASE(10, 0)
@@ -1660,7 +1673,7 @@ static void launch_t2(const LaunchEnv& env, const DevScene& sc, const PathState&
   PT_T2_CASE(12, 0)
   PT_T2_CASE(12, 1)
 #undef PT_T2_CASE
-  launch_t2v<SRC, EXT_MIN_BLOCKS, false>(env, sc, ps, tq, n_ptr, n_host, work, rays, out, max_grid, bins);
+  launch_t2v<SRC, EXT_MIN_BLOCKS, false>(env, sc, ps, tq, n_ptr, n_host, work, rays, out, max_grid, bins, stop);
 }
 
 template <int SRC, int THREADS, int BLOCKS>
@@ -1683,11 +1696,12 @@ template <int SRC>
 static void launch_traverse_shape(const LaunchEnv& env, const DevScene& sc, const PathState& ps,
                                   const uint32_t* tq, const uint32_t* n_ptr, uint32_t n_host,
                                   uint32_t* work, const float4* rays, HitRecord* out, bool batch,
-                                  const BinLists& bins = BinLists{nullptr, nullptr, 0u})
+                                  const BinLists& bins = BinLists{nullptr, nullptr, 0u},
+                                  const uint32_t* stop = nullptr)
 {
   if (sc.n_nodes8 == 0u) {
     launch_t2<SRC>(env, sc, ps, tq, n_ptr, n_host, work, rays, out,
-                   batch ? cdiv(n_host, (uint32_t)EXT_THREADS) : 0xffffffffu, bins);
+                   batch ? cdiv(n_host, (uint32_t)EXT_THREADS) : 0xffffffffu, bins, stop);
     return;
   }
   const TShape sh = t8_shape();
@@ -1726,7 +1740,7 @@ void launch_traverse_parked(const LaunchEnv& env, const DevScene& sc, const Pass
   view.ray = pb.park[iter & 1].ray;
   view.aux = pb.park[iter & 1].aux;
   launch_traverse_shape<SRC_QUEUE>(env, sc, view, nullptr, pb.tcounters + iter, 0u, pb.work + iter,
-                                   nullptr, nullptr, false, bins_of(pb, iter));
+                                   nullptr, nullptr, false, bins_of(pb, iter), pb.stop);
 }
 
 void launch_chain(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb,
@@ -1744,11 +1758,11 @@ void launch_chain(const LaunchEnv& env, const DevScene& sc, const PassBuffers& p
     if (sphere_trees)
       chain_kernel<true, 0, true><<<g0, FULL_THREADS, 0, env.stream>>>(sc, pb.ps, pp, ParkBuf{}, nullptr, n_items_first,
                                                                      pb.park[0], pb.tcounters + 0, max_depth,
-                                                                     pb.total_rays, BinLists{nullptr, nullptr, 0u});
+                                                                     pb.total_rays, BinLists{nullptr, nullptr, 0u}, nullptr);
     else
       chain_kernel<true, 0, false><<<g0, FULL_THREADS, 0, env.stream>>>(sc, pb.ps, pp, ParkBuf{}, nullptr, n_items_first,
                                                                       pb.park[0], pb.tcounters + 0, max_depth,
-                                                                      pb.total_rays, BinLists{nullptr, nullptr, 0u});
+                                                                      pb.total_rays, BinLists{nullptr, nullptr, 0u}, nullptr);
   } else {
     // consumes the traversed state of iteration iter-1, parks into the buffer of iteration iter
     const BinLists bins = bins_of(pb, iter - 1);
@@ -1756,20 +1770,20 @@ void launch_chain(const LaunchEnv& env, const DevScene& sc, const PassBuffers& p
     if (sphere_trees) {
       chain_kernel<false, 0, true><<<grid, FULL_THREADS, 0, env.stream>>>(
           sc, pb.ps, pp, pb.park[(iter - 1) & 1], pb.tcounters + (iter - 1), 0u, pb.park[iter & 1],
-          pb.tcounters + iter, max_depth, pb.total_rays, bins);
+          pb.tcounters + iter, max_depth, pb.total_rays, bins, pb.stop);
     } else if (tma == 1) {
       // (34 KB of dynamic shared memory: below the 48 KB that needs no opt-in)
       chain_kernel<false, 1, false><<<grid, FULL_THREADS, 2 * CHAIN_STAGE_BYTES, env.stream>>>(
           sc, pb.ps, pp, pb.park[(iter - 1) & 1], pb.tcounters + (iter - 1), 0u, pb.park[iter & 1],
-          pb.tcounters + iter, max_depth, pb.total_rays, bins);
+          pb.tcounters + iter, max_depth, pb.total_rays, bins, pb.stop);
     } else if (tma == 2) {
       chain_kernel<false, 2, false><<<grid, FULL_THREADS, 2 * CHAIN_STAGE_BYTES, env.stream>>>(
           sc, pb.ps, pp, pb.park[(iter - 1) & 1], pb.tcounters + (iter - 1), 0u, pb.park[iter & 1],
-          pb.tcounters + iter, max_depth, pb.total_rays, bins);
+          pb.tcounters + iter, max_depth, pb.total_rays, bins, pb.stop);
     } else {
       chain_kernel<false, 0, false><<<grid, FULL_THREADS, 0, env.stream>>>(
           sc, pb.ps, pp, pb.park[(iter - 1) & 1], pb.tcounters + (iter - 1), 0u, pb.park[iter & 1],
-          pb.tcounters + iter, max_depth, pb.total_rays, bins);
+          pb.tcounters + iter, max_depth, pb.total_rays, bins, pb.stop);
     }
   }
 }
