@@ -901,8 +901,7 @@ static int pt_ctx_create_core(const pt_scene* scene, uint32_t width, uint32_t he
     c->own_stream = true;
   }
   const size_t n_ctr = (size_t)p.max_depth + 2;
-  // counters, work cursors, traverse counts, per-iteration bin counters (sort_rays), the stop word
-  c->counters_bytes = (n_ctr * (3 + PT_BINS) + 2) * sizeof(uint32_t);
+  c->counters_bytes = n_ctr * (3 + PT_BINS) * sizeof(uint32_t); // + per-iteration bin counters (sort_rays)
   int rc = PT_OK;
   do {
     if ((e = cudaMalloc(&c->d_counters, c->counters_bytes + 24)) != cudaSuccess) break;
@@ -910,7 +909,6 @@ static int pt_ctx_create_core(const pt_scene* scene, uint32_t width, uint32_t he
     c->pb.work = c->pb.counters + n_ctr;
     c->pb.tcounters = c->pb.counters + 2 * n_ctr;
     c->pb.bin_counts = c->pb.counters + 3 * n_ctr;
-    c->pb.stop = c->pb.counters + (3 + PT_BINS) * n_ctr;
     c->pb.total_rays = (unsigned long long*)((char*)c->d_counters + ((c->counters_bytes + 7) & ~7ull));
     if ((e = cudaMemset(c->d_counters, 0, c->counters_bytes + 24)) != cudaSuccess) break;
     if ((e = cudaHostAlloc((void**)&c->h_counts, n_ctr * sizeof(uint32_t), cudaHostAllocDefault)) !=
@@ -1164,22 +1162,46 @@ static int render_pass(pt_ctx* c, const pt_camera& cam, uint32_t first_iteration
     launch_chain(env, c->scene->dev, c->pb, pp, 0, n0, max_depth);
     prof_end(c);
     launched += 1;
-    // (not with ray binning or the opt-in 8-wide tree: their kernels do not watch the stop word)
-    const uint32_t finish_after =
-        c->pb.bin_list || c->scene->dev.n_nodes8 != 0u ? 0u : (uint32_t)tunable_finish_after();
+    // Where to hand the tail of the pass to finish_kernel: the first bounce >= PT_FINISH at which
+    // the last pass whose counts are known had, scaled to this pass's size, at most PT_FINISH_RAYS
+    // rays parked.  No history (first pass, or the previous one still in flight), ray binning or
+    // the opt-in 8-wide tree: the whole pass runs as a wavefront.
+    const uint64_t paths_now = (uint64_t)samples * pp.band_pixels;
+    uint32_t finish_at = max_depth; // = never
+    if (c->pend_event >= 0 && cudaEventQuery(c->bounce_events[c->pend_event]) == cudaSuccess) {
+      c->hist_counts.assign(c->h_counts, c->h_counts + c->pend_known);
+      c->hist_known = c->pend_known;
+      c->hist_paths = c->pend_paths;
+      c->pend_event = -1;
+    }
+    const uint32_t finish_first = (uint32_t)tunable_finish_after();
+    if (finish_first != 0 && !c->pb.bin_list && c->scene->dev.n_nodes8 == 0u && c->hist_paths != 0) {
+      for (uint32_t it = finish_first; it < c->hist_known && it < max_depth; ++it) {
+        const double predicted = (double)c->hist_counts[it] * (double)paths_now / (double)c->hist_paths;
+        if (predicted <= (double)tunable_finish_rays()) {
+          finish_at = it;
+          break;
+        }
+      }
+    }
+    c->pend_known = 0;
+    c->pend_paths = paths_now;
     if (c->scene->dev.n_tris != 0) {
       for (uint32_t it = 0; it < max_depth; ++it) {
-        if (finish_after != 0 && it >= finish_after) {
-          // offer the parked list to finish_kernel: it takes the rest of the pass over, on the
-          // device, once few enough rays are left; the launches below then return at once
+        PT_CUDA(cudaMemcpyAsync(&c->h_counts[it], c->pb.tcounters + it, sizeof(uint32_t),
+                                cudaMemcpyDeviceToHost, c->stream));
+        PT_CUDA(cudaEventRecord(c->bounce_events[it], c->stream));
+        c->pend_known = it + 1;
+        c->pend_event = (int)it;
+        if (it == finish_at) {
+          // few rays left: the paths still parked are finished in one launch (finish_kernel)
           prof_begin(c, TAG_SHADE);
           launch_finish(env, c->scene->dev, c->pb, it, max_depth);
           prof_end(c);
           launched += 1;
+          c->stats.max_bounce_reached = std::max(c->stats.max_bounce_reached, max_depth);
+          break;
         }
-        PT_CUDA(cudaMemcpyAsync(&c->h_counts[it], c->pb.tcounters + it, sizeof(uint32_t),
-                                cudaMemcpyDeviceToHost, c->stream));
-        PT_CUDA(cudaEventRecord(c->bounce_events[it], c->stream));
         if (it >= kLookBehind) {
           // look-behind early exit: stop enqueueing iterations once an older queue is known
           // to have been empty; never blocks the host.

@@ -132,6 +132,16 @@ struct pt_ctx {
   uint32_t* h_counts = nullptr; // pinned look-behind copies of the bounce counters
   std::vector<cudaEvent_t> bounce_events;
 
+  // Parked-list lengths of the last pass whose counts have reached the host (h_counts, copied
+  // asynchronously): the next pass uses them to predict how many rays are left after each bounce
+  // and hands the tail to finish_kernel at the first bounce where few enough remain.
+  std::vector<uint32_t> hist_counts;
+  uint32_t hist_known = 0;
+  uint64_t hist_paths = 0;
+  uint32_t pend_known = 0; // ... of the pass in flight
+  uint64_t pend_paths = 0;
+  int pend_event = -1;     // bounce event after which h_counts[0 .. pend_known) are complete
+
   bool own_sums = true;
   float4* d_sums = nullptr; // [0,pixels) colour sums + count, [pixels,2*pixels) normal+depth sums
   // denoiser planes (allocated on first use)

@@ -20,7 +20,6 @@ struct PassBuffers {
   uint32_t* work;      // [0 .. max_depth]   persistent-kernel work-fetch cursors
   uint32_t* bin_list;  // PT_BINS x capacity slots (sort_rays only, else null)
   uint32_t* bin_counts; // [0 .. max_depth] x PT_BINS
-  uint32_t* stop;       // 0, or the stamp of the finish_kernel attempt that took the pass over
   uint8_t* flags;      // stable-compaction alive flags (PT_RNG_SLOT_RESEED only)
   uint32_t* block_sums; // stable-compaction block counts / offsets
   unsigned long long* total_rays; // device-side ray counter
@@ -30,9 +29,10 @@ struct PassBuffers {
 // experiment switches read once from the environment (wavefront.cu)
 int tunable_order();        // PT_ORDER: bounce-0 item order, see PassParams::order
 int tunable_stream_state(); // PT_STREAM_STATE
-// PT_FINISH: first wavefront bounce before which finish_kernel is offered the parked list (it takes
-// it over, on the device, once at most PT_FINISH_RAYS rays are left); 0 = never
+// PT_FINISH: first wavefront bounce finish_kernel may replace (0 = never); PT_FINISH_RAYS: ... once
+// at most this many rays are predicted to be parked there
 int tunable_finish_after();
+int tunable_finish_rays();
 void launch_finish(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb, uint32_t iter, uint32_t max_depth);
 
 // bounce 0: raygen + classification of the primary rays (fills the traverse queue).

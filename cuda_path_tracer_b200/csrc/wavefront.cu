@@ -629,7 +629,7 @@ PT_D void stage_prefix(void* smem_dst, const void* gsrc, uint32_t bytes, unsigne
 #define PT_DEFAULT_FINISH 2
 #endif
 #ifndef PT_DEFAULT_FINISH_RAYS
-#define PT_DEFAULT_FINISH_RAYS 131072
+#define PT_DEFAULT_FINISH_RAYS 98304
 #endif
 #ifndef PT_DEFAULT_ORDER
 #define PT_DEFAULT_ORDER 2 // measured: bunny +0.5 %, bunny_1m +1.5 %, terrain +5.5 % over order 0
@@ -650,10 +650,8 @@ __global__ void __launch_bounds__(EXT_THREADS, MINB)
 traverse_kernel(const DevScene sc, const PathState ps, const uint32_t* __restrict__ tq,
                 const uint32_t* __restrict__ n_ptr, uint32_t n_host, uint32_t* __restrict__ work,
                 const float4* __restrict__ batch_rays, HitRecord* __restrict__ batch_out,
-                int refill_min, int inner_min, int stream_state, const BinLists bins,
-                const uint32_t* __restrict__ stop)
+                int refill_min, int inner_min, int stream_state, const BinLists bins)
 {
-  if (SRC == SRC_QUEUE && stop != nullptr && *stop != 0u) return; // finish_kernel took the pass over
   const uint32_t n = SRC == SRC_QUEUE ? *n_ptr : n_host;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t lt_mask = (1u << lane) - 1u;
@@ -1255,9 +1253,8 @@ __global__ void __launch_bounds__(FULL_THREADS)
 chain_kernel(const DevScene sc, const PathState ps, const PassParams pp, const ParkBuf in,
              const uint32_t* __restrict__ n_ptr, uint32_t n_first, const ParkBuf out,
              uint32_t* __restrict__ out_count, uint32_t max_depth,
-             unsigned long long* __restrict__ total_rays, const BinLists bins, const uint32_t* __restrict__ stop)
+             unsigned long long* __restrict__ total_rays, const BinLists bins)
 {
-  if (!FIRST && stop != nullptr && *stop != 0u) return; // finish_kernel took the pass over
   const uint32_t n = FIRST ? n_first : *n_ptr;
   // ray binning: the items are the bins' lists back to back (their counts sum to n)
   uint32_t bin_end[PT_BINS] = {0u, 0u, 0u, 0u};
@@ -1431,30 +1428,22 @@ chain_kernel(const DevScene sc, const PathState ps, const PassParams pp, const P
 }
 
 // =================================================================== finish
-// The late bounces of a SMALL pass in one launch.  A pass is a chain of dependent launches
+// The late bounces of a pass in one launch, once few rays are left.  A pass is a chain of dependent launches
 // (traverse, chain per bounce); the late ones hold a few thousand rays and still cost ~50 us of
 // traversal + ~12 us of shading each, because one ray's dependent walk sets the floor (frame launch
-// list, profiles/README.md).  After `PT_FINISH` wavefront bounces, the paths still parked are
-// finished here: one lane per path, traversal inlined where the wavefront would park — the
+// list, profiles/README.md).  From the first bounce at which the previous pass of the context had
+// at most PT_FINISH_RAYS rays parked (scaled to this pass's size; render_pass), the paths still
+// parked are finished here: one lane per path, traversal inlined where the wavefront would park — the
 // chain loop of chain_kernel with trav_inner/trav_leaf in place of the hand-over.  Divergent, but
-// over few paths; results are bit-identical (every path carries its own RNG stream and the same
+// over few paths (forced on millions of rays it costs 32 % on the 10 M-triangle terrain: hence the
+// prediction); results are bit-identical (every path carries its own RNG stream and the same
 // arithmetic runs in the same order per path).
-//
-// The decision is taken on the device, per attempt: an attempt before wavefront bounce `iter` takes
-// the parked list over only if it holds at most `max_rays` rays (one lane per ray is a good trade
-// for thousands of rays, a bad one for millions: measured -32 % on the terrain when forced), and
-// then stamps `stop` with iter + 1; every later traverse / chain launch and every later attempt of
-// the pass sees a foreign stamp and returns at once.
 template <bool L256, bool ST>
 __global__ void __launch_bounds__(EXT_THREADS)
 finish_kernel(const DevScene sc, const PathState ps, const ParkBuf in, const uint32_t* __restrict__ n_ptr,
-              uint32_t max_depth, unsigned long long* __restrict__ total_rays, uint32_t max_rays,
-              uint32_t* __restrict__ stop, uint32_t stamp)
+              uint32_t max_depth, unsigned long long* __restrict__ total_rays)
 {
   const uint32_t n = *n_ptr;
-  const uint32_t seen = *reinterpret_cast<volatile uint32_t*>(stop);
-  if (n == 0u || n > max_rays || (seen != 0u && seen != stamp)) return;
-  if (blockIdx.x == 0 && threadIdx.x == 0) *stop = stamp; // (CTAs of THIS launch accept their own stamp)
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t stride = gridDim.x * blockDim.x;
   uint32_t rays_local = 0, extra_traversed = 0;
@@ -1521,8 +1510,8 @@ struct Tunables {
   int trav_minb, trav_l256; // traverse_kernel instantiation (PT_TRAV="minb,l256")
   int order;                // bounce-0 item order (PT_ORDER)
   int chain_tma;            // TMA-staged parked state in the re-entry chain launches (PT_CHAIN_TMA)
-  int finish_after;         // first wavefront bounce before which finish_kernel may take over (PT_FINISH, 0 = never)
-  int finish_max_rays;      // ... if at most this many rays are still parked (PT_FINISH_RAYS)
+  int finish_after;         // first wavefront bounce finish_kernel may replace (PT_FINISH, 0 = never)
+  int finish_max_rays;      // ... once at most this many rays are predicted to be parked (PT_FINISH_RAYS)
 };
 static int env_int(const char* name, int dflt)
 {
@@ -1552,18 +1541,18 @@ static const Tunables& tunables()
   return t;
 }
 int tunable_order() { return tunables().order; }
-int tunable_finish_after() { return tunables().finish_after > 0 && tunables().finish_max_rays > 0 ? tunables().finish_after : 0; }
+int tunable_finish_after() { return tunables().finish_after; }
+int tunable_finish_rays() { return tunables().finish_max_rays; }
 
 void launch_finish(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb, uint32_t iter, uint32_t max_depth)
 {
   // consumes the list chain iteration `iter` parked (not yet traversed)
   const bool sphere_trees = sc.sph_root_before >= 0 || sc.sph_root_after >= 0;
   const bool l256 = (size_t)sc.n_nodes * 64 <= (2ull << 20);
-  const uint32_t max_rays = (uint32_t)tunables().finish_max_rays;
-  const uint32_t grid = min((uint32_t)env.sms * 4u, cdiv(max_rays, (uint32_t)EXT_THREADS));
+  const uint32_t grid = (uint32_t)env.sms * 4u;
 #define PT_FIN(L, S)                                                                               \
   finish_kernel<L, S><<<grid, EXT_THREADS, 0, env.stream>>>(sc, pb.ps, pb.park[iter & 1], pb.tcounters + iter, \
-                                                             max_depth, pb.total_rays, max_rays, pb.stop, iter + 1u)
+                                                             max_depth, pb.total_rays)
   if (sphere_trees) {
     if (l256) PT_FIN(true, true); else PT_FIN(false, true);
   } else {
@@ -1626,7 +1615,7 @@ static uint32_t persistent_grid(K kern, const LaunchEnv& env, int threads, size_
 template <int SRC, int MINB, bool L256>
 static void launch_t2v(const LaunchEnv& env, const DevScene& sc, const PathState& ps, const uint32_t* tq,
                        const uint32_t* n_ptr, uint32_t n_host, uint32_t* work, const float4* rays,
-                       HitRecord* out, uint32_t max_grid, const BinLists& bins, const uint32_t* stop)
+                       HitRecord* out, uint32_t max_grid, const BinLists& bins)
 {
   auto kern = traverse_kernel<SRC, MINB, L256, false>;
   static int nb[64] = {0};
@@ -1634,13 +1623,13 @@ static void launch_t2v(const LaunchEnv& env, const DevScene& sc, const PathState
   const Tunables& t = tunables();
   const uint32_t grid = min(persistent_grid(kern, env, EXT_THREADS, 0, nb, sm), max_grid);
   kern<<<grid, EXT_THREADS, 0, env.stream>>>(sc, ps, tq, n_ptr, n_host, work, rays, out, t.refill,
-                                             t.inner_min, t.stream_state, bins, stop);
+                                             t.inner_min, t.stream_state, bins);
 }
 
 template <int SRC>
 static void launch_t2(const LaunchEnv& env, const DevScene& sc, const PathState& ps, const uint32_t* tq,
                       const uint32_t* n_ptr, uint32_t n_host, uint32_t* work, const float4* rays,
-                      HitRecord* out, uint32_t max_grid, const BinLists& bins, const uint32_t* stop)
+                      HitRecord* out, uint32_t max_grid, const BinLists& bins)
 {
   const Tunables& t = tunables();
   if (SRC == SRC_BATCH && (sc.sph_root_before >= 0 || sc.sph_root_after >= 0)) {
@@ -1650,7 +1639,7 @@ static void launch_t2(const LaunchEnv& env, const DevScene& sc, const PathState&
     static size_t sm[64] = {0};
     const uint32_t grid = min(persistent_grid(kern, env, EXT_THREADS, 0, nb, sm), max_grid);
     kern<<<grid, EXT_THREADS, 0, env.stream>>>(sc, ps, tq, n_ptr, n_host, work, rays, out, t.refill, t.inner_min,
-                                               t.stream_state, bins, stop);
+                                               t.stream_state, bins);
     return;
   }
   int minb = t.trav_minb, l256 = t.trav_l256;
@@ -1665,7 +1654,7 @@ static void launch_t2(const LaunchEnv& env, const DevScene& sc, const PathState&
   }
 #define PT_T2_CASE(B, L)                                                                           \
   if (minb == B && l256 == L)                                                                      \
-    return launch_t2v<SRC, B, L != 0>(env, sc, ps, tq, n_ptr, n_host, work, rays, out, max_grid, bins, stop);
+    return launch_t2v<SRC, B, L != 0>(env, sc, ps, tq, n_ptr, n_host, work, rays, out, max_grid, bins);
   PT_T2_CASE(8, 0)
   PT_T2_CASE(8, 1)
   PT_T2_CASE(10, 0)
@@ -1673,7 +1662,7 @@ static void launch_t2(const LaunchEnv& env, const DevScene& sc, const PathState&
   PT_T2_CASE(12, 0)
   PT_T2_CASE(12, 1)
 #undef PT_T2_CASE
-  launch_t2v<SRC, EXT_MIN_BLOCKS, false>(env, sc, ps, tq, n_ptr, n_host, work, rays, out, max_grid, bins, stop);
+  launch_t2v<SRC, EXT_MIN_BLOCKS, false>(env, sc, ps, tq, n_ptr, n_host, work, rays, out, max_grid, bins);
 }
 
 template <int SRC, int THREADS, int BLOCKS>
@@ -1696,12 +1685,11 @@ template <int SRC>
 static void launch_traverse_shape(const LaunchEnv& env, const DevScene& sc, const PathState& ps,
                                   const uint32_t* tq, const uint32_t* n_ptr, uint32_t n_host,
                                   uint32_t* work, const float4* rays, HitRecord* out, bool batch,
-                                  const BinLists& bins = BinLists{nullptr, nullptr, 0u},
-                                  const uint32_t* stop = nullptr)
+                                  const BinLists& bins = BinLists{nullptr, nullptr, 0u})
 {
   if (sc.n_nodes8 == 0u) {
     launch_t2<SRC>(env, sc, ps, tq, n_ptr, n_host, work, rays, out,
-                   batch ? cdiv(n_host, (uint32_t)EXT_THREADS) : 0xffffffffu, bins, stop);
+                   batch ? cdiv(n_host, (uint32_t)EXT_THREADS) : 0xffffffffu, bins);
     return;
   }
   const TShape sh = t8_shape();
@@ -1740,7 +1728,7 @@ void launch_traverse_parked(const LaunchEnv& env, const DevScene& sc, const Pass
   view.ray = pb.park[iter & 1].ray;
   view.aux = pb.park[iter & 1].aux;
   launch_traverse_shape<SRC_QUEUE>(env, sc, view, nullptr, pb.tcounters + iter, 0u, pb.work + iter,
-                                   nullptr, nullptr, false, bins_of(pb, iter), pb.stop);
+                                   nullptr, nullptr, false, bins_of(pb, iter));
 }
 
 void launch_chain(const LaunchEnv& env, const DevScene& sc, const PassBuffers& pb,
@@ -1758,11 +1746,11 @@ void launch_chain(const LaunchEnv& env, const DevScene& sc, const PassBuffers& p
     if (sphere_trees)
       chain_kernel<true, 0, true><<<g0, FULL_THREADS, 0, env.stream>>>(sc, pb.ps, pp, ParkBuf{}, nullptr, n_items_first,
                                                                      pb.park[0], pb.tcounters + 0, max_depth,
-                                                                     pb.total_rays, BinLists{nullptr, nullptr, 0u}, nullptr);
+                                                                     pb.total_rays, BinLists{nullptr, nullptr, 0u});
     else
       chain_kernel<true, 0, false><<<g0, FULL_THREADS, 0, env.stream>>>(sc, pb.ps, pp, ParkBuf{}, nullptr, n_items_first,
                                                                       pb.park[0], pb.tcounters + 0, max_depth,
-                                                                      pb.total_rays, BinLists{nullptr, nullptr, 0u}, nullptr);
+                                                                      pb.total_rays, BinLists{nullptr, nullptr, 0u});
   } else {
     // consumes the traversed state of iteration iter-1, parks into the buffer of iteration iter
     const BinLists bins = bins_of(pb, iter - 1);
@@ -1770,20 +1758,20 @@ void launch_chain(const LaunchEnv& env, const DevScene& sc, const PassBuffers& p
     if (sphere_trees) {
       chain_kernel<false, 0, true><<<grid, FULL_THREADS, 0, env.stream>>>(
           sc, pb.ps, pp, pb.park[(iter - 1) & 1], pb.tcounters + (iter - 1), 0u, pb.park[iter & 1],
-          pb.tcounters + iter, max_depth, pb.total_rays, bins, pb.stop);
+          pb.tcounters + iter, max_depth, pb.total_rays, bins);
     } else if (tma == 1) {
       // (34 KB of dynamic shared memory: below the 48 KB that needs no opt-in)
       chain_kernel<false, 1, false><<<grid, FULL_THREADS, 2 * CHAIN_STAGE_BYTES, env.stream>>>(
           sc, pb.ps, pp, pb.park[(iter - 1) & 1], pb.tcounters + (iter - 1), 0u, pb.park[iter & 1],
-          pb.tcounters + iter, max_depth, pb.total_rays, bins, pb.stop);
+          pb.tcounters + iter, max_depth, pb.total_rays, bins);
     } else if (tma == 2) {
       chain_kernel<false, 2, false><<<grid, FULL_THREADS, 2 * CHAIN_STAGE_BYTES, env.stream>>>(
           sc, pb.ps, pp, pb.park[(iter - 1) & 1], pb.tcounters + (iter - 1), 0u, pb.park[iter & 1],
-          pb.tcounters + iter, max_depth, pb.total_rays, bins, pb.stop);
+          pb.tcounters + iter, max_depth, pb.total_rays, bins);
     } else {
       chain_kernel<false, 0, false><<<grid, FULL_THREADS, 0, env.stream>>>(
           sc, pb.ps, pp, pb.park[(iter - 1) & 1], pb.tcounters + (iter - 1), 0u, pb.park[iter & 1],
-          pb.tcounters + iter, max_depth, pb.total_rays, bins, pb.stop);
+          pb.tcounters + iter, max_depth, pb.total_rays, bins);
     }
   }
 }
