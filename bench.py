@@ -472,7 +472,8 @@ def ref_render(sd, wl, spp, steps, warmup):
     rt.close()
     total = sum(times)
     return {"value": rays / (total * 1e-3) * 1e-6, "unit": "Mrays/s", "ms_per_step": total / len(times),
-            "spp_per_step": spp, "steps": steps, "scene_create_s": round(create_s, 3), "best_step_mrays": max(0.0, rays / len(times) / (min(times) * 1e-3) * 1e-6),
+            "spp_per_step": spp, "steps": steps, "scene_create_s": round(create_s, 3),
+            "step_ms": [round(t, 1) for t in times], "best_step_mrays": max(0.0, rays / len(times) / (min(times) * 1e-3) * 1e-6),
             "build": {"library": os.path.basename(lib.path), "traversal_stack": lib.stack_size,
                       "reference_bvh_depth": depth, "flags": "-O3 -DNDEBUG -arch=sm_100 -rdc=true (the reference's)",
                       "patches": REF_PATCHES, "mode": "streaming (CLI default)"}}
@@ -535,6 +536,7 @@ def run_reference(args):
         r = ref_render(sd, wl, wl["spp"], args.steps, args.warmup)
         v = r["value"]
         line.update(value=v, ms_per_step=r["ms_per_step"], spp_per_s=wl["spp"] / (r["ms_per_step"] * 1e-3),
+                    best_step_value=r["best_step_mrays"], step_ms=r["step_ms"],  # it varies 2-3x between runs
                     gpu_launches=None, reference_build=r["build"],
                     cpu_baseline={"value": v, "unit": "Mrays/s", "cores": 1, "kind": "reference",
                                   "sample": "full workload on the reference's own CUDA build (oracle/_ref/%s, "

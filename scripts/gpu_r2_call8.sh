@@ -26,7 +26,7 @@ for n in (1, 2, 4, 8):
     print("N", n, "bunny", round(j["value"], 1), "ms/step", round(j["ms_per_step"], 3), "eff", round(j["value"] / (n * base[0]), 3),
           "e2e", round(j["e2e"]["value"], 1), "rmse", j.get("image_rmse_vs_single"),
           "| terrain", round(t[0]["value"], 1) if t else None, "eff", round(t[0]["value"] / (n * base[1]), 3) if t and base[1] else None,
-          "rmse", t[0].get("image_rmse_vs_single") if t else None, "| build ms", j["scene"]["scene_build_ms"], "kernel_ms", {k: round(v, 2) for k, v in j["kernel_ms"].items()})
+          "rmse", t[0].get("image_rmse_vs_single") if t else None, "| build ms", j["scene"]["scene_build_ms"], "kernel_ms", {k: (round(v, 2) if isinstance(v, float) else v) for k, v in j["kernel_ms"].items()})
 PY
 # DRAM traffic of every one-lane traverse launch (for roofline.traffic)
 PT_LANES=1 timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum -k regex:traverse --clock-control none \
