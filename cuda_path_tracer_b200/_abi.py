@@ -100,6 +100,7 @@ SYMBOLS = {
     "pt_host_bvh_arrays": (C.c_int, [VP, C.POINTER(VP), C.POINTER(VP), C.POINTER(VP)]),
     "pt_host_bvh_trace_stats": (C.c_int, [VP, VP, C.c_uint64, C.c_int, VP]),
     "pt_host_bvh_free": (C.c_int, [VP]),
+    "pt_host_scene_check": (C.c_int, [C.POINTER(pt_scene_desc), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "pt_scene_load_file": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(VP), C.POINTER(pt_scene_file_info)]),
     "pt_scene_file_read": (C.c_int, [C.c_char_p, C.POINTER(VP), C.POINTER(pt_scene_desc),
                                      C.POINTER(pt_scene_file_info)]),

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cfloat>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -581,6 +582,80 @@ int pt_host_bvh_trace_stats(const pt_host_bvh* hb, const float* rays8, uint64_t 
   if (!hb || !rays8 || !out5) return fail(PT_ERR_INVALID, "pt_host_bvh_trace_stats: null argument");
   trace_stats(reinterpret_cast<const pt_host_bvh_impl*>(hb)->bvh, rays8, n_rays, wide, out5);
   return PT_OK;
+}
+
+static int pt_host_scene_check_impl(const pt_scene_desc* desc, uint64_t* out4, uint64_t* hash_out)
+{
+  if (!desc || !out4) return fail(PT_ERR_INVALID, "pt_host_scene_check: null argument");
+  SceneBuild sb;
+  const int rc = scene_prepare(desc, false, sb); // tables + sphere trees only: no mesh build
+  if (rc != PT_OK) return rc;
+  const uint32_t n = (uint32_t)sb.spheres.size();
+  std::vector<uint32_t> seen(n, 0u);
+  uint64_t violations = 0, trees = 0;
+  struct Item {
+    int node;
+    float lo[3], hi[3];
+  };
+  auto walk = [&](int root, uint32_t lo_i, uint32_t hi_i) {
+    if (root < 0) { // linear group: every sphere is "referenced" by the scan
+      for (uint32_t i = lo_i; i < hi_i; ++i) seen[i]++;
+      return;
+    }
+    ++trees;
+    std::vector<Item> todo;
+    Item r{root, {-FLT_MAX, -FLT_MAX, -FLT_MAX}, {FLT_MAX, FLT_MAX, FLT_MAX}};
+    todo.push_back(r);
+    while (!todo.empty()) {
+      const Item it = todo.back();
+      todo.pop_back();
+      if (it.node >= 0) {
+        if ((size_t)it.node * 16 + 16 > sb.sph_nodes.size()) {
+          ++violations;
+          continue;
+        }
+        const float* nd = sb.sph_nodes.data() + (size_t)it.node * 16;
+        for (int k = 0; k < 2; ++k) {
+          Item c;
+          std::memcpy(&c.node, nd + 12 + k, 4);
+          const float* xy = nd + 4 * k;
+          c.lo[0] = xy[0], c.hi[0] = xy[1], c.lo[1] = xy[2], c.hi[1] = xy[3];
+          c.lo[2] = nd[8 + 2 * k], c.hi[2] = nd[9 + 2 * k];
+          for (int a = 0; a < 3; ++a) // a child box may not stick out of its parent's
+            if (c.lo[a] < it.lo[a] || c.hi[a] > it.hi[a]) ++violations;
+          todo.push_back(c);
+        }
+      } else {
+        const uint32_t leaf = (uint32_t)(~it.node), first = leaf >> 3, count = (leaf & 7u) + 1u;
+        for (uint32_t i = first; i < first + count; ++i) {
+          if (i < lo_i || i >= hi_i) {
+            ++violations;
+            continue;
+          }
+          seen[i]++;
+          const DevSphere& s = sb.spheres[i];
+          const float c3[3] = {s.wx, s.wy, s.wz};
+          for (int a = 0; a < 3; ++a)
+            if (c3[a] - s.wr < it.lo[a] || c3[a] + s.wr > it.hi[a]) ++violations;
+        }
+      }
+    }
+  };
+  walk(sb.sph_root_before, 0u, sb.n_spheres_before);
+  walk(sb.sph_root_after, sb.n_spheres_before, n);
+  for (uint32_t i = 0; i < n; ++i)
+    if (seen[i] != 1u) ++violations;
+  out4[0] = n;
+  out4[1] = sb.sph_nodes.size() / 16;
+  out4[2] = violations;
+  out4[3] = trees;
+  if (hash_out) *hash_out = sb.content_hash;
+  return PT_OK;
+}
+
+int pt_host_scene_check(const pt_scene_desc* desc, uint64_t* out4, uint64_t* hash_out)
+{
+  return guarded("pt_host_scene_check", [&] { return pt_host_scene_check_impl(desc, out4, hash_out); });
 }
 
 int pt_host_bvh_free(pt_host_bvh* hb)

@@ -241,6 +241,13 @@ PT_API int pt_host_bvh_arrays(const pt_host_bvh* bvh, const float** nodes, const
 PT_API int pt_host_bvh_trace_stats(const pt_host_bvh* bvh, const float* rays8, uint64_t n_rays, int wide,
                                    uint64_t* out5);
 PT_API int pt_host_bvh_free(pt_host_bvh* bvh);
+/* Host-only check of the non-mesh half of scene preparation (no CUDA call): the sphere tables are
+ * built exactly as pt_scene_create builds them and the sphere-group trees (more than 32 rigidly
+ * placed spheres per group) are walked.  out4 = {spheres, tree nodes, violations, trees built};
+ * a violation is a sphere that is not referenced by exactly one leaf or whose world-space bound
+ * sticks out of any box on its path from the root.  *hash_out = the description fingerprint that
+ * progressive-state files carry. */
+PT_API int pt_host_scene_check(const pt_scene_desc* desc, uint64_t* out4, uint64_t* hash_out);
 
 /* replaces read_scene/scene_from_json/load_obj (assets/scene_parser.cpp:6-22,
  * assets/json_parser.cpp:174-224, assets/model_loader.cpp:11-44). */

@@ -272,3 +272,35 @@ def test_host_tree_does_not_depend_on_the_thread_count(tmp_path):
         outs.append(r.stdout)
     assert outs[0] == outs[1] == outs[2], outs
     assert len(outs[0].split()) == 6
+
+
+def _scene_check(sd):
+    import ctypes as C
+    d, keep = sd.to_desc()
+    out4 = (C.c_uint64 * 4)()
+    h = C.c_uint64(0)
+    rc = pt.load_library().pt_host_scene_check(C.byref(d), out4, C.byref(h))
+    assert rc == 0, pt.load_library().pt_last_error()
+    return [int(x) for x in out4], int(h.value)
+
+
+def test_sphere_group_trees_are_structurally_valid_and_the_fingerprint_tracks_the_description():
+    """Host only: groups of more than 32 rigidly placed spheres get a tree whose leaves reference
+    every sphere of the group exactly once inside nested boxes; small or non-rigid groups keep the
+    reference's linear scan; the description fingerprint (progressive-state files) changes with
+    the description and only with it."""
+    sd = pt.many_spheres_scene(400, 64, 64)
+    (n, nodes, violations, trees), h1 = _scene_check(sd)
+    assert n == 401 and trees == 2 and nodes >= 2 * (200 // 4 // 2) and violations == 0
+    (_, _, _, _), h1b = _scene_check(pt.many_spheres_scene(400, 64, 64))
+    assert h1 == h1b
+    (_, _, v2, t2), h2 = _scene_check(pt.many_spheres_scene(400, 64, 64, seed=1))
+    assert h2 != h1 and v2 == 0 and t2 == 2
+    # few spheres: no tree (the reference's object loop as it is)
+    (n3, nodes3, v3, t3), _ = _scene_check(pt.three_balls(64, 64))
+    assert (n3, nodes3, v3, t3) == (4, 0, 0, 0)
+    # a scaled (non-rigid) sphere in a big group switches that group back to the scan
+    sd4 = pt.many_spheres_scene(100, 64, 64, with_mesh=False)
+    sd4.add_sphere(0.5, pt.compose(pt.scale(2.0), pt.translate((0.0, 1.0, -3.0))), "a")
+    (n4, nodes4, v4, t4), _ = _scene_check(sd4)
+    assert n4 == 102 and t4 == 0 and nodes4 == 0 and v4 == 0
