@@ -1522,7 +1522,7 @@ static const Tunables& tunables()
 {
   static const Tunables t = [] {
     Tunables t{};
-    t.refill = env_int("PT_REFILL", EXT_REFILL);
+    t.refill = env_int("PT_REFILL", 0); // 0 = choose by scene size (launch_t2v)
     t.inner_min = env_int("PT_INNER_MIN", EXT_INNER_MIN);
     t.stream_state = env_int("PT_STREAM_STATE", 0);
     t.node_min = env_int("PT_NODE_MIN", 12);
@@ -1612,6 +1612,18 @@ static uint32_t persistent_grid(K kern, const LaunchEnv& env, int threads, size_
   return (uint32_t)(env.sms * cache_nb[dev]);
 }
 
+// Lanes still walking below which a warp goes back to refill.  Measured with two lanes: 12 / 16 /
+// 20 / 24 give 10 229 / 10 230 / 10 120 / 9 905 Mrays/s on the bunny and 2 627 / 2 596 / - / 2 331
+// on the 10 M-triangle terrain (walks there are long and uneven: refilling earlier keeps more of
+// the misses in flight).
+static int refill_for(const DevScene& sc)
+{
+  const int r = tunables().refill;
+  if (r > 0) return r;
+  const size_t scene_bytes = (size_t)sc.n_nodes * 64 + (size_t)sc.n_tris * 48;
+  return scene_bytes > (512ull << 20) ? 12 : EXT_REFILL;
+}
+
 template <int SRC, int MINB, bool L256>
 static void launch_t2v(const LaunchEnv& env, const DevScene& sc, const PathState& ps, const uint32_t* tq,
                        const uint32_t* n_ptr, uint32_t n_host, uint32_t* work, const float4* rays,
@@ -1622,7 +1634,7 @@ static void launch_t2v(const LaunchEnv& env, const DevScene& sc, const PathState
   static size_t sm[64] = {0};
   const Tunables& t = tunables();
   const uint32_t grid = min(persistent_grid(kern, env, EXT_THREADS, 0, nb, sm), max_grid);
-  kern<<<grid, EXT_THREADS, 0, env.stream>>>(sc, ps, tq, n_ptr, n_host, work, rays, out, t.refill,
+  kern<<<grid, EXT_THREADS, 0, env.stream>>>(sc, ps, tq, n_ptr, n_host, work, rays, out, refill_for(sc),
                                              t.inner_min, t.stream_state, bins);
 }
 
@@ -1638,7 +1650,7 @@ static void launch_t2(const LaunchEnv& env, const DevScene& sc, const PathState&
     static int nb[64] = {0};
     static size_t sm[64] = {0};
     const uint32_t grid = min(persistent_grid(kern, env, EXT_THREADS, 0, nb, sm), max_grid);
-    kern<<<grid, EXT_THREADS, 0, env.stream>>>(sc, ps, tq, n_ptr, n_host, work, rays, out, t.refill, t.inner_min,
+    kern<<<grid, EXT_THREADS, 0, env.stream>>>(sc, ps, tq, n_ptr, n_host, work, rays, out, refill_for(sc), t.inner_min,
                                                t.stream_state, bins);
     return;
   }
@@ -1646,10 +1658,15 @@ static void launch_t2(const LaunchEnv& env, const DevScene& sc, const PathState&
   if (minb == 0) {
     // Measured (profiles/README.md, round 2): a tree that lives in L1/L2 is bound by L1 data-pipe
     // wavefronts and likes the 256-bit node fetch (bunny: traverse -3 %); a scene far beyond the
-    // 126 MB L2 is bound by DRAM latency and likes 12 CTAs per SM at 40 registers (10 M-triangle
-    // terrain: -5 %); in between (2.6 M triangles) both lose 2 %.
+    // 126 MB L2 likes more resident warps to hide its misses: 10 CTAs per SM at 48 registers
+    // (10 M-triangle terrain, two lanes: 2 476 -> 2 596 Mrays/s; 12 CTAs at 40 registers spill
+    // into the same L1 data pipe and only matched it in one-lane passes); in between (2.6 M
+    // triangles) neither moves the result by more than 0.5 %.
+    // (ld.global.nc.L2::256B / ::128B prefetch-size hints on the triangle and node loads and
+    // cudaLimitMaxL2FetchGranularity = 32 / 128 were measured on all three scenes: no effect
+    // beyond 0.1 %, profiles/README.md; removed.)
     const size_t node_bytes = (size_t)sc.n_nodes * 64, scene_bytes = node_bytes + (size_t)sc.n_tris * 48;
-    minb = scene_bytes > (512ull << 20) ? 12 : EXT_MIN_BLOCKS;
+    minb = scene_bytes > (512ull << 20) ? 10 : EXT_MIN_BLOCKS;
     l256 = node_bytes <= (2ull << 20) ? 1 : 0;
   }
 #define PT_T2_CASE(B, L)                                                                           \
@@ -1677,7 +1694,7 @@ static void launch_t8(const LaunchEnv& env, const DevScene& sc, const PathState&
   static size_t sm[64] = {0};
   const uint32_t grid = min(persistent_grid(kern, env, THREADS, smem, nb, sm), max_grid);
   kern<<<grid, THREADS, smem, env.stream>>>(sc, ps, tq, n_ptr, n_host, work, rays, out,
-                                            tunables().refill, tunables().node_min,
+                                            refill_for(sc), tunables().node_min,
                                             tunables().tri_min, n_staged, 0x4B000000u);
 }
 
