@@ -207,6 +207,13 @@ struct DevScene {
   // order); root < 0 = test the group linearly.
   const float4* sph_nodes;
   int32_t sph_root_before, sph_root_after;
+  // 32-byte companion of `nodes` for the traversal kernels (null = walk the 64-byte nodes): the
+  // twelve child planes on a 16-bit grid over the root box, always rounded outwards by at least one
+  // cell, plus the two child references:  x lo|hi<<16, y, z of child 0; x, y, z of child 1; ref 0;
+  // ref 1.  A plane is q_org + q * q_cell.  Half the bytes per inner-node visit through the L1 data
+  // pipe, which is what bounds traverse_kernel.
+  const uint4* qnodes;
+  float q_org[3], q_cell[3];
 };
 #define PT_SPHERE_BVH_MIN 32
 

@@ -370,6 +370,50 @@ int scene_prepare(const pt_scene_desc* desc, bool host_build, SceneBuild& sb)
   return PT_OK;
 }
 
+// The 32-byte quantised companion of the 64-byte nodes (DevScene::qnodes): every child plane on a
+// 16-bit grid over the root box, rounded outwards and then moved one more cell outwards — the
+// reserve the device's half-cell rounding needs (trav_init<QN>).  The grid spans 65 000 cells per
+// axis (an axis thinner than 1/1024 of the longest one is given that much), 200 cells below the
+// root box.  Returns false — the traversal then walks the exact nodes — if a plane does not fit.
+static bool quantise_nodes(const FlatBVH& bvh, std::vector<uint32_t>& q, float org[3], float cell[3])
+{
+  const uint32_t n = bvh.n_nodes;
+  if (n == 0 || bvh.nodes.size() < (size_t)n * 16) return false;
+  float ext[3], longest = 0.f;
+  for (int a = 0; a < 3; ++a) {
+    ext[a] = bvh.root_hi[a] - bvh.root_lo[a];
+    if (!(ext[a] >= 0.f) || !std::isfinite(ext[a])) return false;
+    longest = std::max(longest, ext[a]);
+  }
+  if (!(longest > 0.f)) return false;
+  for (int a = 0; a < 3; ++a) {
+    cell[a] = std::max(ext[a], longest / 1024.f) / 65000.f;
+    org[a] = bvh.root_lo[a] - 200.f * cell[a];
+    if (!(cell[a] > 0.f) || !std::isfinite(org[a])) return false;
+  }
+  q.resize((size_t)n * 8);
+  // plane slots of the 64-byte node (common.cuh): {lo, hi} x {x, y, z} x {child 0, child 1}
+  static const int src[6][2] = {{0, 1}, {2, 3}, {8, 9}, {4, 5}, {6, 7}, {10, 11}};
+  static const int axis[6] = {0, 1, 2, 0, 1, 2};
+  bool ok = true;
+#pragma omp parallel for schedule(static) reduction(&& : ok)
+  for (long long i = 0; i < (long long)n; ++i) {
+    const float* nd = &bvh.nodes[(size_t)i * 16];
+    uint32_t* w = &q[(size_t)i * 8];
+    for (int k = 0; k < 6; ++k) {
+      const int a = axis[k];
+      const double lo = std::floor(((double)nd[src[k][0]] - (double)org[a]) / (double)cell[a]) - 1.0;
+      const double hi = std::ceil(((double)nd[src[k][1]] - (double)org[a]) / (double)cell[a]) + 1.0;
+      if (!(lo >= 0.0 && hi <= 65535.0 && lo <= hi)) ok = false;
+      const uint32_t ql = (uint32_t)std::min(65535.0, std::max(0.0, lo)), qh = (uint32_t)std::min(65535.0, std::max(0.0, hi));
+      w[k] = ql | (qh << 16);
+    }
+    std::memcpy(&w[6], &nd[12], 4);
+    std::memcpy(&w[7], &nd[13], 4);
+  }
+  return ok;
+}
+
 int scene_upload(const pt_scene_desc* desc, const SceneBuild& sb, DeviceLBVH* dl, int device, pt_scene** out)
 {
   *out = nullptr;
@@ -404,6 +448,21 @@ int scene_upload(const pt_scene_desc* desc, const SceneBuild& sb, DeviceLBVH* dl
     if (e == cudaSuccess) e = upload(bvh.tris.data(), bvh.tris.size() * 4, &sc->d_tris);
   }
   if (e == cudaSuccess) e = upload(bvh.nodes8.data(), bvh.nodes8.size() * 4, &sc->d_nodes8);
+  // Quantised nodes for the traversal kernels: host-built binary trees of scenes that are not
+  // 'big' (the > 512 MB variant of traverse_kernel keeps the exact nodes: its cells would be a
+  // visible fraction of a triangle) and have no sphere trees.  PT_QNODES=0 / 1 forces off / on.
+  float q_org[3] = {0.f, 0.f, 0.f}, q_cell[3] = {0.f, 0.f, 0.f};
+  if (e == cudaSuccess && !from_device && bvh.n_nodes8 == 0 && bvh.n_nodes != 0) {
+    static const int q_env = [] {
+      const char* v = getenv("PT_QNODES");
+      return v ? atoi(v) : -1;
+    }();
+    const size_t scene_bytes = (size_t)bvh.n_nodes * 64 + (size_t)bvh.n_tris * 48;
+    const bool sphere_trees = sb.sph_root_before >= 0 || sb.sph_root_after >= 0;
+    const bool want = q_env >= 0 ? q_env != 0 : scene_bytes <= (512ull << 20);
+    std::vector<uint32_t> q;
+    if (want && !sphere_trees && quantise_nodes(bvh, q, q_org, q_cell)) e = upload(q.data(), q.size() * 4, &sc->d_qnodes);
+  }
   if (e == cudaSuccess) e = upload(sb.spheres.data(), sb.spheres.size() * sizeof(DevSphere), &sc->d_spheres);
   if (e == cudaSuccess) e = upload(sb.sph_nodes.data(), sb.sph_nodes.size() * 4, &sc->d_sph_nodes);
   if (e == cudaSuccess) e = upload(sb.mats.data(), sb.mats.size() * sizeof(DevMaterial), &sc->d_materials);
@@ -425,6 +484,8 @@ int scene_upload(const pt_scene_desc* desc, const SceneBuild& sb, DeviceLBVH* dl
   sc->dev.sph_root_before = sb.sph_root_before;
   sc->dev.sph_root_after = sb.sph_root_after;
   sc->dev.n_nodes = n_nodes;
+  sc->dev.qnodes = (const uint4*)sc->d_qnodes;
+  for (int a = 0; a < 3; ++a) sc->dev.q_org[a] = q_org[a], sc->dev.q_cell[a] = q_cell[a];
   // the wide traversal keeps a PT_STACK8-entry stack: one node group per level at most
   const bool use_wide = !from_device && bvh.n_nodes8 != 0 && bvh.depth8 <= PT_STACK8;
   sc->dev.nodes8 = use_wide ? (const uint4*)sc->d_nodes8 : nullptr;
@@ -671,6 +732,7 @@ int pt_scene_destroy(pt_scene* sc)
   cudaFree(sc->d_nodes);
   cudaFree(sc->d_tris);
   cudaFree(sc->d_nodes8);
+  cudaFree(sc->d_qnodes);
   cudaFree(sc->d_spheres);
   cudaFree(sc->d_sph_nodes);
   cudaFree(sc->d_materials);

@@ -92,6 +92,7 @@ struct pt_scene {
   void* d_nodes = nullptr;
   void* d_tris = nullptr;
   void* d_nodes8 = nullptr;
+  void* d_qnodes = nullptr; // 32-byte quantised companion of d_nodes (DevScene::qnodes), or null
   void* d_spheres = nullptr;
   void* d_sph_nodes = nullptr;
   void* d_materials = nullptr;

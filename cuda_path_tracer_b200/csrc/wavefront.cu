@@ -398,19 +398,37 @@ struct Trav {
 // (A hybrid stack — the first 8 or 16 entries in shared memory laid out [entry][thread], one
 // conflict-free wavefront per warp access, the rest in local memory — was measured and rejected:
 // traverse 15.27 -> 15.82 / 16.10 ms on the bunny frame, profiles/README.md.)
-PT_D void trav_init(Trav& T, f3 o, f3 d, float tmin, float tbest, int start, int* stack)
+// QN: the inner nodes are read from DevScene::qnodes.  A plane arrives as the float 2^23 + q (its
+// 16 bits dropped into the mantissa of 0x4B000000 by one PRMT), so with
+//   idx = cell / d   and   odx = 2^23 * idx - (org - o) / d
+// the slab distance (org + q * cell - o) / d is the SAME fused multiply-add f * idx - odx as for a
+// 64-byte node: de-quantisation costs no arithmetic.  Rounding odx loses at most half a cell (the
+// grid keeps a whole one in reserve); what is proportional to the distance is covered by the
+// widened comparison below, as for the exact planes.
+template <bool QN = false>
+PT_D void trav_init(const DevScene& sc, Trav& T, f3 o, f3 d, float tmin, float tbest, int start, int* stack)
 {
   T.o = o;
   T.d = d;
   T.tmin = tmin;
   T.tbest = tbest;
   T.best = -1;
-  T.idx = safe_inv(d.x);
-  T.idy = safe_inv(d.y);
-  T.idz = safe_inv(d.z);
-  T.odx = o.x * T.idx;
-  T.ody = o.y * T.idy;
-  T.odz = o.z * T.idz;
+  const float ix = safe_inv(d.x), iy = safe_inv(d.y), iz = safe_inv(d.z);
+  if (QN) {
+    T.idx = sc.q_cell[0] * ix;
+    T.idy = sc.q_cell[1] * iy;
+    T.idz = sc.q_cell[2] * iz;
+    T.odx = fmaf(8388608.0f, T.idx, -((sc.q_org[0] - o.x) * ix));
+    T.ody = fmaf(8388608.0f, T.idy, -((sc.q_org[1] - o.y) * iy));
+    T.odz = fmaf(8388608.0f, T.idz, -((sc.q_org[2] - o.z) * iz));
+  } else {
+    T.idx = ix;
+    T.idy = iy;
+    T.idz = iz;
+    T.odx = o.x * T.idx;
+    T.ody = o.y * T.idy;
+    T.odz = o.z * T.idz;
+  }
   stack[0] = PT_SENTINEL;
   T.sp = 1;
   T.node = start;
@@ -418,12 +436,33 @@ PT_D void trav_init(Trav& T, f3 o, f3 d, float tmin, float tbest, int start, int
 
 // Inner-node visit: two slab tests against the children's boxes stored in the node, ordered
 // descent (nearer child first), farther child pushed.
-template <bool L256>
+PT_D float q_lo(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)); }
+PT_D float q_hi(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)); }
+
+template <bool L256, bool QN = false>
 PT_D void trav_inner(const DevScene& sc, Trav& T, int* stack)
 {
   float4 n0, n1, n2, n3;
   PT_CHECK((uint32_t)T.node < sc.n_nodes, "inner node index outside the tree");
-  load_node<L256>(sc.nodes + (size_t)T.node * 4, n0, n1, n2, n3);
+  if (QN) {
+    // (the same variables as the 64-byte node, so that everything below is shared)
+    uint4 a, b;
+    const uint4* qp = sc.qnodes + (size_t)T.node * 2;
+    if (L256) {
+      asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                   : "l"(qp));
+    } else {
+      a = __ldg(qp);
+      b = __ldg(qp + 1);
+    }
+    n0 = make_float4(q_lo(a.x), q_hi(a.x), q_lo(a.y), q_hi(a.y));
+    n1 = make_float4(q_lo(a.w), q_hi(a.w), q_lo(b.x), q_hi(b.x));
+    n2 = make_float4(q_lo(a.z), q_hi(a.z), q_lo(b.y), q_hi(b.y));
+    n3 = make_float4(__uint_as_float(b.z), __uint_as_float(b.w), 0.f, 0.f);
+  } else {
+    load_node<L256>(sc.nodes + (size_t)T.node * 4, n0, n1, n2, n3);
+  }
   const float c0lox = n0.x * T.idx - T.odx, c0hix = n0.y * T.idx - T.odx;
   const float c0loy = n0.z * T.idy - T.ody, c0hiy = n0.w * T.idy - T.ody;
   const float c0loz = n2.x * T.idz - T.odz, c0hiz = n2.y * T.idz - T.odz;
@@ -645,7 +684,7 @@ enum { SRC_QUEUE = 1, SRC_BATCH = 2 };
 // MINB: resident CTAs per SM the register allocation is bounded for (8 -> 64 registers, 50 % of
 // the warp slots; 10 -> 48; 12 -> 40); L256: node fetch with two 256-bit loads.  Both are
 // run-time choices between instantiations (PT_TRAV="minb,l256"), measured in profiles/README.md.
-template <int SRC, int MINB, bool L256, bool ST>
+template <int SRC, int MINB, bool L256, bool ST, bool QN = false>
 __global__ void __launch_bounds__(EXT_THREADS, MINB)
 traverse_kernel(const DevScene sc, const PathState ps, const uint32_t* __restrict__ tq,
                 const uint32_t* __restrict__ n_ptr, uint32_t n_host, uint32_t* __restrict__ work,
@@ -679,7 +718,7 @@ traverse_kernel(const DevScene sc, const PathState ps, const uint32_t* __restric
             const float4 ro = ld_state(ps.ray + 2 * (size_t)pid, (uint32_t)stream_state);
             const float4 rd = ld_state(ps.ray + 2 * (size_t)pid + 1, (uint32_t)stream_state);
             const uint4 ax = ld_state(ps.aux + pid, (uint32_t)stream_state);
-            trav_init(T, xyz(ro), xyz(rd), ro.w, __uint_as_float(ax.x), (int)ax.z, stack);
+            trav_init<QN>(sc, T, xyz(ro), xyz(rd), ro.w, __uint_as_float(ax.x), (int)ax.z, stack);
             has = true;
           } else {
             pid = idx;
@@ -687,7 +726,7 @@ traverse_kernel(const DevScene sc, const PathState ps, const uint32_t* __restric
             float tbest;
             int start;
             const bool complex_ray = classify<ST>(sc, xyz(ro), xyz(rd), ro.w, rd.w, tbest, code, start);
-            trav_init(T, xyz(ro), xyz(rd), ro.w, tbest, start, stack);
+            trav_init<QN>(sc, T, xyz(ro), xyz(rd), ro.w, tbest, start, stack);
             if (!complex_ray) T.node = PT_SENTINEL;
             has = true;
           }
@@ -712,7 +751,7 @@ traverse_kernel(const DevScene sc, const PathState ps, const uint32_t* __restric
         const uint32_t m_leaf = __ballot_sync(0xffffffffu, has && T.node < 0);
         if (m_inner == 0u) break;
         if (__popc(m_inner) < inner_min && m_leaf != 0u) break;
-        if (inner) trav_inner<L256>(sc, T, stack);
+        if (inner) trav_inner<L256, QN>(sc, T, stack);
       }
       if (has && T.node < 0) trav_leaf(sc, T, stack);
     }
@@ -1438,7 +1477,7 @@ chain_kernel(const DevScene sc, const PathState ps, const PassParams pp, const P
 // over few paths (forced on millions of rays it costs 32 % on the 10 M-triangle terrain: hence the
 // prediction); results are bit-identical (every path carries its own RNG stream and the same
 // arithmetic runs in the same order per path).
-template <bool L256, bool ST>
+template <bool L256, bool ST, bool QN = false>
 __global__ void __launch_bounds__(EXT_THREADS)
 finish_kernel(const DevScene sc, const PathState ps, const ParkBuf in, const uint32_t* __restrict__ n_ptr,
               uint32_t max_depth, unsigned long long* __restrict__ total_rays)
@@ -1462,10 +1501,10 @@ finish_kernel(const DevScene sc, const PathState ps, const ParkBuf in, const uin
     for (;;) {
       if (need_traversal) {
         Trav T;
-        trav_init(T, o, d, tmin, tbest, start, stack);
+        trav_init<QN>(sc, T, o, d, tmin, tbest, start, stack);
         while (T.node != PT_SENTINEL) {
           if (T.node >= 0)
-            trav_inner<L256>(sc, T, stack);
+            trav_inner<L256, QN>(sc, T, stack);
           else
             trav_leaf(sc, T, stack);
         }
@@ -1550,13 +1589,17 @@ void launch_finish(const LaunchEnv& env, const DevScene& sc, const PassBuffers& 
   const bool sphere_trees = sc.sph_root_before >= 0 || sc.sph_root_after >= 0;
   const bool l256 = (size_t)sc.n_nodes * 64 <= (2ull << 20);
   const uint32_t grid = (uint32_t)env.sms * 4u;
-#define PT_FIN(L, S)                                                                               \
-  finish_kernel<L, S><<<grid, EXT_THREADS, 0, env.stream>>>(sc, pb.ps, pb.park[iter & 1], pb.tcounters + iter, \
-                                                             max_depth, pb.total_rays)
+#define PT_FIN(L, S, Q)                                                                            \
+  finish_kernel<L, S, Q><<<grid, EXT_THREADS, 0, env.stream>>>(sc, pb.ps, pb.park[iter & 1], pb.tcounters + iter, \
+                                                                max_depth, pb.total_rays)
+  // (the same node fetch as traverse_kernel, so that a path's walk — hence the winner of an exact
+  // tie — does not depend on which of the two kernels finishes it)
   if (sphere_trees) {
-    if (l256) PT_FIN(true, true); else PT_FIN(false, true);
+    if (l256) PT_FIN(true, true, false); else PT_FIN(false, true, false);
+  } else if (sc.qnodes != nullptr) {
+    if (l256) PT_FIN(true, false, true); else PT_FIN(false, false, true);
   } else {
-    if (l256) PT_FIN(true, false); else PT_FIN(false, false);
+    if (l256) PT_FIN(true, false, false); else PT_FIN(false, false, false);
   }
 #undef PT_FIN
 }
@@ -1624,12 +1667,12 @@ static int refill_for(const DevScene& sc)
   return scene_bytes > (512ull << 20) ? 12 : EXT_REFILL;
 }
 
-template <int SRC, int MINB, bool L256>
+template <int SRC, int MINB, bool L256, bool QN = false>
 static void launch_t2v(const LaunchEnv& env, const DevScene& sc, const PathState& ps, const uint32_t* tq,
                        const uint32_t* n_ptr, uint32_t n_host, uint32_t* work, const float4* rays,
                        HitRecord* out, uint32_t max_grid, const BinLists& bins)
 {
-  auto kern = traverse_kernel<SRC, MINB, L256, false>;
+  auto kern = traverse_kernel<SRC, MINB, L256, false, QN>;
   static int nb[64] = {0};
   static size_t sm[64] = {0};
   const Tunables& t = tunables();
@@ -1668,6 +1711,13 @@ static void launch_t2(const LaunchEnv& env, const DevScene& sc, const PathState&
     const size_t node_bytes = (size_t)sc.n_nodes * 64, scene_bytes = node_bytes + (size_t)sc.n_tris * 48;
     minb = scene_bytes > (512ull << 20) ? 10 : EXT_MIN_BLOCKS;
     l256 = node_bytes <= (2ull << 20) ? 1 : 0;
+  }
+  // quantised nodes (scene_upload builds them for host-built trees that are not 'big'): the
+  // 8-CTA instantiation, 256-bit fetch as chosen above
+  if (sc.qnodes != nullptr) {
+    if (minb == 10) return launch_t2v<SRC, 10, false, true>(env, sc, ps, tq, n_ptr, n_host, work, rays, out, max_grid, bins);
+    if (l256) return launch_t2v<SRC, EXT_MIN_BLOCKS, true, true>(env, sc, ps, tq, n_ptr, n_host, work, rays, out, max_grid, bins);
+    return launch_t2v<SRC, EXT_MIN_BLOCKS, false, true>(env, sc, ps, tq, n_ptr, n_host, work, rays, out, max_grid, bins);
   }
 #define PT_T2_CASE(B, L)                                                                           \
   if (minb == B && l256 == L)                                                                      \
