@@ -54,6 +54,18 @@ def build_debug(verbose: bool = False) -> str:
     return LIB_DEBUG
 
 
+def build_variant(name: str, defines: list[str], verbose: bool = False) -> str:
+    """libb200pt_<name>.so: the same sources with extra -D flags, for A/B runs of compile-time
+    choices (select with B200PT_LIB=<path>, e.g. through scripts/ab.py).  Not built by default."""
+    out = os.path.join(HERE, f"libb200pt_{name}.so")
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [_nvcc(), *NVCC_FLAGS, *defines, "-shared", "-o", out, *srcs, "-lz", "-lgomp"]
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.run(cmd, check=True, cwd=CSRC)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
     deps = srcs + [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
@@ -75,5 +87,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 if __name__ == "__main__":
     if "--debug" in sys.argv:
         print(build_debug(verbose="-v" in sys.argv))
+    elif "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], [a for a in sys.argv[i + 2:] if a.startswith("-D")], verbose="-v" in sys.argv))
     else:
         print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -393,6 +393,10 @@ struct Trav {
   int node; // current node, PT_SENTINEL when done
   int sp;
   int best; // best triangle slot or -1
+  // quantised nodes: PRMT selectors that drop the NEAR plane of an axis pair (lo | hi << 16) into
+  // the float 2^23 + q — the low half for a ray that travels up the axis, the high half otherwise;
+  // the far plane's selector is sel ^ 0x22.  The slab test then needs no per-axis min / max.
+  uint32_t selx, sely, selz;
 };
 
 // (A hybrid stack — the first 8 or 16 entries in shared memory laid out [entry][thread], one
@@ -421,6 +425,9 @@ PT_D void trav_init(const DevScene& sc, Trav& T, f3 o, f3 d, float tmin, float t
     T.odx = fmaf(8388608.0f, T.idx, -((sc.q_org[0] - o.x) * ix));
     T.ody = fmaf(8388608.0f, T.idy, -((sc.q_org[1] - o.y) * iy));
     T.odz = fmaf(8388608.0f, T.idz, -((sc.q_org[2] - o.z) * iz));
+    T.selx = T.idx >= 0.0f ? 0x7610u : 0x7632u;
+    T.sely = T.idy >= 0.0f ? 0x7610u : 0x7632u;
+    T.selz = T.idz >= 0.0f ? 0x7610u : 0x7632u;
   } else {
     T.idx = ix;
     T.idy = iy;
@@ -436,16 +443,18 @@ PT_D void trav_init(const DevScene& sc, Trav& T, f3 o, f3 d, float tmin, float t
 
 // Inner-node visit: two slab tests against the children's boxes stored in the node, ordered
 // descent (nearer child first), farther child pushed.
-PT_D float q_lo(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)); }
-PT_D float q_hi(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)); }
+#ifndef PT_QN_SIGNSEL
+#define PT_QN_SIGNSEL 1
+#endif
+PT_D float q_pick(uint32_t w, uint32_t sel) { return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)); }
 
 template <bool L256, bool QN = false>
 PT_D void trav_inner(const DevScene& sc, Trav& T, int* stack)
 {
-  float4 n0, n1, n2, n3;
   PT_CHECK((uint32_t)T.node < sc.n_nodes, "inner node index outside the tree");
+  float c0min, c0max, c1min, c1max;
+  int c0, c1;
   if (QN) {
-    // (the same variables as the 64-byte node, so that everything below is shared)
     uint4 a, b;
     const uint4* qp = sc.qnodes + (size_t)T.node * 2;
     if (L256) {
@@ -456,32 +465,53 @@ PT_D void trav_inner(const DevScene& sc, Trav& T, int* stack)
       a = __ldg(qp);
       b = __ldg(qp + 1);
     }
-    n0 = make_float4(q_lo(a.x), q_hi(a.x), q_lo(a.y), q_hi(a.y));
-    n1 = make_float4(q_lo(a.w), q_hi(a.w), q_lo(b.x), q_hi(b.x));
-    n2 = make_float4(q_lo(a.z), q_hi(a.z), q_lo(b.y), q_hi(b.y));
-    n3 = make_float4(__uint_as_float(b.z), __uint_as_float(b.w), 0.f, 0.f);
+#if PT_QN_SIGNSEL
+    // f * idx - odx is monotonic in f with the sign of idx, so the plane the ray meets first is
+    // known per axis from the ray alone: 4 min/max per child instead of 10, same values
+    const uint32_t fx = T.selx ^ 0x22u, fy = T.sely ^ 0x22u, fz = T.selz ^ 0x22u;
+    const float n0x = q_pick(a.x, T.selx) * T.idx - T.odx, f0x = q_pick(a.x, fx) * T.idx - T.odx;
+    const float n0y = q_pick(a.y, T.sely) * T.idy - T.ody, f0y = q_pick(a.y, fy) * T.idy - T.ody;
+    const float n0z = q_pick(a.z, T.selz) * T.idz - T.odz, f0z = q_pick(a.z, fz) * T.idz - T.odz;
+    const float n1x = q_pick(a.w, T.selx) * T.idx - T.odx, f1x = q_pick(a.w, fx) * T.idx - T.odx;
+    const float n1y = q_pick(b.x, T.sely) * T.idy - T.ody, f1y = q_pick(b.x, fy) * T.idy - T.ody;
+    const float n1z = q_pick(b.y, T.selz) * T.idz - T.odz, f1z = q_pick(b.y, fz) * T.idz - T.odz;
+    c0min = fmaxf(fmaxf(n0x, n0y), fmaxf(n0z, T.tmin));
+    c0max = fminf(fminf(f0x, f0y), fminf(f0z, T.tbest));
+    c1min = fmaxf(fmaxf(n1x, n1y), fmaxf(n1z, T.tmin));
+    c1max = fminf(fminf(f1x, f1y), fminf(f1z, T.tbest));
+#else
+    const float c0lox = q_pick(a.x, 0x7610u) * T.idx - T.odx, c0hix = q_pick(a.x, 0x7632u) * T.idx - T.odx;
+    const float c0loy = q_pick(a.y, 0x7610u) * T.idy - T.ody, c0hiy = q_pick(a.y, 0x7632u) * T.idy - T.ody;
+    const float c0loz = q_pick(a.z, 0x7610u) * T.idz - T.odz, c0hiz = q_pick(a.z, 0x7632u) * T.idz - T.odz;
+    const float c1lox = q_pick(a.w, 0x7610u) * T.idx - T.odx, c1hix = q_pick(a.w, 0x7632u) * T.idx - T.odx;
+    const float c1loy = q_pick(b.x, 0x7610u) * T.idy - T.ody, c1hiy = q_pick(b.x, 0x7632u) * T.idy - T.ody;
+    const float c1loz = q_pick(b.y, 0x7610u) * T.idz - T.odz, c1hiz = q_pick(b.y, 0x7632u) * T.idz - T.odz;
+    c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), T.tmin));
+    c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), T.tbest));
+    c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), T.tmin));
+    c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), T.tbest));
+#endif
+    c0 = (int)b.z;
+    c1 = (int)b.w;
   } else {
+    float4 n0, n1, n2, n3;
     load_node<L256>(sc.nodes + (size_t)T.node * 4, n0, n1, n2, n3);
+    const float c0lox = n0.x * T.idx - T.odx, c0hix = n0.y * T.idx - T.odx;
+    const float c0loy = n0.z * T.idy - T.ody, c0hiy = n0.w * T.idy - T.ody;
+    const float c0loz = n2.x * T.idz - T.odz, c0hiz = n2.y * T.idz - T.odz;
+    const float c1lox = n1.x * T.idx - T.odx, c1hix = n1.y * T.idx - T.odx;
+    const float c1loy = n1.z * T.idy - T.ody, c1hiy = n1.w * T.idy - T.ody;
+    const float c1loz = n2.z * T.idz - T.odz, c1hiz = n2.w * T.idz - T.odz;
+    c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), T.tmin));
+    c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), T.tbest));
+    c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), T.tmin));
+    c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), T.tbest));
+    c0 = __float_as_int(n3.x);
+    c1 = __float_as_int(n3.y);
   }
-  const float c0lox = n0.x * T.idx - T.odx, c0hix = n0.y * T.idx - T.odx;
-  const float c0loy = n0.z * T.idy - T.ody, c0hiy = n0.w * T.idy - T.ody;
-  const float c0loz = n2.x * T.idz - T.odz, c0hiz = n2.y * T.idz - T.odz;
-  const float c1lox = n1.x * T.idx - T.odx, c1hix = n1.y * T.idx - T.odx;
-  const float c1loy = n1.z * T.idy - T.ody, c1hiy = n1.w * T.idy - T.ody;
-  const float c1loz = n2.z * T.idz - T.odz, c1hiz = n2.w * T.idz - T.odz;
-  const float c0min =
-      fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), T.tmin));
-  const float c0max =
-      fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), T.tbest));
-  const float c1min =
-      fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), T.tmin));
-  const float c1max =
-      fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), T.tbest));
   // robust slab comparison (Ize 2013): widen the far side by 2 ulp
   const bool trav0 = c0max * 1.0000004f >= c0min;
   const bool trav1 = c1max * 1.0000004f >= c1min;
-  const int c0 = __float_as_int(n3.x);
-  const int c1 = __float_as_int(n3.y);
   if (!trav0 && !trav1) {
     PT_CHECK(T.sp > 0, "traversal stack underflow");
     T.node = stack[--T.sp];
@@ -674,6 +704,15 @@ PT_D void stage_prefix(void* smem_dst, const void* gsrc, uint32_t bytes, unsigne
 #define PT_DEFAULT_ORDER 2 // measured: bunny +0.5 %, bunny_1m +1.5 %, terrain +5.5 % over order 0
 #endif
 
+#ifndef PT_INNER_STEPS
+// Inner nodes a lane visits per pair of warp votes in traverse_kernel.  The kernel is bound by
+// instruction issue and by the length of one lane's dependent chain, not by the L1 data pipe
+// (halving the node bytes bought 2.5 %), and the two ballots, the population count and the branches
+// of the while-while loop are ~20 of the ~80 instructions of a visit.  Measured (bunny, Mrays/s):
+// 1 / 2 / 3 / 4 steps = 10 301 / 10 600 / 10 784 / 10 593; same order on 150 k and 2.6 M triangles.
+#define PT_INNER_STEPS 3
+#endif
+
 enum { SRC_QUEUE = 1, SRC_BATCH = 2 };
 
 // (Staging the hottest nodes of the binary tree in shared memory — area-ordered prefix, 80-byte
@@ -751,7 +790,13 @@ traverse_kernel(const DevScene sc, const PathState ps, const uint32_t* __restric
         const uint32_t m_leaf = __ballot_sync(0xffffffffu, has && T.node < 0);
         if (m_inner == 0u) break;
         if (__popc(m_inner) < inner_min && m_leaf != 0u) break;
-        if (inner) trav_inner<L256, QN>(sc, T, stack);
+        if (inner) {
+          trav_inner<L256, QN>(sc, T, stack);
+          // further nodes before the next pair of votes (lanes that reached a leaf sit them out)
+#pragma unroll
+          for (int s = 1; s < PT_INNER_STEPS; ++s)
+            if ((uint32_t)T.node < (uint32_t)PT_SENTINEL) trav_inner<L256, QN>(sc, T, stack);
+        }
       }
       if (has && T.node < 0) trav_leaf(sc, T, stack);
     }
@@ -1714,10 +1759,14 @@ static void launch_t2(const LaunchEnv& env, const DevScene& sc, const PathState&
   }
   // quantised nodes (scene_upload builds them for host-built trees that are not 'big'): the
   // 8-CTA instantiation, 256-bit fetch as chosen above
+  // Their node data takes 8 registers instead of 16, so one more CTA fits per SM: 9 (56 registers)
+  // — measured with the final node test: bunny 11 300 (9) / 11 168 (10) Mrays/s, 150 k triangles
+  // 5 164 / 5 099, 2.6 M triangles 6 656 / 6 617 (profiles/r2_ab_traverse_sign_selected_planes.log).
   if (sc.qnodes != nullptr) {
-    if (minb == 10) return launch_t2v<SRC, 10, false, true>(env, sc, ps, tq, n_ptr, n_host, work, rays, out, max_grid, bins);
-    if (l256) return launch_t2v<SRC, EXT_MIN_BLOCKS, true, true>(env, sc, ps, tq, n_ptr, n_host, work, rays, out, max_grid, bins);
-    return launch_t2v<SRC, EXT_MIN_BLOCKS, false, true>(env, sc, ps, tq, n_ptr, n_host, work, rays, out, max_grid, bins);
+    const int qb = t.trav_minb != 0 ? t.trav_minb : 9;
+    if (qb >= 10) return launch_t2v<SRC, 10, false, true>(env, sc, ps, tq, n_ptr, n_host, work, rays, out, max_grid, bins);
+    if (l256) return launch_t2v<SRC, 9, true, true>(env, sc, ps, tq, n_ptr, n_host, work, rays, out, max_grid, bins);
+    return launch_t2v<SRC, 9, false, true>(env, sc, ps, tq, n_ptr, n_host, work, rays, out, max_grid, bins);
   }
 #define PT_T2_CASE(B, L)                                                                           \
   if (minb == B && l256 == L)                                                                      \
