@@ -1642,7 +1642,7 @@ void launch_finish(const LaunchEnv& env, const DevScene& sc, const PassBuffers& 
   if (sphere_trees) {
     if (l256) PT_FIN(true, true, false); else PT_FIN(false, true, false);
   } else if (sc.qnodes != nullptr) {
-    if (l256) PT_FIN(true, false, true); else PT_FIN(false, false, true);
+    PT_FIN(true, false, true);
   } else {
     if (l256) PT_FIN(true, false, false); else PT_FIN(false, false, false);
   }
@@ -1757,16 +1757,16 @@ static void launch_t2(const LaunchEnv& env, const DevScene& sc, const PathState&
     minb = scene_bytes > (512ull << 20) ? 10 : EXT_MIN_BLOCKS;
     l256 = node_bytes <= (2ull << 20) ? 1 : 0;
   }
-  // quantised nodes (scene_upload builds them for host-built trees that are not 'big'): the
-  // 8-CTA instantiation, 256-bit fetch as chosen above
-  // Their node data takes 8 registers instead of 16, so one more CTA fits per SM: 9 (56 registers)
-  // — measured with the final node test: bunny 11 300 (9) / 11 168 (10) Mrays/s, 150 k triangles
+  // Quantised nodes (scene_upload builds them for host-built trees that are not 'big').  Their
+  // node data takes 8 registers instead of 16, so one more CTA fits per SM: 9 (56 registers) —
+  // measured with the final node test: bunny 11 300 (9) / 11 168 (10) Mrays/s, 150 k triangles
   // 5 164 / 5 099, 2.6 M triangles 6 656 / 6 617 (profiles/r2_ab_traverse_sign_selected_planes.log).
+  // A quantised node is one 32-byte sector: always ONE 256-bit load, whatever the tree's size
+  // (2.6 M triangles: 6 647 -> 6 789 Mrays/s against two 128-bit loads).
   if (sc.qnodes != nullptr) {
     const int qb = t.trav_minb != 0 ? t.trav_minb : 9;
-    if (qb >= 10) return launch_t2v<SRC, 10, false, true>(env, sc, ps, tq, n_ptr, n_host, work, rays, out, max_grid, bins);
-    if (l256) return launch_t2v<SRC, 9, true, true>(env, sc, ps, tq, n_ptr, n_host, work, rays, out, max_grid, bins);
-    return launch_t2v<SRC, 9, false, true>(env, sc, ps, tq, n_ptr, n_host, work, rays, out, max_grid, bins);
+    if (qb >= 10) return launch_t2v<SRC, 10, true, true>(env, sc, ps, tq, n_ptr, n_host, work, rays, out, max_grid, bins);
+    return launch_t2v<SRC, 9, true, true>(env, sc, ps, tq, n_ptr, n_host, work, rays, out, max_grid, bins);
   }
 #define PT_T2_CASE(B, L)                                                                           \
   if (minb == B && l256 == L)                                                                      \
