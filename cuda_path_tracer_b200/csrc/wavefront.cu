@@ -291,7 +291,13 @@ PT_D void spheres_closest(const DevScene& sc, int root, uint32_t lo, uint32_t hi
   }
 }
 
+// Length of the stack-free walk below.  Re-measured with the final traversal kernel (2 / 4 / 6 / 8
+// nodes): bunny 11 213 / 11 204 / 11 320 / 11 252 Mrays/s, 150 k triangles 5 295 / 5 212 / 5 204 /
+// 5 233, terrain 2 727 / 2 686 / 2 672 / 2 638 (profiles/r2_ab_prefix_walk_chain_bounds.log): a
+// shorter walk moves work from the chain kernels into traversal, which wins or loses by scene.
+#ifndef PREFIX_MAX
 #define PREFIX_MAX 6
+#endif
 // `hs` receives the full Intersection of the sphere named by `code` (valid when the ray is simple
 // and code != 0): a caller that shades the ray at once (chain_kernel) need not rebuild it.
 template <bool ST = false>
@@ -1332,8 +1338,16 @@ PT_D void mbar_wait(unsigned long long* bar, uint32_t parity)
   }
 }
 
+// Three CTAs of 256 threads per SM, stated: left to itself nvcc also stops at 80 registers but keeps
+// 64 B of stack instead of 48 (re-entry launches 5.30 -> 5.14 ms on the bunny, 15.5 -> 14.7 on the
+// terrain).  The kernel is latency bound, yet more warps do not pay for fewer registers: 4 CTAs
+// (64 registers) 5.89 / 25.5 ms, 5 CTAs (48) 6.84 / 29.9 ms; nor do more registers for fewer warps:
+// 2 CTAs (86 registers) 6.54 / 18.6 ms (profiles/r2_ab_chain_register_bounds.log).
+#ifndef CHAIN_MIN_BLOCKS
+#define CHAIN_MIN_BLOCKS 3
+#endif
 template <bool FIRST, int TMA, bool ST>
-__global__ void __launch_bounds__(FULL_THREADS)
+__global__ void __launch_bounds__(FULL_THREADS, CHAIN_MIN_BLOCKS)
 chain_kernel(const DevScene sc, const PathState ps, const PassParams pp, const ParkBuf in,
              const uint32_t* __restrict__ n_ptr, uint32_t n_first, const ParkBuf out,
              uint32_t* __restrict__ out_count, uint32_t max_depth,
@@ -1766,6 +1780,7 @@ static void launch_t2(const LaunchEnv& env, const DevScene& sc, const PathState&
   if (sc.qnodes != nullptr) {
     const int qb = t.trav_minb != 0 ? t.trav_minb : 9;
     if (qb >= 10) return launch_t2v<SRC, 10, true, true>(env, sc, ps, tq, n_ptr, n_host, work, rays, out, max_grid, bins);
+    if (qb <= 8) return launch_t2v<SRC, 8, true, true>(env, sc, ps, tq, n_ptr, n_host, work, rays, out, max_grid, bins);
     return launch_t2v<SRC, 9, true, true>(env, sc, ps, tq, n_ptr, n_host, work, rays, out, max_grid, bins);
   }
 #define PT_T2_CASE(B, L)                                                                           \
