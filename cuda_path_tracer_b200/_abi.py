@@ -98,6 +98,7 @@ SYMBOLS = {
     "pt_host_bvh_build": (C.c_int, [C.POINTER(pt_scene_desc), C.c_int, C.POINTER(VP), C.POINTER(pt_scene_info)]),
     "pt_host_bvh_validate": (C.c_int, [VP, C.POINTER(C.c_uint64)]),
     "pt_host_bvh_arrays": (C.c_int, [VP, C.POINTER(VP), C.POINTER(VP), C.POINTER(VP)]),
+    "pt_host_bvh_quantised": (C.c_int, [VP, C.POINTER(VP), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "pt_host_bvh_trace_stats": (C.c_int, [VP, VP, C.c_uint64, C.c_int, VP]),
     "pt_host_bvh_free": (C.c_int, [VP]),
     "pt_host_scene_check": (C.c_int, [C.POINTER(pt_scene_desc), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),

@@ -75,6 +75,17 @@ class HostBVH:
                 view(b, int(i.n_bvh8_nodes), 20, C.c_uint32, np.uint32),
                 view(t, n_tris, 12, C.c_float, np.float32))
 
+    def quantised(self):
+        """(quantised nodes [n,8] u32, grid origin [3] f32, cell size [3] f32): the 32-byte nodes the
+        traversal kernels read, as numpy copies."""
+        q = C.c_void_p()
+        org = (C.c_float * 3)()
+        cell = (C.c_float * 3)()
+        check(load_library().pt_host_bvh_quantised(self._h, C.byref(q), org, cell))
+        n = int(self.info.n_bvh_nodes)
+        arr = np.ctypeslib.as_array(C.cast(q, C.POINTER(C.c_uint32)), shape=(n, 8)).astype(np.uint32, copy=True)
+        return arr, np.array(list(org), np.float32), np.array(list(cell), np.float32)
+
     def trace_stats(self, rays8: np.ndarray, wide=False) -> dict:
         """Host walk in the device kernels' order: what the rays cost in this tree (analysis tool).
         wide: False/0 binary tree, True/1 compressed 8-wide tree, 2 a virtual 4-wide tree (every

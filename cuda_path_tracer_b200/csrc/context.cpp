@@ -580,6 +580,10 @@ int pt_scene_create(const pt_scene_desc* desc, int device, pt_scene** out)
 struct pt_host_bvh_impl {
   FlatBVH bvh;
   double build_ms = 0.0;
+  // quantised companion of bvh.nodes, made on first request (pt_host_bvh_quantised)
+  std::vector<uint32_t> qnodes;
+  float q_org[3] = {0.f, 0.f, 0.f}, q_cell[3] = {0.f, 0.f, 0.f};
+  int q_state = 0; // 0 = not tried, 1 = built, -1 = the quantiser declined
 };
 
 static int pt_host_bvh_build_impl(const pt_scene_desc* desc, int wide, pt_host_bvh** out, pt_scene_info* info)
@@ -636,6 +640,19 @@ int pt_host_bvh_arrays(const pt_host_bvh* hb, const float** nodes, const uint32_
   if (nodes8) *nodes8 = b.nodes8.data();
   if (tris) *tris = b.tris.data();
   return PT_OK;
+}
+
+int pt_host_bvh_quantised(pt_host_bvh* hb, const uint32_t** qnodes, float* org3, float* cell3)
+{
+  if (!hb || !qnodes || !org3 || !cell3) return fail(PT_ERR_INVALID, "pt_host_bvh_quantised: null argument");
+  return guarded("pt_host_bvh_quantised", [&] {
+    auto* h = reinterpret_cast<pt_host_bvh_impl*>(hb);
+    if (h->q_state == 0) h->q_state = quantise_nodes(h->bvh, h->qnodes, h->q_org, h->q_cell) ? 1 : -1;
+    if (h->q_state < 0) return fail(PT_ERR_INVALID, "the tree does not fit the 16-bit grid (degenerate or non-finite bounds)");
+    *qnodes = h->qnodes.data();
+    for (int a = 0; a < 3; ++a) org3[a] = h->q_org[a], cell3[a] = h->q_cell[a];
+    return (int)PT_OK;
+  });
 }
 
 int pt_host_bvh_trace_stats(const pt_host_bvh* hb, const float* rays8, uint64_t n_rays, int wide, uint64_t* out5)

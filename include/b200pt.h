@@ -234,6 +234,14 @@ PT_API int pt_host_bvh_build(const pt_scene_desc* desc, int wide, pt_host_bvh** 
 PT_API int pt_host_bvh_validate(const pt_host_bvh* bvh, uint64_t* violations);
 PT_API int pt_host_bvh_arrays(const pt_host_bvh* bvh, const float** nodes, const uint32_t** nodes8,
                               const float** tris);
+/* The 32-byte quantised nodes the traversal kernels read (DevScene::qnodes; pt_scene_create builds
+ * them the same way for host-built trees up to 512 MB): n_bvh_nodes x 8 words = the twelve child
+ * planes as 16-bit grid coordinates (x lo | hi << 16, y, z of child 0; x, y, z of child 1), always
+ * at least one whole cell outside the exact plane, then the two child references of the 64-byte
+ * node; a plane is org3[axis] + q * cell3[axis].  PT_ERR_INVALID when the tree's bounds are
+ * degenerate (the kernels then walk the 64-byte nodes).  Test hook: the CPU suite checks the
+ * containment and restates the device's de-quantising slab test. */
+PT_API int pt_host_bvh_quantised(pt_host_bvh* bvh, const uint32_t** qnodes, float* org3, float* cell3);
 /* Analysis tool: walks the host-built tree for n rays {o, t_min, d, t_max} in the device kernels'
  * visiting order and returns {inner-node visits, leaf visits, triangle tests, rays that hit,
  * deepest stack} in out5.  wide = 0: binary tree, 1: compressed 8-wide tree.  No image is

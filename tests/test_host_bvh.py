@@ -189,6 +189,127 @@ def test_wide_tree_with_device_arithmetic_matches_oracle(name):
     assert hits > n // 4
 
 
+# ---------------------------------------------------------------- quantised nodes
+# The 32-byte nodes traverse_kernel / finish_kernel read (DevScene::qnodes, wavefront.cu trav_init<QN>
+# / trav_inner<QN>): the reference walks exact boxes un-culled (path_tracer.cu:36-84); a conservative
+# box may only change which subtrees are skipped, never the closest hit.
+_Q_SRC = [(0, 1), (2, 3), (8, 9), (4, 5), (6, 7), (10, 11)]   # plane slots of the 64-byte node per word
+_Q_AXIS = [0, 1, 2, 0, 1, 2]
+
+
+@pytest.mark.parametrize("name", ["bunny_320", "bunny_5k", "bunny_20k", "terrain_5k", "flat_quads", "three_coincident"])
+def test_quantised_nodes_enclose_the_exact_boxes_with_a_cell_in_reserve(name):
+    hb = HostBVH(_mesh_scene(MESHES[name]()), wide=False)
+    nodes, _, _ = hb.arrays()
+    q, org, cell = hb.quantised()
+    assert q.shape == (nodes.shape[0], 8)
+    assert np.all(cell > 0)
+    # child references are the 64-byte node's, bit for bit
+    assert np.array_equal(q[:, 6:8], nodes[:, 12:14].view(np.uint32))
+    org64, cell64 = org.astype(np.float64), cell.astype(np.float64)
+    for k in range(6):
+        a = _Q_AXIS[k]
+        lo = org64[a] + (q[:, k] & 0xFFFF).astype(np.float64) * cell64[a]
+        hi = org64[a] + (q[:, k] >> 16).astype(np.float64) * cell64[a]
+        ex_lo = nodes[:, _Q_SRC[k][0]].astype(np.float64)
+        ex_hi = nodes[:, _Q_SRC[k][1]].astype(np.float64)
+        # at least one whole cell outside (the device's rounding takes half of it), at most two
+        assert np.all(ex_lo - lo >= cell64[a] * (1 - 1e-9)), k
+        assert np.all(hi - ex_hi >= cell64[a] * (1 - 1e-9)), k
+        assert np.all(ex_lo - lo <= cell64[a] * (2 + 1e-9)), k
+        assert np.all(hi - ex_hi <= cell64[a] * (2 + 1e-9)), k
+
+
+def _q_float(h16):
+    return np.array([0x4B000000 | int(h16)], np.uint32).view(f32)[0]
+
+
+def _trace_quantised(q, org, cell, tris, o, d, tmin, tmax):
+    """Closest hit through the quantised nodes with the device's arithmetic (trav_init<QN>,
+    trav_inner<QN>, trav_leaf): near/far planes picked by the direction signs, nearer child first."""
+    o, d = o.astype(f32), d.astype(f32)
+    inv = np.array([_safe_inv(x) for x in d], f32)
+    A = np.array([f32(cell[a] * inv[a]) for a in range(3)], f32)
+    B = np.array([_fma(f32(8388608.0), A[a], -f32(f32(org[a] - o[a]) * inv[a])) for a in range(3)], f32)
+    near_lo = [A[a] >= 0 for a in range(3)]
+    tbest, best, visited = f32(tmax), -1, 0
+    stack, node = [], 0
+    SENT = 0x7FFFFFFF
+
+    def child(w, base):
+        cmin, cmax = f32(tmin), tbest
+        for a in range(3):
+            lo, hi = _q_float(w[base + a] & 0xFFFF), _q_float(w[base + a] >> 16)
+            tn = _fma(lo if near_lo[a] else hi, A[a], -B[a])
+            tf = _fma(hi if near_lo[a] else lo, A[a], -B[a])
+            cmin, cmax = max(cmin, tn), min(cmax, tf)
+        return bool(f32(cmax * f32(1.0000004)) >= cmin), cmin
+
+    while node != SENT:
+        if node >= 0:
+            w = q[node]
+            visited += 1
+            t0, m0 = child(w, 0)
+            t1, m1 = child(w, 3)
+            c0, c1 = int(np.int32(w[6])), int(np.int32(w[7]))
+            if not t0 and not t1:
+                node = stack.pop() if stack else SENT
+            else:
+                swap = t1 and (not t0 or m1 < m0)
+                node = c1 if swap else c0
+                if t0 and t1:
+                    stack.append(c0 if swap else c1)
+        else:
+            code = ~node & 0xFFFFFFFF
+            first, count = code >> 3, (code & 7) + 1
+            for k in range(count):
+                t = _tri_test(tris, first + k, o, d, f32(tmin), tbest)
+                if t is not None:
+                    tbest, best = t, first + k
+            node = stack.pop() if stack else SENT
+    return tbest, best, visited
+
+
+@pytest.mark.parametrize("name", ["bunny_5k", "terrain_5k", "flat_quads"])
+def test_quantised_nodes_with_device_arithmetic_match_oracle(name):
+    mesh = MESHES[name]()
+    xf = pt.compose(pt.translate((0.3, -0.2, -3.0)), pt.rotate(0.7, (0.2, 1.0, 0.1)), pt.scale((1.3, 0.9, 1.1)))
+    sd = _mesh_scene(mesh, xf)
+    hb = HostBVH(sd, wide=False)
+    _, _, tris = hb.arrays()
+    q, org, cell = hb.quantised()
+    rng = np.random.default_rng(11)
+    n = 160
+    lo = tris[:, 0:3].min(axis=0) - 0.5
+    hi = tris[:, 0:3].max(axis=0) + 0.5
+    cen, rad = 0.5 * (lo + hi), 0.5 * np.linalg.norm(hi - lo)
+    dirs = rng.normal(size=(n, 3))
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    # origins from inside the bounds out to 40 radii away (the far ones exercise the part of the
+    # error that grows with the distance and is covered by the widened comparison)
+    org_r = cen + dirs * rad * np.concatenate([rng.uniform(0.05, 2.0, size=(n - 24, 1)), rng.uniform(10.0, 40.0, size=(24, 1))])
+    tgt = cen + rng.uniform(-0.5, 0.5, size=(n, 3)) * (hi - lo)
+    d = tgt - org_r
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d[:12] = np.eye(3)[rng.integers(0, 3, 12)] * rng.choice([-1.0, 1.0], size=(12, 1))
+    rays = np.concatenate([org_r, np.full((n, 1), 1e-4), d, np.full((n, 1), 3.4e38)], axis=1).astype(np.float32)
+    ref = load_oracle().scene(sd).trace_batch(rays)
+    hits = 0
+    coord = float(np.abs(tris[:, 0:3]).max())
+    for i in range(n):
+        t, slot, _ = _trace_quantised(q, org, cell, tris, rays[i, 0:3], rays[i, 4:7], rays[i, 3], rays[i, 7])
+        if ref["t"][i] < 0:
+            assert slot < 0, (i, t, slot)
+            continue
+        hits += 1
+        assert slot >= 0, (i, ref["t"][i])
+        assert abs(t - ref["t"][i]) <= max(1e-5 * abs(ref["t"][i]), 4e-7 * coord * max(1.0, np.linalg.norm(rays[i, 0:3] - cen) / rad)), (i, t, ref["t"][i])
+        prim = int(tris[slot, 3:4].view(np.uint32)[0])
+        if prim != ref["prim"][i]:      # ties between coincident/adjacent triangles only
+            assert abs(t - ref["t"][i]) <= 1e-6 * abs(ref["t"][i])
+    assert hits > n // 4
+
+
 @pytest.mark.parametrize("name", ["bunny_320", "bunny_5k", "bunny_20k", "terrain_5k", "flat_quads", "three_coincident"])
 def test_lbvh_restatement_is_structurally_valid(name):
     """The host restatement of the device LBVH builder (lbvh.h shared with lbvh.cu): every triangle
