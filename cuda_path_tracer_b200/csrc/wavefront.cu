@@ -729,6 +729,7 @@ enum { SRC_QUEUE = 1, SRC_BATCH = 2 };
 // MINB: resident CTAs per SM the register allocation is bounded for (8 -> 64 registers, 50 % of
 // the warp slots; 10 -> 48; 12 -> 40); L256: node fetch with two 256-bit loads.  Both are
 // run-time choices between instantiations (PT_TRAV="minb,l256"), measured in profiles/README.md.
+// QN: the inner nodes are read in their 32-byte quantised form (DevScene::qnodes; trav_inner).
 template <int SRC, int MINB, bool L256, bool ST, bool QN = false>
 __global__ void __launch_bounds__(EXT_THREADS, MINB)
 traverse_kernel(const DevScene sc, const PathState ps, const uint32_t* __restrict__ tq,
@@ -1758,8 +1759,9 @@ static void launch_t2(const LaunchEnv& env, const DevScene& sc, const PathState&
   }
   int minb = t.trav_minb, l256 = t.trav_l256;
   if (minb == 0) {
-    // Measured (profiles/README.md, round 2): a tree that lives in L1/L2 is bound by L1 data-pipe
-    // wavefronts and likes the 256-bit node fetch (bunny: traverse -3 %); a scene far beyond the
+    // The exact-node instantiations (trees the quantiser is not used for).  Measured
+    // (profiles/README.md, round 2): a tree that lives in L1/L2 likes the 256-bit node fetch — fewer
+    // instructions (bunny: traverse -3 %); a scene far beyond the
     // 126 MB L2 likes more resident warps to hide its misses: 10 CTAs per SM at 48 registers
     // (10 M-triangle terrain, two lanes: 2 476 -> 2 596 Mrays/s; 12 CTAs at 40 registers spill
     // into the same L1 data pipe and only matched it in one-lane passes); in between (2.6 M
