@@ -347,6 +347,10 @@ def bench_render(name, steps, warmup, D: Dist, with_clocks=True):
                   "wavefront_bytes_per_ray": 164,
                   "wavefront_frac": rays_all / D.world * 164 / (ms * 1e-3) * 1e-9 / hbm,
                   "peak_source": peak_src,
+                  # HBM is the contract's denominator, not this kernel's limiter (ncu capture in
+                  # profiles/r2_traverse_bunny_final_ncu_full_summary.csv)
+                  "limiter": "instruction issue / ALU pipe on L2-resident scenes (ncu: issue-active 64-75 %, ALU "
+                             "pipe 54-65 %, DRAM 56 B per ray); memory latency on scenes far beyond the L2",
                   "per_rank": "rank 0's launches" if D.multi else None},
         kernel_ms={"raygen_classify": st.ms_raygen_extend0 / k_steps, "traverse": st.ms_extend / k_steps,
                    "shade_classify_compact": st.ms_shade / k_steps, "accumulate": st.ms_accumulate / k_steps,
